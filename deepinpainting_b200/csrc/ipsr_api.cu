@@ -1,0 +1,228 @@
+// Error plumbing, workspace carving and the fused forward of libipsr_sm100.so.
+//
+// ipsr_shift_forward is the C-ABI counterpart of models/IPSRFunction.py:13-140 for
+// shift_sz = stride = 1 (the only configuration the reference can execute): it
+// enqueues (a) extract+normalise, (b,c) correlation + arg-max (+ exact recheck), (d) blend scan and
+// paste, and the bookkeeping the backward needs -- on one stream, without host synchronisation or
+// allocation, so the whole layer is CUDA-graph capturable.
+#include <stdarg.h>
+
+#include "ipsr_common.cuh"
+
+namespace ipsr {
+
+static thread_local char g_err[512] = "no error";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return IPSR_ERR_CUDA;
+  }
+  return IPSR_OK;
+}
+
+constexpr int kMaxPsplit = 8;
+constexpr float kDefaultTolRel = 5e-5f;   // x ||R[q]||: > 2x the worst-case error of the 3 x bf16 split
+constexpr float kDefaultTolAbs = 1e-12f;
+
+struct Workspace {
+  size_t total = 0;
+  size_t inv_norm, rnorm, counters /* nonfinite[B] + nrecheck[B] */, xt, r_masked, staged, vmask, y, packed, list;
+  size_t x_tiles, r_tiles, part_best, part_idx, part_second;
+  bool tensor = false;
+};
+
+static size_t take(size_t& cur, size_t bytes) {
+  const size_t at = cur;
+  cur += (bytes + 255) & ~(size_t)255;
+  return at;
+}
+
+static int resolve_mode(int mode, int C, int N) {
+  if (mode == IPSR_MODE_AUTO) return ipsr_tensor_path_supported(C, N) ? IPSR_MODE_TENSOR : IPSR_MODE_EXACT;
+  return mode;
+}
+
+static Workspace carve(int B, int C, int N, int M, int mode) {
+  Workspace w;
+  size_t cur = 0;
+  const size_t BN = (size_t)B * N, BM = (size_t)B * (M > 0 ? M : 1);
+  w.inv_norm = take(cur, BN * 4);
+  w.rnorm = take(cur, BN * 4);
+  w.counters = take(cur, (size_t)2 * B * 4);
+  w.xt = take(cur, BN * C * 4);
+  w.r_masked = take(cur, BM * C * 4);
+  w.staged = take(cur, BM * 2 * C * 4);
+  w.vmask = take(cur, BM * 4);
+  w.y = take(cur, BM * C * 4);
+  w.packed = take(cur, BN * 8);
+  w.list = take(cur, BN * 4);
+  w.tensor = (resolve_mode(mode, C, N) == IPSR_MODE_TENSOR);
+  if (w.tensor) {
+    w.x_tiles = take(cur, BN * C * 4);
+    w.r_tiles = take(cur, BN * C * 4);
+    w.part_best = take(cur, (size_t)kMaxPsplit * BN * 4);
+    w.part_idx = take(cur, (size_t)kMaxPsplit * BN * 4);
+    w.part_second = take(cur, (size_t)kMaxPsplit * BN * 4);
+  } else {
+    w.x_tiles = w.r_tiles = w.part_best = w.part_idx = w.part_second = 0;
+  }
+  w.total = cur;
+  return w;
+}
+
+template <typename T>
+static T* at(const ipsr_fwd_args* a, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(a->workspace) + off);
+}
+
+static int validate(const ipsr_fwd_args* a, Workspace* w, int* mode_out) {
+  IPSR_REQUIRE(a != nullptr, IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: args is null");
+  IPSR_REQUIRE(a->x && a->ref && a->flag && a->rank && a->out && a->ind, IPSR_ERR_INVALID_ARG,
+               "ipsr_shift_forward: null tensor pointer");
+  IPSR_REQUIRE(a->B > 0 && a->C > 0 && a->H > 0 && a->W > 0 && a->M >= 0 && a->M <= a->H * a->W, IPSR_ERR_INVALID_ARG,
+               "ipsr_shift_forward: bad dims B=%d C=%d H=%d W=%d M=%d", a->B, a->C, a->H, a->W, a->M);
+  IPSR_REQUIRE(a->M == 0 || (a->mask_idx && a->wn && a->wo), IPSR_ERR_INVALID_ARG,
+               "ipsr_shift_forward: mask_idx / wn / wo required when M > 0");
+  const int N = a->H * a->W;
+  IPSR_REQUIRE(a->C % 32 == 0, IPSR_ERR_UNSUPPORTED, "ipsr_shift_forward: C=%d must be a multiple of 32", a->C);
+  const int mode = resolve_mode(a->mode, a->C, N);
+  IPSR_REQUIRE(mode == IPSR_MODE_TENSOR || mode == IPSR_MODE_EXACT, IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: bad mode %d", a->mode);
+  IPSR_REQUIRE(mode != IPSR_MODE_TENSOR || ipsr_tensor_path_supported(a->C, N), IPSR_ERR_UNSUPPORTED,
+               "ipsr_shift_forward: tensor mode needs C %% 64 == 0 and N %% 128 == 0 (C=%d N=%d)", a->C, N);
+  const int cb = a->col_begin, ce = (a->col_end > 0 ? a->col_end : N);
+  IPSR_REQUIRE(cb >= 0 && cb < ce && ce <= N, IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: bad column shard [%d,%d)", cb, ce);
+  IPSR_REQUIRE(mode != IPSR_MODE_TENSOR || (cb % 128 == 0 && ce % 128 == 0), IPSR_ERR_UNSUPPORTED,
+               "ipsr_shift_forward: tensor mode needs 128-aligned column shards, got [%d,%d)", cb, ce);
+  if (a->need_grad) {
+    IPSR_REQUIRE(a->route_ptr && a->route_q, IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: need_grad without route buffers");
+    IPSR_REQUIRE(a->M <= 1 || (a->exc_start && a->exc_cnt && a->exc_l && a->exc_w && a->exc_total && a->exc_cap > 0),
+                 IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: need_grad without exception buffers");
+  }
+  *w = carve(a->B, a->C, N, a->M, mode);
+  IPSR_REQUIRE(a->workspace && a->workspace_bytes >= w->total, IPSR_ERR_WORKSPACE,
+               "ipsr_shift_forward: workspace %zu B < required %zu B", a->workspace_bytes, w->total);
+  IPSR_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, IPSR_ERR_WORKSPACE,
+               "ipsr_shift_forward: workspace must be 256-byte aligned");
+  *mode_out = mode;
+  return IPSR_OK;
+}
+
+// (d) and the backward bookkeeping; ind[b,q] must be final.
+static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void* stream) {
+  const int B = a->B, C = a->C, N = a->H * a->W, M = a->M;
+  if (M > 0) {
+    IPSR_FORWARD(ipsr_blend_stage(at<float>(a, w.xt), at<float>(a, w.r_masked), at<float>(a, w.inv_norm), a->ind,
+                                  a->mask_idx, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask), stream));
+    IPSR_FORWARD(ipsr_blend_scan(at<float>(a, w.staged), at<float>(a, w.vmask), B, C, M, at<float>(a, w.y), a->wn, a->wo,
+                                 stream));
+  }
+  if (a->need_grad) {
+    IPSR_FORWARD(ipsr_build_routes(a->ind, a->flag, a->mask_idx, B, N, M, a->route_ptr, a->route_q, stream));
+    if (M > 1)
+      IPSR_FORWARD(ipsr_build_exceptions(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l,
+                                         a->exc_w, a->exc_total, a->exc_cap, stream));
+  }
+  return ipsr_paste(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream);
+}
+
+}  // namespace ipsr
+
+extern "C" const char* ipsr_last_error_string(void) { return ipsr::g_err; }
+extern "C" int ipsr_version(void) { return 100; }
+
+extern "C" size_t ipsr_workspace_bytes(int B, int C, int H, int W, int M, int mode) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || M < 0) return 0;
+  return ipsr::carve(B, C, H * W, M, mode).total;
+}
+
+extern "C" int64_t* ipsr_workspace_packed(const ipsr_fwd_args* a) {
+  if (!a || !a->workspace) return nullptr;
+  const ipsr::Workspace w = ipsr::carve(a->B, a->C, a->H * a->W, a->M, a->mode);
+  return ipsr::at<int64_t>(a, w.packed);
+}
+
+extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
+  using namespace ipsr;
+  Workspace w;
+  int mode = 0;
+  IPSR_FORWARD(validate(a, &w, &mode));
+  const int B = a->B, C = a->C, N = a->H * a->W, M = a->M;
+  const int cb = a->col_begin, ce = (a->col_end > 0 ? a->col_end : N);
+  cudaStream_t st = as_stream(stream);
+  int32_t* nonfinite = at<int32_t>(a, w.counters);
+  int32_t* nrecheck = nonfinite + B;
+  int32_t* list = at<int32_t>(a, w.list);
+  int64_t* packed = at<int64_t>(a, w.packed);
+
+  cudaError_t e = cudaMemsetAsync(nonfinite, 0, (size_t)2 * B * sizeof(int32_t), st);
+  IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memset: %s", cudaGetErrorString(e));
+  if (a->need_grad && M > 1) {
+    e = cudaMemsetAsync(a->exc_total, 0, (size_t)B * sizeof(int32_t), st);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memset: %s", cudaGetErrorString(e));
+  }
+
+  const bool tensor = (mode == IPSR_MODE_TENSOR);
+  IPSR_FORWARD(ipsr_extract_normalize(a->x, a->ref, B, C, N, a->rank, M, at<float>(a, w.inv_norm), at<float>(a, w.rnorm),
+                                      at<float>(a, w.xt), at<float>(a, w.r_masked),
+                                      tensor ? at<void>(a, w.x_tiles) : nullptr, tensor ? at<void>(a, w.r_tiles) : nullptr,
+                                      nonfinite, stream));
+  if (tensor) {
+    int psplit = a->psplit;
+    if (psplit <= 0) {
+      const long long tiles = (long long)B * (N / kTileRows);
+      psplit = (int)((148 + tiles - 1) / tiles);
+    }
+    if (psplit > kMaxPsplit) psplit = kMaxPsplit;
+    const int max_split = (ce - cb) / 128;
+    if (psplit > max_split) psplit = max_split;
+    if (psplit < 1) psplit = 1;
+    IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, psplit,
+                                          at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
+                                          at<float>(a, w.part_second), nullptr, stream));
+    const float tol_rel = a->tol_rel >= 0.f ? a->tol_rel : kDefaultTolRel;
+    const float tol_abs = a->tol_abs >= 0.f ? a->tol_abs : kDefaultTolAbs;
+    // psplit may have been clamped again inside the launcher only when blocks < psplit; recompute identically
+    int block_n = (C <= 256) ? 128 : 256;
+    if ((ce - cb) % block_n != 0) block_n = 128;
+    const int blocks_total = (ce - cb) / block_n;
+    if (psplit > blocks_total) psplit = blocks_total;
+    IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
+                                      psplit, at<float>(a, w.rnorm), nonfinite, B, N, tol_rel, tol_abs, a->ind, list,
+                                      nrecheck, packed, stream));
+  } else {
+    IPSR_FORWARD(ipsr_select_all_rows(B, N, list, nrecheck, packed, stream));
+  }
+  IPSR_FORWARD(ipsr_correlate_argmax_fp32(a->x, a->ref, at<float>(a, w.inv_norm), B, C, N, cb, ce, list, nrecheck,
+                                          tensor ? 2 : (N + 63) / 64, packed, stream));
+  if (a->nrecheck_out) {
+    e = cudaMemcpyAsync(a->nrecheck_out, nrecheck, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memcpy: %s", cudaGetErrorString(e));
+  }
+  if (a->stop_after_corr) {
+    // bank-sharded mode: every row leaves with an exact (score, idx) key of its LOCAL winner
+    if (tensor)
+      IPSR_FORWARD(ipsr_pack_winner_scores(at<float>(a, w.xt), a->ref, at<float>(a, w.inv_norm), a->ind, B, C, N, packed, stream));
+    return IPSR_OK;
+  }
+  IPSR_FORWARD(ipsr_apply_recheck(packed, list, nrecheck, B, N, a->ind, nullptr, stream));
+  return run_blend_and_paste(a, w, stream);
+}
+
+extern "C" int ipsr_shift_forward_finish(const ipsr_fwd_args* a, void* stream) {
+  using namespace ipsr;
+  Workspace w;
+  int mode = 0;
+  IPSR_FORWARD(validate(a, &w, &mode));
+  const int B = a->B, N = a->H * a->W;
+  IPSR_FORWARD(ipsr_unpack_maxidx(at<int64_t>(a, w.packed), (int64_t)B * N, nullptr, a->ind, stream));
+  return run_blend_and_paste(a, w, stream);
+}

@@ -1,0 +1,201 @@
+// Shared device/host helpers for libipsr_sm100.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ipsr_sm100.h"
+
+namespace ipsr {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define IPSR_REQUIRE(cond, code, ...)                 \
+  do {                                                \
+    if (!(cond)) {                                    \
+      ::ipsr::set_error(__VA_ARGS__);                 \
+      return (code);                                  \
+    }                                                 \
+  } while (0)
+
+#define IPSR_FORWARD(expr)                            \
+  do {                                                \
+    int rc__ = (expr);                                \
+    if (rc__ != IPSR_OK) return rc__;                 \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---------------------------------------------------------------------------------------------
+// tile-image geometry of the bf16 hi/lo operands (written by prep, read by the tcgen05 GEMM)
+//   [B][KB = C/64][2 (hi, lo)][RB = N/128][128 rows x 128 bytes, 128B swizzle]
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileRows = 128;
+constexpr int kTileK = 64;                       // bf16 elements per row of a tile = 128 bytes
+constexpr int kTileBytes = kTileRows * kTileK * 2;  // 16 KiB
+
+__host__ __device__ inline size_t tile_offset_bytes(int b, int kb, int hl, int rb, int KB, int RB) {
+  return ((((size_t)b * KB + kb) * 2 + hl) * RB + rb) * (size_t)kTileBytes;
+}
+
+// byte offset of the 16-byte chunk `chunk` (0..7, 8 bf16 each) of row `r` (0..127) inside a tile
+// image: canonical UMMA K-major SWIZZLE_128B layout = Swizzle<3,4,3> on (row*128 + chunk*16).
+__host__ __device__ inline uint32_t tile_chunk_offset(int r, int chunk) {
+  return (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving (score, index) key: signed 64-bit so that ncclMax/int64 (and gloo MAX) work.
+//   high 32 bits: fp32 score as an orderable signed int (NaN canonicalised to +NaN > +inf, -0 -> +0)
+//   low  32 bits: 0xFFFFFFFF - idx  (lowest index wins ties, util/MaxCoord.py:22 = torch.max)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline long long pack_maxidx(float v, int idx) {
+  uint32_t bits;
+#ifdef __CUDA_ARCH__
+  if (v != v) bits = 0x7FC00000u;
+  else bits = __float_as_uint(v + 0.0f);
+#else
+  if (v != v) bits = 0x7FC00000u;
+  else { float t = v + 0.0f; memcpy(&bits, &t, 4); }
+#endif
+  int32_t key = (bits & 0x80000000u) ? (int32_t)(bits ^ 0x7FFFFFFFu) : (int32_t)bits;
+  return (long long)(((unsigned long long)(uint32_t)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx));
+}
+
+__host__ __device__ inline void unpack_maxidx(long long packed, float* v, int* idx) {
+  uint32_t hi = (uint32_t)((unsigned long long)packed >> 32);
+  uint32_t lo = (uint32_t)((unsigned long long)packed & 0xFFFFFFFFull);
+  uint32_t bits = (hi & 0x80000000u) ? (hi ^ 0x7FFFFFFFu) : hi;
+#ifdef __CUDA_ARCH__
+  *v = __uint_as_float(bits);
+#else
+  memcpy(v, &bits, 4);
+#endif
+  *idx = (int)(0xFFFFFFFFu - lo);
+}
+
+constexpr long long kPackedIdentity = (long long)0x8000000000000000ull;  // INT64_MIN
+
+// ---------------------------------------------------------------------------------------------
+// small device utilities
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// float -> int64 store of the reference (models/IPSRFunction.py:36,134), returned as the float
+// the backward multiplies with: truncation toward zero; NaN / inf / |v| >= 2^63 -> INT64_MIN.
+__device__ __forceinline__ float trunc_as_reference(float e) {
+  if (!(fabsf(e) < 9.2233720368547758e18f)) return -9.2233720368547758e18f;
+  return truncf(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy / tcgen05 PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Bounded wait: a protocol bug must end in a trap (reported as a CUDA error), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s
+  }
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor of a K-major, 128B-swizzled operand whose 8-row groups are
+// 1024 bytes apart (dense tile image): start address, LBO = 16 B (ignored for swizzled K-major),
+// SBO = 1024 B, descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__host__ __device__ inline uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// tcgen05 instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M x N tile.
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+}  // namespace ipsr

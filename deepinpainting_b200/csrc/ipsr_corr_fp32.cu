@@ -1,0 +1,250 @@
+// Exact fp32 correlation + arg-max (the recheck path of the tensor mode and the whole of
+// IPSR_MODE_EXACT), (max, idx) key packing for the bank-sharded exchange, and MaxCoord on a
+// materialised score tensor.
+//
+// Replaces models/IPSRFunction.py:59 (conv_enc(ref): S[q,p] = <R[q], Xn[p]>) followed by
+// util/MaxCoord.py:22 (torch.max over the bank axis) without writing S.
+#include "ipsr_common.cuh"
+
+namespace ipsr {
+
+constexpr int kFpTile = 64;     // rows x cols per CTA tile
+constexpr int kFpKc = 16;       // channels per shared-memory slab
+constexpr int kFpThreads = 256;
+
+// grid = (column tiles, row_ctas, B).  A CTA walks the row list of its image in chunks of 64 rows
+// and, for each chunk, computes the 64 x 64 scores against its column tile with register-tiled
+// FFMA (4 x 4 per thread, channels in ascending order), then folds them into packed[b,q] with
+// one 64-bit atomicMax per (row, CTA).
+__global__ void __launch_bounds__(kFpThreads)
+corr_fp32_kernel(const float* __restrict__ x, const float* __restrict__ ref, const float* __restrict__ inv_norm,
+                 int C, int N, int col_begin, int col_end,
+                 const int* __restrict__ list, const int* __restrict__ nlist, long long* __restrict__ packed) {
+  __shared__ __align__(16) float Rs[kFpKc][kFpTile];
+  __shared__ __align__(16) float Xs[kFpKc][kFpTile];
+  __shared__ int rows[kFpTile];
+  __shared__ float invs[kFpTile];
+
+  const int b = blockIdx.z;
+  const int nrows = min(nlist[b], N);
+  const int col0 = col_begin + blockIdx.x * kFpTile;
+  const float* xb = x + (size_t)b * C * N;
+  const float* rb = ref + (size_t)b * C * N;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  if (threadIdx.x < kFpTile) {
+    const int p = col0 + threadIdx.x;
+    invs[threadIdx.x] = (p < col_end) ? inv_norm[(size_t)b * N + p] : 0.f;
+  }
+
+  for (int rc = blockIdx.y; rc * kFpTile < nrows; rc += gridDim.y) {
+    __syncthreads();
+    if (threadIdx.x < kFpTile) {
+      const int i = rc * kFpTile + threadIdx.x;
+      rows[threadIdx.x] = (i < nrows) ? list[(size_t)b * N + i] : -1;
+    }
+    __syncthreads();
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int c0 = 0; c0 < C; c0 += kFpKc) {
+      // 16 x 64 slabs: 1024 elements each, 4 per thread
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int id = threadIdx.x + e * kFpThreads;
+        const int kk = id >> 6, jj = id & 63;
+        const int c = c0 + kk;
+        const int q = rows[jj];
+        const int p = col0 + jj;
+        Rs[kk][jj] = (c < C && q >= 0) ? __ldg(rb + (size_t)c * N + q) : 0.f;
+        // Xn = fl(X * inv_norm): the reference normalises the patch first (NPS:40), then correlates
+        Xs[kk][jj] = (c < C && p < col_end) ? __fmul_rn(__ldg(xb + (size_t)c * N + p), invs[jj]) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kFpKc; ++kk) {
+        const float4 rv = *reinterpret_cast<const float4*>(&Rs[kk][ty * 4]);
+        const float4 xv = *reinterpret_cast<const float4*>(&Xs[kk][tx * 4]);
+        const float r4[4] = {rv.x, rv.y, rv.z, rv.w};
+        const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(r4[i], x4[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+
+    // per row: best of this thread's 4 columns, then across the 16 threads sharing the row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      long long key = kPackedIdentity;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = col0 + tx * 4 + j;
+        if (p < col_end) {
+          const long long k2 = pack_maxidx(acc[i][j], p);
+          key = k2 > key ? k2 : key;
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      const int q = rows[ty * 4 + i];
+      if (tx == 0 && q >= 0 && key != kPackedIdentity) atomicMax(packed + (size_t)b * N + q, key);
+    }
+  }
+}
+
+__global__ void select_all_kernel(int N, int* __restrict__ list, int* __restrict__ nlist, long long* __restrict__ packed) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < N) {
+    list[(size_t)b * N + q] = q;
+    packed[(size_t)b * N + q] = kPackedIdentity;
+  }
+  if (q == 0) nlist[b] = N;
+}
+
+__global__ void apply_recheck_kernel(const long long* __restrict__ packed, const int* __restrict__ list,
+                                     const int* __restrict__ nlist, int N, int* __restrict__ ind, float* __restrict__ vmax) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= min(nlist[b], N)) return;
+  const int q = list[(size_t)b * N + i];
+  float v;
+  int idx;
+  unpack_maxidx(packed[(size_t)b * N + q], &v, &idx);
+  ind[(size_t)b * N + q] = idx;
+  if (vmax) vmax[(size_t)b * N + q] = v;
+}
+
+// one warp per (b, q): exact score of the already chosen winner, as an exchange key.
+__global__ void __launch_bounds__(256)
+pack_winner_kernel(const float* __restrict__ xt, const float* __restrict__ ref, const float* __restrict__ inv_norm,
+                   const int* __restrict__ ind, int C, int N, long long* __restrict__ packed) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= N) return;
+  long long* slot = packed + (size_t)b * N + q;
+  if (*slot != kPackedIdentity) return;
+  const int p = ind[(size_t)b * N + q];
+  const float inv = inv_norm[(size_t)b * N + p];
+  const float* xr = xt + ((size_t)b * N + p) * C;
+  const float* rr = ref + (size_t)b * C * N + q;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(rr + (size_t)c * N), __fmul_rn(__ldg(xr + c), inv), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) *slot = pack_maxidx(acc, p);
+}
+
+__global__ void pack_kernel(const float* __restrict__ v, const int* __restrict__ idx, long long n, long long* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = pack_maxidx(v[i], idx[i]);
+}
+__global__ void unpack_kernel(const long long* __restrict__ in, long long n, float* __restrict__ v, int* __restrict__ idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float vv;
+  int ii;
+  unpack_maxidx(in[i], &vv, &ii);
+  if (v) v[i] = vv;
+  if (idx) idx[i] = ii;
+}
+
+// MaxCoord on a materialised [P, L] score tensor: thread per location, coalesced over l.
+__global__ void maxcoord_kernel(const float* __restrict__ s, int P, int L, long long* __restrict__ ind, float* __restrict__ vmax) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  long long key = kPackedIdentity;
+  for (int p = 0; p < P; ++p) {
+    const long long k2 = pack_maxidx(__ldg(s + (size_t)p * L + l), p);
+    key = k2 > key ? k2 : key;
+  }
+  float v;
+  int idx;
+  unpack_maxidx(key, &v, &idx);
+  // the key canonicalises -0 -> +0 and NaN payloads; report the stored element itself
+  ind[l] = idx;
+  vmax[l] = s[(size_t)idx * L + l];
+}
+
+}  // namespace ipsr
+
+extern "C" int ipsr_select_all_rows(int B, int N, int32_t* recheck_list, int32_t* nrecheck, int64_t* packed, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(recheck_list && nrecheck && packed && B > 0 && N > 0, IPSR_ERR_INVALID_ARG, "ipsr_select_all_rows: bad arguments");
+  select_all_kernel<<<dim3((N + 255) / 256, B), 256, 0, as_stream(stream)>>>(N, recheck_list, nrecheck,
+                                                                             reinterpret_cast<long long*>(packed));
+  return check_launch("ipsr_select_all_rows");
+}
+
+extern "C" int ipsr_correlate_argmax_fp32(const float* x, const float* ref, const float* inv_norm,
+                                          int B, int C, int N, int col_begin, int col_end,
+                                          const int32_t* recheck_list, const int32_t* nrecheck, int row_ctas,
+                                          int64_t* packed, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(x && ref && inv_norm && recheck_list && nrecheck && packed, IPSR_ERR_INVALID_ARG,
+               "ipsr_correlate_argmax_fp32: null pointer");
+  IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && col_begin >= 0 && col_end <= N && col_begin < col_end, IPSR_ERR_INVALID_ARG,
+               "ipsr_correlate_argmax_fp32: bad dims B=%d C=%d N=%d cols=[%d,%d)", B, C, N, col_begin, col_end);
+  IPSR_REQUIRE(B <= 65535, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_fp32: B=%d > 65535", B);
+  const int max_ctas = (N + kFpTile - 1) / kFpTile;
+  if (row_ctas < 1) row_ctas = 1;
+  if (row_ctas > max_ctas) row_ctas = max_ctas;
+  dim3 grid((col_end - col_begin + kFpTile - 1) / kFpTile, row_ctas, B);
+  corr_fp32_kernel<<<grid, kFpThreads, 0, as_stream(stream)>>>(x, ref, inv_norm, C, N, col_begin, col_end,
+                                                                recheck_list, nrecheck,
+                                                                reinterpret_cast<long long*>(packed));
+  return check_launch("ipsr_correlate_argmax_fp32");
+}
+
+extern "C" int ipsr_apply_recheck(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck,
+                                  int B, int N, int32_t* ind, float* vmax, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(packed && recheck_list && nrecheck && ind && B > 0 && N > 0, IPSR_ERR_INVALID_ARG,
+               "ipsr_apply_recheck: bad arguments");
+  apply_recheck_kernel<<<dim3((N + 255) / 256, B), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const long long*>(packed), recheck_list, nrecheck, N, ind, vmax);
+  return check_launch("ipsr_apply_recheck");
+}
+
+extern "C" int ipsr_pack_winner_scores(const float* xt, const float* ref, const float* inv_norm, const int32_t* ind,
+                                       int B, int C, int N, int64_t* packed, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(xt && ref && inv_norm && ind && packed && B > 0 && C > 0 && N > 0, IPSR_ERR_INVALID_ARG,
+               "ipsr_pack_winner_scores: bad arguments");
+  pack_winner_kernel<<<dim3((N + 7) / 8, B), 256, 0, as_stream(stream)>>>(xt, ref, inv_norm, ind, C, N,
+                                                                          reinterpret_cast<long long*>(packed));
+  return check_launch("ipsr_pack_winner_scores");
+}
+
+extern "C" int ipsr_pack_maxidx(const float* v, const int32_t* idx, int64_t n, int64_t* packed, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(v && idx && packed && n >= 0, IPSR_ERR_INVALID_ARG, "ipsr_pack_maxidx: bad arguments");
+  if (n == 0) return IPSR_OK;
+  pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(v, idx, n, reinterpret_cast<long long*>(packed));
+  return check_launch("ipsr_pack_maxidx");
+}
+
+extern "C" int ipsr_unpack_maxidx(const int64_t* packed, int64_t n, float* v, int32_t* idx, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(packed && n >= 0, IPSR_ERR_INVALID_ARG, "ipsr_unpack_maxidx: bad arguments");
+  if (n == 0) return IPSR_OK;
+  unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(packed), n, v, idx);
+  return check_launch("ipsr_unpack_maxidx");
+}
+
+extern "C" int ipsr_maxcoord(const float* s, int P, int L, int64_t* ind_i64, float* vmax, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(s && ind_i64 && vmax && P > 0 && L > 0, IPSR_ERR_INVALID_ARG, "ipsr_maxcoord: bad arguments");
+  maxcoord_kernel<<<(L + 127) / 128, 128, 0, as_stream(stream)>>>(s, P, L, reinterpret_cast<long long*>(ind_i64), vmax);
+  return check_launch("ipsr_maxcoord");
+}

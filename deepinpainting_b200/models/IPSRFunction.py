@@ -1,0 +1,43 @@
+"""``IPSRFunction`` -- the shift operator as a torch.autograd.Function with the reference's exact
+call signature (models/IPSRFunction.py:10-178), executed by libipsr_sm100.so.
+
+    IPSRFunction.apply(input, mask, ref, shift_sz, stride, triple_w, flag, nonmask_point_idx,
+                       mask_point_idx, flatten_offsets, sp_x, sp_y) -> output
+
+Semantics: per image, every position q is matched against the bank of ALL
+L2-normalised 1x1 patches of ``input`` by correlating ``ref.relu4_3`` with it; unmasked positions
+receive their best match, masked positions (``flag``) the sequentially blended patch; the backward
+routes gradients through the truncated attention exactly as the reference's LongTensor store does.
+"""
+import torch
+
+from .. import shift_ops
+
+
+class IPSRFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, input, mask, ref, shift_sz, stride, triple_w, flag, nonmask_point_idx, mask_point_idx,
+                flatten_offsets, sp_x, sp_y):
+        assert input.dim() == 4, "Input Dim has to be 4"
+        assert mask.dim() == 2, "Mask dimension must be 2"
+        if shift_sz != 1 or stride != 1:
+            # the reference itself cannot execute these (IPSRFunction.py:133-134 shape errors)
+            raise NotImplementedError("IPSRFunction: only shift_sz = stride = 1 is defined by the reference")
+        ctx.triple_w = triple_w
+        ctx.flag = flag
+        ctx.flatten_offsets = flatten_offsets
+        ctx.bz, c_real, ctx.h, ctx.w = input.size()
+        # sp_x, sp_y, nonmask_point_idx, flatten_offsets and the 2-D mask are accepted and unused,
+        # as in the reference; mask_point_idx is implied by flag.
+        mi = shift_ops.lookup_mask_index(flag, input.device)
+        need_grad = bool(ctx.needs_input_grad[0])
+        output, saved = shift_ops.shift_forward(input.detach(), ref.relu4_3.detach(), mi, need_grad=need_grad)
+        ctx.saved_shift = saved
+        ctx.ind_lst = saved.ind          # [B, N] int32 arg-max indices (the reference keeps A as int64 [B,N,H,W])
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad_input = shift_ops.shift_backward(grad_output, ctx.saved_shift, ctx.triple_w)
+        return grad_input, None, None, None, None, None, None, None, None, None, None, None

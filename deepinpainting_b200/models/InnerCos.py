@@ -1,0 +1,68 @@
+"""``InnerCos`` -- identity layer that records a masked consistency loss, with the reference's
+interface (models/InnerCos.py:5-53).  loss = crit(in_data * mask * strength, target) is one fused
+kernel (``innercos_loss_fwd``) and stays differentiable w.r.t. in_data (``innercos_loss_bwd``).
+"""
+import torch
+import torch.nn as nn
+
+from .. import shift_ops
+from ..util import util
+
+
+class _InnerCosLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in_data, mask, target, strength, crit, c_limit):
+        ctx.save_for_backward(in_data, mask, target)
+        ctx.strength, ctx.crit, ctx.c_limit = strength, crit, c_limit
+        return shift_ops.innercos_loss(in_data.detach(), mask, target.detach(), strength, crit, c_limit)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        in_data, mask, target = ctx.saved_tensors
+        gx = shift_ops.innercos_loss_grad(in_data, mask, target, grad_loss.contiguous(), ctx.strength, ctx.crit, ctx.c_limit)
+        return gx, None, None, None, None, None
+
+
+class InnerCos(nn.Module):
+    def __init__(self, crit='MSE', strength=1, skip=0):
+        super(InnerCos, self).__init__()
+        self.crit = crit
+        self.strength = strength
+        self.target = None
+        self.skip = skip
+        self._c_limit = None
+
+    def set_mask(self, mask_global, opt):
+        mask = util.cal_feat_mask(mask_global, 3, opt.threshold)
+        self.mask = mask.squeeze().float()
+
+    def set_target(self, targetIn):
+        self.target = targetIn
+
+    def get_target(self):
+        return self.target
+
+    def forward(self, in_data):
+        if not self.skip:
+            self.bs = in_data.size(0)
+            self.c = in_data.size(1) if self._c_limit is None else min(self._c_limit, in_data.size(1))
+            self.former = in_data
+            mask = self.mask if self.mask.device == in_data.device else self.mask.to(in_data.device)
+            self.loss = _InnerCosLoss.apply(in_data, mask, self.target, float(self.strength), self.crit, self._c_limit)
+            self.output = in_data
+        else:
+            self.loss = 0
+            self.output = in_data
+        return self.output
+
+    def backward(self, retain_graph=True):
+        if not self.skip:
+            self.loss.backward(retain_graph=retain_graph)
+        return self.loss
+
+    def __repr__(self):
+        # the reference prints 'True' when the layer is NOT skipped (InnerCos.py:50); kept as is
+        skip_str = 'True' if not self.skip else 'False'
+        return self.__class__.__name__ + '(' \
+            + 'skip: ' + skip_str \
+            + ' ,strength: ' + str(self.strength) + ')'

@@ -1,0 +1,309 @@
+"""Thin tensor-level wrappers over the C ABI (``include/ipsr_sm100.h``).
+
+PyTorch is used for device memory, streams and autograd plumbing only; every computation is a
+kernel of libipsr_sm100.so.  Nothing here falls back to torch ops or to the CPU: tensors must be
+CUDA tensors and the library must load.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+# --------------------------------------------------------------------------------------
+# configuration knobs of the drop-in (module level, like the reference's opt object)
+# --------------------------------------------------------------------------------------
+config = {
+    "correlation_mode": "auto",   # "auto" | "tensor" | "exact"
+    "tol_rel": -1.0,              # < 0: library default (5e-5 * ||R[q]||)
+    "tol_abs": -1.0,
+    "psplit": 0,                  # <= 0: auto
+    "exc_cap_factor": 8,          # exception capacity = factor * N per image
+}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: deepinpainting_b200 has no CPU path" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# mask helpers
+# --------------------------------------------------------------------------------------
+def feat_mask(mask_2d: torch.Tensor, conv_layers: int, threshold: float) -> torch.Tensor:
+    """util/util.py:68-84 on device.  mask_2d: [S_h, S_w] (bool/uint8/float, non-zero = hole)."""
+    m = _require_cuda(mask_2d, "mask")
+    if m.dim() != 2:
+        raise ValueError("feat_mask expects a 2-D mask")
+    m8 = (m != 0).to(torch.uint8).contiguous()
+    sh, sw = m8.shape
+    out = torch.empty((sh >> conv_layers, sw >> conv_layers), dtype=torch.uint8, device=m.device)
+    scratch = torch.empty((2 * max(1, (sh // 2) * (sw // 2)),), dtype=torch.int32, device=m.device)
+    _lib.call("ipsr_feat_mask", m8.data_ptr(), sh, sw, int(conv_layers), float(threshold), out.data_ptr(),
+              scratch.data_ptr(), _stream_ptr(m.device))
+    return out
+
+
+@dataclass
+class MaskIndex:
+    """Device-side flag / index vectors of one mask (util/util.py:88-147)."""
+    flag: torch.Tensor       # int32 [N]
+    mask_idx: torch.Tensor   # int32 [M]
+    rank: torch.Tensor       # int32 [N]  position inside mask_idx or -1
+    M: int
+    nH: int
+    nW: int
+
+
+def build_flags(feat: torch.Tensor, patch: int, stride: int, mask_thred: int) -> MaskIndex:
+    f = _require_cuda(feat, "mask", torch.uint8)
+    if f.dim() != 2:
+        raise AssertionError("mask has to be 2 dimenison!")
+    H, W = f.shape
+    nH, nW = (H - patch) // stride + 1, (W - patch) // stride + 1
+    P = nH * nW
+    dev = f.device
+    flag = torch.empty(P, dtype=torch.int32, device=dev)
+    midx = torch.empty(P, dtype=torch.int32, device=dev)
+    rank = torch.empty(P, dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.call("ipsr_build_flags", f.data_ptr(), H, W, int(patch), int(stride), int(mask_thred), flag.data_ptr(),
+              midx.data_ptr(), rank.data_ptr(), count.data_ptr(), _stream_ptr(dev))
+    M = int(count.item())            # one host sync per NEW mask, never per forward
+    return MaskIndex(flag=flag, mask_idx=midx[:M].contiguous(), rank=rank, M=M, nH=nH, nW=nW)
+
+
+_mask_registry = {}
+
+
+def register_mask_index(flag: torch.Tensor, mi: MaskIndex) -> None:
+    """Remember the device vectors that belong to a reference-style ``flag`` tensor (keyed by object
+    identity, dropped when the tensor dies) so IPSRFunction.apply need not rebuild them."""
+    key = id(flag)
+    _mask_registry[key] = mi
+    weakref.finalize(flag, _mask_registry.pop, key, None)
+
+
+def lookup_mask_index(flag: torch.Tensor, device) -> MaskIndex:
+    mi = _mask_registry.get(id(flag))
+    if mi is not None and mi.flag.device == torch.device(device):
+        return mi
+    mi = mask_index_from_flag(flag, device)
+    register_mask_index(flag, mi)
+    return mi
+
+
+def mask_index_from_flag(flag: torch.Tensor, device) -> MaskIndex:
+    """Device vectors from a reference-style ``flag`` vector (any integer dtype, any device):
+    the flag is its own 1 x N feature mask with 1 x 1 patches."""
+    f8 = (flag.to(device=device) != 0).to(torch.uint8).reshape(1, -1).contiguous()
+    return build_flags(f8, 1, 1, 1)
+
+
+# --------------------------------------------------------------------------------------
+# shift operator
+# --------------------------------------------------------------------------------------
+@dataclass
+class ShiftSaved:
+    B: int
+    C: int
+    H: int
+    W: int
+    M: int
+    ind: torch.Tensor
+    wn: Optional[torch.Tensor]
+    wo: Optional[torch.Tensor]
+    mask_idx: Optional[torch.Tensor]
+    route_ptr: Optional[torch.Tensor] = None
+    route_q: Optional[torch.Tensor] = None
+    exc_start: Optional[torch.Tensor] = None
+    exc_cnt: Optional[torch.Tensor] = None
+    exc_l: Optional[torch.Tensor] = None
+    exc_w: Optional[torch.Tensor] = None
+    exc_total: Optional[torch.Tensor] = None
+    exc_cap: int = 0
+    nrecheck: Optional[torch.Tensor] = None
+
+
+class _Call:
+    """Owns the argument struct and every buffer of one forward call."""
+
+    def __init__(self, x, ref, mi: MaskIndex, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics):
+        B, Cc, H, W = x.shape
+        N = H * W
+        dev = x.device
+        M = mi.M
+        if mi.flag.numel() != N:
+            raise ValueError("flag has %d entries but the feature map has %d positions" % (mi.flag.numel(), N))
+        self.out = torch.empty_like(x)
+        self.saved = ShiftSaved(B=B, C=Cc, H=H, W=W, M=M,
+                                ind=torch.empty((B, N), dtype=torch.int32, device=dev),
+                                wn=torch.empty((B, max(M, 1)), dtype=torch.float32, device=dev),
+                                wo=torch.empty((B, max(M, 1)), dtype=torch.float32, device=dev),
+                                mask_idx=mi.mask_idx)
+        s = self.saved
+        if need_grad:
+            s.route_ptr = torch.empty((B, N + 1), dtype=torch.int32, device=dev)
+            s.route_q = torch.empty((B, N), dtype=torch.int32, device=dev)
+            if M > 1:
+                s.exc_cap = max(1, int(config["exc_cap_factor"] * N))
+                s.exc_start = torch.empty((B, N), dtype=torch.int32, device=dev)
+                s.exc_cnt = torch.empty((B, N), dtype=torch.int32, device=dev)
+                s.exc_l = torch.empty((B, s.exc_cap), dtype=torch.int32, device=dev)
+                s.exc_w = torch.empty((B, s.exc_cap), dtype=torch.float32, device=dev)
+                s.exc_total = torch.empty((B,), dtype=torch.int32, device=dev)
+        if diagnostics:
+            s.nrecheck = torch.empty((B,), dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        mode_id = _lib.MODES[mode]
+        nbytes = lib.ipsr_workspace_bytes(B, Cc, H, W, M, mode_id)
+        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        a = _lib.FwdArgs()
+        a.x, a.ref = x.data_ptr(), ref.data_ptr()
+        a.flag, a.mask_idx, a.rank = mi.flag.data_ptr(), _ptr(mi.mask_idx) if M else None, mi.rank.data_ptr()
+        a.B, a.C, a.H, a.W, a.M = B, Cc, H, W, M
+        a.mode, a.need_grad = mode_id, int(bool(need_grad))
+        a.col_begin, a.col_end, a.stop_after_corr = int(col_begin), int(col_end), int(bool(stop_after_corr))
+        a.psplit, a.exc_cap = int(config["psplit"]), s.exc_cap
+        a.tol_rel, a.tol_abs = float(config["tol_rel"]), float(config["tol_abs"])
+        a.out, a.ind, a.wn, a.wo = self.out.data_ptr(), s.ind.data_ptr(), s.wn.data_ptr(), s.wo.data_ptr()
+        a.route_ptr, a.route_q = _ptr(s.route_ptr), _ptr(s.route_q)
+        a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total = (_ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l),
+                                                               _ptr(s.exc_w), _ptr(s.exc_total))
+        a.nrecheck_out = _ptr(s.nrecheck)
+        a.workspace, a.workspace_bytes = self.workspace.data_ptr(), nbytes
+        self.args = a
+        self.keep = (x, ref, mi)
+        self.device = dev
+
+    def packed_keys(self) -> torch.Tensor:
+        """[B,N] int64 view of the exchange keys inside the workspace (bank-sharded mode)."""
+        lib = _lib.load()
+        addr = lib.ipsr_workspace_packed(C.byref(self.args))
+        off = addr - self.workspace.data_ptr()
+        n = self.saved.B * self.saved.H * self.saved.W
+        return self.workspace[off:off + 8 * n].view(torch.int64).view(self.saved.B, -1)
+
+
+def shift_forward(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, need_grad: bool = True,
+                  mode: Optional[str] = None, diagnostics: bool = False):
+    """models/IPSRFunction.py:13-140 for shift_sz = stride = 1.  Returns (out, ShiftSaved)."""
+    x = _require_cuda(x, "input", torch.float32)
+    ref = _require_cuda(ref, "ref.relu4_3", torch.float32)
+    if x.dim() != 4:
+        raise AssertionError("Input Dim has to be 4")
+    if ref.shape != x.shape:
+        raise ValueError("ref.relu4_3 %s must have the shape of the input %s" % (tuple(ref.shape), tuple(x.shape)))
+    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], 0, 0, False, diagnostics)
+    _lib.call("ipsr_shift_forward", C.byref(call.args), _stream_ptr(x.device))
+    return call.out, call.saved
+
+
+def shift_forward_sharded(x, ref, mi: MaskIndex, col_begin: int, col_end: int, reduce_max, need_grad: bool = True,
+                          mode: Optional[str] = None):
+    """Bank-sharded forward: this rank correlates against bank columns [col_begin, col_end) only;
+    ``reduce_max(int64 tensor)`` performs the one exchange step (all-reduce MAX, in place) of the
+    packed (score, index) keys; everything after it runs replicated."""
+    x = _require_cuda(x, "input", torch.float32)
+    ref = _require_cuda(ref, "ref.relu4_3", torch.float32)
+    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], col_begin, col_end, True, False)
+    st = _stream_ptr(x.device)
+    _lib.call("ipsr_shift_forward", C.byref(call.args), st)
+    keys = call.packed_keys()
+    reduce_max(keys)
+    call.args.stop_after_corr = 0
+    _lib.call("ipsr_shift_forward_finish", C.byref(call.args), st)
+    return call.out, call.saved
+
+
+def shift_backward(grad_out: torch.Tensor, saved: ShiftSaved, triple_w: float) -> torch.Tensor:
+    """models/IPSRFunction.py:144-178."""
+    g = _require_cuda(grad_out, "grad_output", torch.float32)
+    s = saved
+    if s.route_ptr is None:
+        raise RuntimeError("forward was run with need_grad=False: nothing saved for backward")
+    gin = torch.empty_like(g)
+    N = s.H * s.W
+    _lib.call("ipsr_shift_bwd", g.data_ptr(), s.B, s.C, N, s.M, s.route_ptr.data_ptr(), s.route_q.data_ptr(),
+              _ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l), _ptr(s.exc_w), _ptr(s.exc_total), s.exc_cap,
+              s.ind.data_ptr(), _ptr(s.mask_idx) if s.M else None, s.wn.data_ptr(), s.wo.data_ptr(),
+              float(triple_w), gin.data_ptr(), _stream_ptr(g.device))
+    return gin
+
+
+# --------------------------------------------------------------------------------------
+# InnerCos side loss
+# --------------------------------------------------------------------------------------
+def innercos_loss(x: torch.Tensor, mask_f32: torch.Tensor, target: torch.Tensor, strength: float, crit: str,
+                  c_limit: Optional[int] = None) -> torch.Tensor:
+    x = _require_cuda(x, "in_data", torch.float32)
+    t = _require_cuda(target, "target", torch.float32)
+    m = _require_cuda(mask_f32, "mask", torch.float32)
+    B, Ct, H, W = x.shape
+    cl = Ct if c_limit is None else min(int(c_limit), Ct)
+    if tuple(t.shape) != (B, cl, H, W):
+        raise ValueError("target %s does not match the masked activations %s" % (tuple(t.shape), (B, cl, H, W)))
+    if m.numel() != H * W:
+        raise ValueError("mask has %d entries, feature map has %d positions" % (m.numel(), H * W))
+    dev = x.device
+    scratch = torch.zeros(1025, dtype=torch.float32, device=dev)      # 1024 partials + the ticket word
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    _lib.call("innercos_loss_fwd", x.data_ptr(), m.data_ptr(), t.data_ptr(), B, Ct, cl, H * W, float(strength),
+              0 if crit == "MSE" else 1, scratch.data_ptr(), scratch.data_ptr() + 4096, loss.data_ptr(), _stream_ptr(dev))
+    return loss
+
+
+def innercos_loss_grad(x, mask_f32, target, grad_loss, strength: float, crit: str, c_limit: Optional[int] = None):
+    x = _require_cuda(x, "in_data", torch.float32)
+    t = _require_cuda(target, "target", torch.float32)
+    m = _require_cuda(mask_f32, "mask", torch.float32)
+    gl = _require_cuda(grad_loss, "grad_loss", torch.float32).reshape(1)
+    B, Ct, H, W = x.shape
+    cl = Ct if c_limit is None else min(int(c_limit), Ct)
+    gx = torch.empty_like(x)
+    _lib.call("innercos_loss_bwd", x.data_ptr(), m.data_ptr(), t.data_ptr(), gl.data_ptr(), B, Ct, cl, H * W,
+              float(strength), 0 if crit == "MSE" else 1, gx.data_ptr(), _stream_ptr(x.device))
+    return gx
+
+
+# --------------------------------------------------------------------------------------
+# stand-alone pieces used by the API-compatibility modules and the tests
+# --------------------------------------------------------------------------------------
+def extract_normalize(x: torch.Tensor):
+    """util/NonparametricShift.py:36-40,59-73 for one batch: returns (xt [B,N,C], inv_norm [B,N])."""
+    x = _require_cuda(x, "target_img", torch.float32)
+    B, Cc, H, W = x.shape
+    N = H * W
+    xt = torch.empty((B, N, Cc), dtype=torch.float32, device=x.device)
+    inv = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    _lib.call("ipsr_extract_normalize", x.data_ptr(), x.data_ptr(), B, Cc, N, None, 0, inv.data_ptr(), None,
+              xt.data_ptr(), None, None, None, None, _stream_ptr(x.device))
+    return xt, inv
+
+
+def maxcoord(scores: torch.Tensor):
+    """util/MaxCoord.py:22 on a materialised [P, L] score tensor: (ind int64 [L], vmax [L])."""
+    s = _require_cuda(scores, "input", torch.float32)
+    P, L = s.shape
+    ind = torch.empty(L, dtype=torch.int64, device=s.device)
+    vmax = torch.empty(L, dtype=torch.float32, device=s.device)
+    _lib.call("ipsr_maxcoord", s.data_ptr(), P, L, ind.data_ptr(), vmax.data_ptr(), _stream_ptr(s.device))
+    return ind, vmax

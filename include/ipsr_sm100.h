@@ -1,0 +1,252 @@
+/*
+ * ipsr_sm100.h -- C ABI of libipsr_sm100.so: the B200 (sm_100a) implementation of the
+ * IPSR / CSA patch-shift attention layer of DeepInPainting.
+ *
+ * The reference has no native code and no FFI: every function below replaces a PyTorch
+ * call sequence of the reference (cited as file:line relative to the reference tree), and is
+ * bound from Python with ctypes by deepinpainting_b200/_lib.py (see INTEGRATION.md for the
+ * binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are contiguous; feature maps are NCHW fp32 exactly as the reference holds them;
+ *   - N = H*W positions in raster order (q = i*W + j), M = number of masked positions;
+ *   - every launcher enqueues on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     never allocates: scratch memory comes from the caller (ipsr_workspace_bytes);
+ *   - return value 0 = success, negative = error (ipsr_last_error_string() describes it).
+ */
+#ifndef IPSR_SM100_H_
+#define IPSR_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPSR_OK                 0
+#define IPSR_ERR_INVALID_ARG   -1
+#define IPSR_ERR_UNSUPPORTED   -2
+#define IPSR_ERR_CUDA          -3
+#define IPSR_ERR_WORKSPACE     -4
+
+/* correlation precision modes (north_star (b)) */
+#define IPSR_MODE_AUTO    0   /* tensor path when the shape allows it, else exact */
+#define IPSR_MODE_TENSOR  1   /* tcgen05 3xBF16 split GEMM + fp32 recheck of ambiguous rows */
+#define IPSR_MODE_EXACT   2   /* fp32 FFMA correlation for every row */
+
+const char* ipsr_last_error_string(void);
+int ipsr_version(void);
+/* 1 when (C, N) can run on the tcgen05 path (C % 64 == 0, N % 128 == 0, N <= 65536). */
+int ipsr_tensor_path_supported(int C, int N);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mask helpers
+ * ------------------------------------------------------------------------------------------- */
+
+/* util/util.py:68-84 cal_feat_mask: `conv_layers` chained 4x4/stride-2/pad-1 box filters
+ * (weights 1/16) then `> threshold`.  mask_u8 [S_h,S_w] (0/1) -> feat_u8 [S_h>>L, S_w>>L].
+ * scratch_i32 must hold 2 * (S_h/2)*(S_w/2) ints.  Exact integer arithmetic
+ * (S_h, S_w multiples of 2^L, L <= 5). */
+int ipsr_feat_mask(const uint8_t* mask_u8, int S_h, int S_w, int conv_layers, float threshold,
+                   uint8_t* feat_u8, int32_t* scratch_i32, void* stream);
+
+/* util/util.py:88-147 cal_mask_given_mask_thred: flag[P] = (sum of mask over the k x k window
+ * >= mask_thred); mask_idx = ascending positions with flag==1; rank[q] = position of q inside
+ * mask_idx or -1; *count = M.  P = nH*nW patch positions.  One CTA; P <= 65536. */
+int ipsr_build_flags(const uint8_t* feat_u8, int H, int W, int patch, int stride, int mask_thred,
+                     int32_t* flag_i32, int32_t* mask_idx_i32, int32_t* rank_i32, int32_t* count_i32,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a) patch extraction + L2 normalisation   (util/NonparametricShift.py:36-40,59-73)
+ *
+ * For X = x[b] viewed [N,C]:  inv_norm[b,p] = 1/(||X[p]||_2 + 1e-8);
+ *   xt        fp32 [B,N,C]   position-major copy of x (raw patches = decoder weights, NPS:54);
+ *   x_tiles   bf16 hi/lo split of Xn = X*inv_norm in the UMMA tile image layout (may be NULL);
+ * For R = ref[b] viewed [N,C]:  rnorm[b,q] = ||R[q]||_2;
+ *   r_masked  fp32 [B,M,C]   rows of R at masked positions (rank_i32 from ipsr_build_flags);
+ *   r_tiles   bf16 hi/lo split of R, same layout (may be NULL).
+ * nonfinite [B] (may be NULL): set to 1 when x[b] or ref[b] holds a NaN/inf (the tensor path
+ * then defers every row of that image to the exact path).  Must be zero on entry.
+ * Tile image layout: [B][C/64][2 (hi,lo)][N/128][128 rows x 64 bf16, 128B-swizzled K-major].
+ * ------------------------------------------------------------------------------------------- */
+int ipsr_extract_normalize(const float* x, const float* ref, int B, int C, int N,
+                           const int32_t* rank_i32, int M,
+                           float* inv_norm, float* rnorm, float* xt, float* r_masked,
+                           void* x_tiles, void* r_tiles, int32_t* nonfinite, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (b)+(c) correlation + fused row arg-max   (models/IPSRFunction.py:59, util/MaxCoord.py:22)
+ *
+ * S[q,p] = <R[q], Xn[p]> is never written to memory.
+ * ------------------------------------------------------------------------------------------- */
+
+/* tcgen05/TMEM GEMM (3 x BF16 split) over bank columns [col_begin, col_end) (multiples of 128),
+ * split into `psplit` column ranges per 128-row tile.  Writes per row and per split the best
+ * score, its (global) column index and the runner-up score: part_* are [psplit][B][N].
+ * s_dump (optional, tests only): fp32 [B][N][N] receives the full score matrix. */
+int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles, int B, int C, int N,
+                             int col_begin, int col_end, int psplit,
+                             float* part_best, int32_t* part_idx, float* part_second,
+                             float* s_dump, void* stream);
+
+/* Merge the `psplit` partial (best, idx, second) triples per row, then decide per row:
+ *   gap = best - second >= tol_rel * rnorm[b,q] + tol_abs  -> ind[b,q] = idx (trusted);
+ *   otherwise (or when nonfinite[b] != 0) the row is appended to recheck_list[b] and
+ *   packed[b,q] is reset, so that ipsr_correlate_argmax_fp32 recomputes it exactly.
+ * nrecheck[b] must be zero on entry. */
+int ipsr_finalize_argmax(const float* part_best, const int32_t* part_idx, const float* part_second,
+                         int psplit, const float* rnorm, const int32_t* nonfinite,
+                         int B, int N, float tol_rel, float tol_abs,
+                         int32_t* ind, int32_t* recheck_list, int32_t* nrecheck, int64_t* packed,
+                         void* stream);
+
+/* Select every row for the exact path (IPSR_MODE_EXACT): recheck_list[b] = 0..N-1,
+ * nrecheck[b] = N, packed = identity. */
+int ipsr_select_all_rows(int B, int N, int32_t* recheck_list, int32_t* nrecheck, int64_t* packed,
+                         void* stream);
+
+/* Exact fp32 correlation (sequential-in-channel FFMA on Xn = fl(X*inv_norm), the reference's
+ * fp32 arithmetic) for the rows in recheck_list over bank columns [col_begin, col_end):
+ * packed[b,q] = max(packed[b,q], pack(score, col)) with the order-preserving packing of
+ * ipsr_pack_maxidx (largest score wins, lowest index on ties, NaN wins -- torch.max).
+ * row_ctas: CTAs cooperating over the row list of one image (1..N/64). */
+int ipsr_correlate_argmax_fp32(const float* x, const float* ref, const float* inv_norm,
+                               int B, int C, int N, int col_begin, int col_end,
+                               const int32_t* recheck_list, const int32_t* nrecheck, int row_ctas,
+                               int64_t* packed, void* stream);
+
+/* packed[b,q] -> ind[b,q] (and optionally vmax[b,q]) for the rows in recheck_list. */
+int ipsr_apply_recheck(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck,
+                       int B, int N, int32_t* ind, float* vmax, void* stream);
+
+/* Bank-sharded mode: exact fp32 score of the (trusted) local winner of EVERY row, packed for the
+ * exchange step: packed[b,q] = pack(<R[q], Xn[ind[b,q]]>, ind[b,q]).  Rows already holding an
+ * exact key from ipsr_correlate_argmax_fp32 (packed != identity) are left alone. */
+int ipsr_pack_winner_scores(const float* xt, const float* ref, const float* inv_norm, const int32_t* ind,
+                            int B, int C, int N, int64_t* packed, void* stream);
+
+/* (max, idx) <-> int64 keys for ncclAllReduce(ncclInt64, ncclMax) / gloo MAX. */
+int ipsr_pack_maxidx(const float* v, const int32_t* idx, int64_t n, int64_t* packed, void* stream);
+int ipsr_unpack_maxidx(const int64_t* packed, int64_t n, float* v, int32_t* idx, void* stream);
+
+/* util/MaxCoord.py:16-28 on a MATERIALISED score tensor s [P,L] (P bank patches, L locations):
+ * ind[l] = argmax_p s[p,l] (first index on ties, NaN wins), vmax[l] = the maximum. */
+int ipsr_maxcoord(const float* s, int P, int L, int64_t* ind_i64, float* vmax, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (d) coherent blend over masked positions + gather-paste   (models/IPSRFunction.py:70-133)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Stage the operands of the sequential blend, one warp per masked position l
+ * (q_l = mask_idx[l], p_l = ind[b,q_l]):
+ *   staged[b,l,0,:] = u_l = X[q_l] * inv_norm[q_l]      (IPSRFunction.py:109)
+ *   staged[b,l,1,:] = X[p_l]                             (known_region, :95)
+ *   vmask[b,l]      = <R[q_l], Xn[p_l]>  exact fp32      (vmax at masked positions, :70)  */
+int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
+                     const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
+                     float* staged, float* vmask, void* stream);
+
+/* The recurrence itself: one warp per image, operands streamed through shared memory by bulk
+ * async copies.  l=0: y_0 = X[p_0] (:98-101);  l>0: a = <u_l, y_{l-1}>; wn = a/(a+v);
+ * wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).
+ * Writes y [B,M,C], wn/wo [B,M] (wn[b,0] = 0, wo[b,0] = 1). */
+int ipsr_blend_scan(const float* staged, const float* vmask, int B, int C, int M,
+                    float* y, float* wn, float* wo, void* stream);
+
+/* out[b,:,q] = y[b,rank[q],:] for masked q, x[b,:,ind[b,q]] otherwise (replaces the dense
+ * conv_transpose of IPSRFunction.py:131). */
+int ipsr_paste(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
+               int B, int C, int N, int M, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (e) backward   (models/IPSRFunction.py:144-178)
+ *
+ * The reference stores the attention A in a LongTensor (:36,134), so the backward sees
+ * trunc(A): weight 1 for every unmasked row q and for the first masked row q_0 (the "unit
+ * routes" q -> ind[q]), and for masked rows l >= 1 only the entries with |A| >= 1
+ * ("exceptions", absent for well-conditioned inputs).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Unit routes grouped by bank column p = ind[b,q], ascending q inside a group (deterministic):
+ * route_ptr [B][N+1] (CSR), route_q [B][N].  N <= 16384. */
+int ipsr_build_routes(const int32_t* ind, const int32_t* flag, const int32_t* mask_idx,
+                      int B, int N, int M, int32_t* route_ptr, int32_t* route_q, void* stream);
+
+/* Replay the attention rows (:123-125: row_l = row_{l-1}*wn_l; row_l[p_l] += wo_l) per bank
+ * column and emit every entry of rows l >= 1 that survives the float -> int64 store:
+ * exc_start/exc_cnt [B][N], exc_l / exc_w [B][exc_cap], exc_total [B] (zero on entry;
+ * > exc_cap afterwards means the lists are incomplete and the backward replays instead). */
+int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
+                          int B, int N, int M, int32_t* exc_start, int32_t* exc_cnt,
+                          int32_t* exc_l, float* exc_w, int32_t* exc_total, int exc_cap, void* stream);
+
+/* gin[b,:,p] = g[b,:,p] + triple_w * ( sum_{q in routes(p)} g[b,:,q]
+ *                                      + sum_{e in exc(p)} exc_w[e] * g[b,:,mask_idx[exc_l[e]]] ) */
+int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
+                   const int32_t* route_ptr, const int32_t* route_q,
+                   const int32_t* exc_start, const int32_t* exc_cnt, const int32_t* exc_l, const float* exc_w,
+                   const int32_t* exc_total, int exc_cap,
+                   const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
+                   float triple_w, float* gin, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InnerCos / InnerCos2   (models/InnerCos.py:30-36, models/InnerCos2.py:34-41)
+ *   loss = mean_{b, c < c_limit, q} crit(x[b,c,q]*mask[q]*strength - target[b,c,q]);
+ *   crit: 0 = squared error (MSELoss), 1 = absolute error (L1Loss).
+ *   x is [B,C_total,N]; target is [B,c_limit,N].  partials: 1024 floats; ticket: one zeroed u32
+ *   (left zeroed on return).
+ * ------------------------------------------------------------------------------------------- */
+int innercos_loss_fwd(const float* x, const float* mask_f32, const float* target,
+                      int B, int C_total, int c_limit, int N, float strength, int crit,
+                      float* partials, uint32_t* ticket, float* loss, void* stream);
+/* grad_x[b,c,q] (c < c_limit; channels beyond are zeroed) = dloss/dx * grad_loss[0]. */
+int innercos_loss_bwd(const float* x, const float* mask_f32, const float* target, const float* grad_loss,
+                      int B, int C_total, int c_limit, int N, float strength, int crit,
+                      float* grad_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused forward: (a) -> (b,c) -> recheck -> (d) [-> routes/exceptions], one call, one stream,
+ * no host sync, CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ipsr_fwd_args {
+  const float* x;          /* [B,C,H,W] layer input                                      */
+  const float* ref;        /* [B,C,H,W] ref.relu4_3                                      */
+  const int32_t* flag;     /* [N]                                                        */
+  const int32_t* mask_idx; /* [M]                                                        */
+  const int32_t* rank;     /* [N]                                                        */
+  int32_t B, C, H, W, M;
+  int32_t mode;            /* IPSR_MODE_*                                                */
+  int32_t need_grad;       /* build backward routes / exceptions                         */
+  int32_t col_begin, col_end; /* bank column shard; 0, N for the whole bank              */
+  int32_t stop_after_corr; /* bank-sharded mode: stop after (b,c) with packed keys ready */
+  int32_t psplit;          /* column splits per row tile on the tensor path (<=0: auto)  */
+  int32_t exc_cap;
+  float tol_rel, tol_abs;  /* recheck threshold (<0: library default)                    */
+  float* out;              /* [B,C,H,W]                                                  */
+  /* saved for backward (caller-owned) */
+  int32_t* ind;            /* [B,N]                                                      */
+  float* wn; float* wo;    /* [B,M]                                                      */
+  int32_t* route_ptr;      /* [B,N+1]                                                    */
+  int32_t* route_q;        /* [B,N]                                                      */
+  int32_t* exc_start; int32_t* exc_cnt;   /* [B,N]                                       */
+  int32_t* exc_l; float* exc_w;           /* [B,exc_cap]                                 */
+  int32_t* exc_total;      /* [B]                                                        */
+  int32_t* nrecheck_out;   /* [B] optional: rows that took the exact path (diagnostics)  */
+  void* workspace; size_t workspace_bytes;
+} ipsr_fwd_args;
+
+size_t ipsr_workspace_bytes(int B, int C, int H, int W, int M, int mode);
+int ipsr_shift_forward(const ipsr_fwd_args* args, void* stream);
+/* Second half of the fused forward for the bank-sharded mode: after the caller all-reduced
+ * (MAX) the packed keys returned by ipsr_workspace_packed, unpack them and run (d). */
+int ipsr_shift_forward_finish(const ipsr_fwd_args* args, void* stream);
+/* Address inside the workspace of the [B,N] int64 keys the bank-sharded exchange reduces. */
+int64_t* ipsr_workspace_packed(const ipsr_fwd_args* args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPSR_SM100_H_ */

@@ -334,24 +334,26 @@ def innercos_loss(x: np.ndarray, mask2d: np.ndarray, target: np.ndarray, strengt
 # bank-sharded (max, idx) reduction -- the one exchange step of the sharded mode
 # --------------------------------------------------------------------------------------
 def pack_max_idx(v: np.ndarray, idx: np.ndarray) -> np.ndarray:
-    """Order-preserving packing used for the (max, index) all-reduce: high 32 bits = fp32
-    score mapped to an unsigned orderable key (-0 canonicalised to +0, NaN sorts above +inf as
+    """Order-preserving packing used for the (max, index) all-reduce, as SIGNED int64 so that
+    ncclMax / gloo MAX on int64 tensors apply: high 32 bits = fp32 score mapped to an orderable
+    signed int (-0 canonicalised to +0, NaN canonicalised to the quiet NaN above +inf because
     torch.max lets NaN win), low 32 bits = 0xFFFFFFFF - idx so that on equal scores the LOWEST
-    index wins (MaxCoord.py:22 tie rule)."""
+    index wins (MaxCoord.py:22 tie rule).  Identity of the reduction = INT64_MIN."""
     v = np.asarray(v, np.float32) + np.float32(0.0)
-    bits = v.view(np.uint32).astype(np.uint64)
-    neg = (bits >> np.uint64(31)) & np.uint64(1)
-    key = np.where(neg == 1, (~bits) & np.uint64(0xFFFFFFFF), bits | np.uint64(0x80000000))
-    low = np.uint64(0xFFFFFFFF) - np.asarray(idx).astype(np.uint64)
-    return (key << np.uint64(32)) | low
+    bits = v.view(np.uint32).copy()
+    bits[np.isnan(v)] = np.uint32(0x7FC00000)
+    neg = (bits >> np.uint32(31)) == 1
+    key = np.where(neg, bits ^ np.uint32(0x7FFFFFFF), bits).astype(np.uint32)
+    low = (np.uint64(0xFFFFFFFF) - np.asarray(idx).astype(np.uint64))
+    return ((key.astype(np.uint64) << np.uint64(32)) | low).view(np.int64)
 
 
 def unpack_max_idx(packed: np.ndarray):
-    packed = np.asarray(packed, np.uint64)
-    key = (packed >> np.uint64(32)).astype(np.uint64)
-    idx = (np.uint64(0xFFFFFFFF) - (packed & np.uint64(0xFFFFFFFF))).astype(np.int64)
-    pos = (key >> np.uint64(31)) & np.uint64(1)
-    bits = np.where(pos == 1, key & np.uint64(0x7FFFFFFF), (~key) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    u = np.ascontiguousarray(np.asarray(packed)).view(np.uint64)
+    key = (u >> np.uint64(32)).astype(np.uint32)
+    idx = (np.uint64(0xFFFFFFFF) - (u & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    neg = (key >> np.uint32(31)) == 1
+    bits = np.where(neg, key ^ np.uint32(0x7FFFFFFF), key).astype(np.uint32)
     return bits.view(np.float32), idx
 
 
