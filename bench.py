@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the IPSR / CSA patch-shift layer (BASELINE.json metric: shift-layer fwd+bwd images/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward + backward of the shift layer over one batch of synthetic features.
+Workload at N=1: BASELINE.json configs[1] -- batch 16, 256^2 images, 32x32x256 feature maps, centre
+mask (M = 256 of N = 1024 positions masked).  With N > 1 GPUs every rank runs the same per-GPU batch on
+its own synthetic shard (batch sharding: images are independent, no collective in the data path) and
+`value` is the aggregate images/s -- weak scaling.
+
+Printed JSON line (rank 0): value = device-resident throughput (CUDA events, max over ranks);
+e2e = the same metric through the reference-shaped module API with HOST (pinned) buffers, H2D and D2H
+copies inside the timed region; roofline = the correlation kernel against the measured bf16 peak;
+cpu_baseline = the numpy port of the reference's CPU path timed on this box's host cores.
+`--impl reference` times that CPU path alone (the reference is pure Python/PyTorch-on-CPU for this
+layer and cannot travel to the GPU box; the pinned numpy port of it in oracle/ stands in).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="configs[1]: shift layer fwd+bwd, batch 16 per GPU, 256^2 images, 32x32x256 features, centre mask",
+                B=16, C=256, H=32, W=32)
+METRIC = "shift_layer_fwd_bwd_images_per_sec"
+UNIT = "images/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=WORKLOAD["B"])
+    ap.add_argument("--channels", type=int, default=WORKLOAD["C"])
+    ap.add_argument("--size", type=int, default=WORKLOAD["H"], help="feature map side (32 = 256^2 image, 64 = 512^2)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "tensor", "exact"])
+    ap.add_argument("--graphs", type=int, default=1, help="replay the step from a CUDA graph (1) or launch eagerly (0)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: min(steps, 200))")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images of the CPU-baseline sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def centre_flag(H, W):
+    import numpy as np
+    f = np.zeros((H, W), np.int64)
+    f[H // 4:3 * H // 4, W // 4:3 * W // 4] = 1
+    return f.reshape(-1)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU path (numpy port pinned against the reference's own outputs, oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_path_images_per_sec(C, H, W, n_images, seed=1234):
+    import numpy as np
+    from oracle import ipsr_oracle as O
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+    flag = centre_flag(H, W)
+
+    def one():
+        x = rng.standard_normal((1, C, H, W)).astype(np.float32)
+        ref = (np.maximum(rng.standard_normal((1, C, H, W)), 0) * 3).astype(np.float32)
+        g = rng.standard_normal((1, C, H, W)).astype(np.float32)
+        t0 = time.perf_counter()
+        res = O.shift_forward(x, ref, flag, np.float32, keep_attn=True, with_gap=False)
+        O.shift_backward(g, res.attn_trunc, 1.0)
+        return time.perf_counter() - t0
+
+    one()                                       # warm-up (BLAS thread pool, page faults)
+    total = sum(one() for _ in range(n_images))
+    return n_images / total, threads, total
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on this box's host cores, same metric / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    C, H = args.channels, args.size
+    per_step = max(1, min(args.batch, 2 if H <= 32 else 1))          # bounded sample of the batch per step
+    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        cpu_path_images_per_sec(C, H, H, 1)
+    t_imgs, t_secs, threads = 0, 0.0, 1
+    for _ in range(steps):
+        ips, threads, secs = cpu_path_images_per_sec(C, H, H, per_step)
+        t_imgs += per_step
+        t_secs += secs
+    value = t_imgs / t_secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * t_secs / steps * (args.batch / per_step), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"] if (args.batch, C, H) == (16, 256, 32) else
+                   "shift layer fwd+bwd, batch %d, %dx%dx%d features, centre mask" % (args.batch, H, H, C),
+                   "batch_per_gpu": args.batch, "C": C, "H": H, "W": H,
+                   "note": "reference CPU path = numpy port (oracle/ipsr_oracle.py) pinned on the reference's golden outputs; "
+                           "the Python reference itself cannot travel to the GPU box"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d steps x %d image(s) of the batch, fwd+bwd, fp32" % (steps, per_step)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import collections
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from deepinpainting_b200 import shift_ops
+    from deepinpainting_b200.models import IPSR_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, C, H = args.batch, args.channels, args.size
+    N = H * H
+    shift_ops.config["correlation_mode"] = args.mode
+    flag = centre_flag(H, H)
+    M = int(flag.sum())
+    mi = shift_ops.mask_index_from_flag(torch.from_numpy(flag), dev)
+
+    # ---- synthetic inputs: a rotating pool larger than L2 so every step starts from HBM ----
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    bytes_per_set = 3 * B * C * N * 4
+    pool = max(2, -(-2 * 126 * (1 << 20) // bytes_per_set) + 1)
+    pool = min(pool, 16)
+    sets = []
+    for _ in range(pool):
+        x = torch.randn(B, C, H, H, generator=gen)
+        ref = torch.relu(torch.randn(B, C, H, H, generator=gen)) * 3
+        g = torch.randn(B, C, H, H, generator=gen)
+        sets.append((x.to(dev), ref.to(dev), g.to(dev)))
+
+    def step_eager(i, events=None):
+        x, ref, g = sets[i % pool]
+        out, saved = shift_ops.shift_forward(x, ref, mi, need_grad=True, events=events)
+        gin = shift_ops.shift_backward(g, saved, 1.0)
+        return out, gin
+
+    launches_per_step = shift_ops.launches_per_step(C, N, M, need_grad=True, mode=args.mode, backward=True)
+
+    # ---- optional CUDA graphs: one per input set ----
+    graphs = None
+    if args.graphs:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(min(3, pool)):
+                    step_eager(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graphs, keep = [], []
+            for i in range(pool):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    keep.append(step_eager(i))
+                graphs.append(gr)
+        except Exception as exc:                                   # graphs are an optimisation, eager is the same work
+            sys.stderr.write("CUDA graph capture failed (%s); running eagerly\n" % exc)
+            graphs = None
+            torch.cuda.synchronize()
+
+    def step(i):
+        if graphs is not None:
+            graphs[i % pool].replay()
+        else:
+            step_eager(i)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up, then EXACTLY K timed steps ----
+    W_, K = max(3, args.warmup), args.steps
+    for i in range(W_):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        step(W_ + i)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max * 1e-3)
+
+    # ---- live roofline of the correlation kernel: event pairs recorded by the library around it ----
+    RK = min(K, 200)
+    pairs = []
+    for i in range(RK):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); b_.record()                                   # materialise the handles
+        pairs.append((a, b_))
+    torch.cuda.synchronize()
+    for i in range(RK):
+        step_eager(i, events=pairs[i])
+    torch.cuda.synchronize()
+    corr_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in pairs)
+    pk = peaks()
+    tensor_mode = args.mode == "tensor" or (args.mode == "auto" and C % 64 == 0 and N % 128 == 0)
+    flops = 2.0 * N * N * C * B                                    # algorithmic: one N x N x C correlation per image
+    achieved = flops / (corr_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "corr_tc_kernel (tcgen05, 3 x bf16 split)" if tensor_mode else "corr_fp32_kernel (FFMA)",
+                "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                "traffic": None, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
+                "peak_source": pk["source"] + " bf16 dense, sustained",
+                "note": "algorithmic FLOPs = 2*N^2*C per image (the 3 split passes are not counted: ceiling = 1/3 of peak)"}
+
+    # ---- e2e: reference-shaped module API, host pinned buffers, H2D + D2H inside the timed region ----
+    Ref = collections.namedtuple("Ref", ["relu4_3"])
+    layer = IPSR_model(5 / 16.0, 1, 1, 1, 1, 1)
+    S = H * 8
+    mg = torch.zeros(1, 1, S, S, dtype=torch.bool)
+    mg[:, :, S // 4:3 * S // 4, S // 4:3 * S // 4] = True
+    layer.set_mask(mg.to(dev), 3, 5 / 16.0)
+    hx, hr, hg = (torch.empty(B, C, H, H).pin_memory() for _ in range(3))
+    hx.copy_(sets[0][0]); hr.copy_(sets[0][1]); hg.copy_(sets[0][2])
+    hout, hgin = torch.empty(B, C, H, H).pin_memory(), torch.empty(B, C, H, H).pin_memory()
+    dx, dr, dg = (torch.empty(B, C, H, H, device=dev) for _ in range(3))
+
+    def e2e_step():
+        dx.copy_(hx, non_blocking=True); dr.copy_(hr, non_blocking=True); dg.copy_(hg, non_blocking=True)
+        xin = dx.detach().requires_grad_(True)
+        layer.set_ref(Ref(dr))
+        y = layer(xin)
+        y.backward(dg)
+        hout.copy_(y.detach(), non_blocking=True)
+        hgin.copy_(xin.grad, non_blocking=True)
+
+    EK = args.e2e_steps or min(K, 200)
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(EK):
+        e2e_step()
+    f1.record()
+    sync_all()
+    wall = time.perf_counter() - t0
+    te = torch.tensor([max(f0.elapsed_time(f1) * 1e-3, 0.0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * EK / float(te.item())
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * B * C * N * 4, "d2h_bytes_per_step": 2 * B * C * N * 4,
+           "steps": EK, "wall_s": wall, "api": "IPSR_model.forward + autograd backward, pinned host buffers"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_img = args.cpu_images or (24 if H <= 32 else 6)
+        ips, threads, secs = cpu_path_images_per_sec(C, H, H, n_img)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d images of the workload (B=1 each), fwd+bwd, fp32, %.1f s" % (n_img, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (correlation: 3 x bf16 split on tcgen05, fp32 accumulate + exact fp32 recheck)" if tensor_mode else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"] if (B, C, H) == (16, 256, 32) else
+                       "shift layer fwd+bwd, batch %d per GPU, %dx%dx%d features, centre mask" % (B, H, H, C),
+                       "batch_per_gpu": B, "global_batch": B * world, "C": C, "H": H, "W": H, "N": N, "M": M,
+                       "parallelism": "batch-sharded x%d, no data-path collective" % world,
+                       "mode": args.mode, "cuda_graphs": graphs is not None,
+                       "l2": "rotating pool of %d input sets (%d MB) > 126 MB L2" % (pool, pool * bytes_per_set >> 20)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": launches_per_step * K,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

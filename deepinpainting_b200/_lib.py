@@ -32,7 +32,7 @@ class FwdArgs(C.Structure):
         ("out", _p), ("ind", _p), ("wn", _p), ("wo", _p),
         ("route_ptr", _p), ("route_q", _p),
         ("exc_start", _p), ("exc_cnt", _p), ("exc_l", _p), ("exc_w", _p), ("exc_total", _p),
-        ("nrecheck_out", _p),
+        ("nrecheck_out", _p), ("ev_corr_begin", _p), ("ev_corr_end", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
     ]
 

@@ -171,6 +171,12 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   }
 
   const bool tensor = (mode == IPSR_MODE_TENSOR);
+  auto record = [&](void* ev) -> int {
+    if (!ev) return IPSR_OK;
+    cudaError_t ee = cudaEventRecord(reinterpret_cast<cudaEvent_t>(ev), st);
+    IPSR_REQUIRE(ee == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: event record: %s", cudaGetErrorString(ee));
+    return IPSR_OK;
+  };
   IPSR_FORWARD(ipsr_extract_normalize(a->x, a->ref, B, C, N, a->rank, M, at<float>(a, w.inv_norm), at<float>(a, w.rnorm),
                                       at<float>(a, w.xt), at<float>(a, w.r_masked),
                                       tensor ? at<void>(a, w.x_tiles) : nullptr, tensor ? at<void>(a, w.r_tiles) : nullptr,
@@ -185,24 +191,23 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
     const int max_split = (ce - cb) / 128;
     if (psplit > max_split) psplit = max_split;
     if (psplit < 1) psplit = 1;
+    IPSR_FORWARD(record(a->ev_corr_begin));
     IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, psplit,
                                           at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
                                           at<float>(a, w.part_second), nullptr, stream));
+    IPSR_FORWARD(record(a->ev_corr_end));
     const float tol_rel = a->tol_rel >= 0.f ? a->tol_rel : kDefaultTolRel;
     const float tol_abs = a->tol_abs >= 0.f ? a->tol_abs : kDefaultTolAbs;
-    // psplit may have been clamped again inside the launcher only when blocks < psplit; recompute identically
-    int block_n = (C <= 256) ? 128 : 256;
-    if ((ce - cb) % block_n != 0) block_n = 128;
-    const int blocks_total = (ce - cb) / block_n;
-    if (psplit > blocks_total) psplit = blocks_total;
     IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
                                       psplit, at<float>(a, w.rnorm), nonfinite, B, N, tol_rel, tol_abs, a->ind, list,
                                       nrecheck, packed, stream));
   } else {
     IPSR_FORWARD(ipsr_select_all_rows(B, N, list, nrecheck, packed, stream));
   }
+  if (!tensor) IPSR_FORWARD(record(a->ev_corr_begin));
   IPSR_FORWARD(ipsr_correlate_argmax_fp32(a->x, a->ref, at<float>(a, w.inv_norm), B, C, N, cb, ce, list, nrecheck,
                                           tensor ? 2 : (N + 63) / 64, packed, stream));
+  if (!tensor) IPSR_FORWARD(record(a->ev_corr_end));
   if (a->nrecheck_out) {
     e = cudaMemcpyAsync(a->nrecheck_out, nrecheck, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memcpy: %s", cudaGetErrorString(e));

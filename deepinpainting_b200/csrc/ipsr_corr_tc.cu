@@ -289,7 +289,7 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   prm.B = B; prm.KB = C / kTileK; prm.RB = N / kTileRows; prm.N = N;
   prm.col_begin = col_begin;
   prm.blocks_total = ncols / block_n;
-  if (psplit > prm.blocks_total) psplit = prm.blocks_total;
+  // psplit > blocks_total is allowed: the surplus splits own no column block and report -inf
   prm.psplit = psplit;
   prm.part_best = part_best; prm.part_idx = part_idx; prm.part_second = part_second; prm.s_dump = s_dump;
   size_t smem = 0;

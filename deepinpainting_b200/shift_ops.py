@@ -146,7 +146,8 @@ class ShiftSaved:
 class _Call:
     """Owns the argument struct and every buffer of one forward call."""
 
-    def __init__(self, x, ref, mi: MaskIndex, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics):
+    def __init__(self, x, ref, mi: MaskIndex, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics,
+                 events=None):
         B, Cc, H, W = x.shape
         N = H * W
         dev = x.device
@@ -189,6 +190,8 @@ class _Call:
         a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total = (_ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l),
                                                                _ptr(s.exc_w), _ptr(s.exc_total))
         a.nrecheck_out = _ptr(s.nrecheck)
+        if events is not None:                       # (begin, end) torch.cuda.Event pair, already materialised
+            a.ev_corr_begin, a.ev_corr_end = events[0].cuda_event, events[1].cuda_event
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), nbytes
         self.args = a
         self.keep = (x, ref, mi)
@@ -204,7 +207,7 @@ class _Call:
 
 
 def shift_forward(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, need_grad: bool = True,
-                  mode: Optional[str] = None, diagnostics: bool = False):
+                  mode: Optional[str] = None, diagnostics: bool = False, events=None):
     """models/IPSRFunction.py:13-140 for shift_sz = stride = 1.  Returns (out, ShiftSaved)."""
     x = _require_cuda(x, "input", torch.float32)
     ref = _require_cuda(ref, "ref.relu4_3", torch.float32)
@@ -212,9 +215,27 @@ def shift_forward(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, need_grad: 
         raise AssertionError("Input Dim has to be 4")
     if ref.shape != x.shape:
         raise ValueError("ref.relu4_3 %s must have the shape of the input %s" % (tuple(ref.shape), tuple(x.shape)))
-    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], 0, 0, False, diagnostics)
+    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], 0, 0, False, diagnostics, events)
     _lib.call("ipsr_shift_forward", C.byref(call.args), _stream_ptr(x.device))
     return call.out, call.saved
+
+
+def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Optional[str] = None, backward: bool = True) -> int:
+    """Number of libipsr_sm100 KERNEL launches of one forward (+ backward) -- what bench.py reports as
+    gpu_launches (memsets / event records are not kernels)."""
+    mode = mode or config["correlation_mode"]
+    tensor = mode == "tensor" or (mode == "auto" and _lib.load().ipsr_tensor_path_supported(C, N) == 1)
+    n = 1                                   # extract_normalize
+    n += 2 if tensor else 1                 # correlate_tc + finalize | select_all_rows
+    n += 2                                  # correlate_fp32 + apply_recheck
+    if M > 0:
+        n += 2                              # blend_stage + blend_scan
+    if need_grad:
+        n += 1 + (1 if M > 1 else 0)        # build_routes (+ build_exceptions)
+    n += 1                                  # paste
+    if backward:
+        n += 1                              # shift_bwd
+    return n
 
 
 def shift_forward_sharded(x, ref, mi: MaskIndex, col_begin: int, col_end: int, reduce_max, need_grad: bool = True,

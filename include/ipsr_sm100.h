@@ -235,6 +235,8 @@ typedef struct ipsr_fwd_args {
   int32_t* exc_l; float* exc_w;           /* [B,exc_cap]                                 */
   int32_t* exc_total;      /* [B]                                                        */
   int32_t* nrecheck_out;   /* [B] optional: rows that took the exact path (diagnostics)  */
+  void* ev_corr_begin;     /* optional cudaEvent_t pair recorded on `stream` around the      */
+  void* ev_corr_end;       /*   correlation kernel ((b,c)), for live roofline measurement    */
   void* workspace; size_t workspace_bytes;
 } ipsr_fwd_args;
 

@@ -155,7 +155,7 @@ def float_to_int64_trunc(a: np.ndarray) -> np.ndarray:
 
 
 def shift_forward(x: np.ndarray, ref: np.ndarray, flag: np.ndarray, dtype=np.float32,
-                  keep_attn: bool = True) -> ShiftResult:
+                  keep_attn: bool = True, with_gap: bool = True) -> ShiftResult:
     """IPSRFunction.py:13-140 with shift_sz = stride = 1.
 
     x   [B,C,H,W]  the layer input (bank source; patches of ALL positions form the bank)
@@ -189,7 +189,9 @@ def shift_forward(x: np.ndarray, ref: np.ndarray, flag: np.ndarray, dtype=np.flo
         S = (R @ Xn.T).astype(dtype)                          # :59  conv_enc(ref): S[q,p]
         ind = S.argmax(axis=1)                                # MaxCoord.py:22 (first index on ties)
         vmax = S[np.arange(N), ind]
-        if N > 1:
+        if not with_gap:
+            gap_all[b] = np.nan
+        elif N > 1:
             part = np.partition(S, N - 2, axis=1)
             gap_all[b] = part[:, N - 1] - part[:, N - 2]
         else:
