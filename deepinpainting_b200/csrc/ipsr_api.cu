@@ -60,7 +60,7 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
   w.counters = take(cur, (size_t)2 * B * 4);
   w.xt = take(cur, BN * C * 4);
   w.r_masked = take(cur, BM * C * 4);
-  w.staged = take(cur, BM * 2 * C * 4);
+  w.staged = take(cur, BM * (size_t)(2 * C + 4) * 4);
   w.vmask = take(cur, BM * 4);
   w.y = take(cur, BM * C * 4);
   w.packed = take(cur, BN * 8);
@@ -122,15 +122,12 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
   if (M > 0) {
     IPSR_FORWARD(ipsr_blend_stage(at<float>(a, w.xt), at<float>(a, w.r_masked), at<float>(a, w.inv_norm), a->ind,
                                   a->mask_idx, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask), stream));
-    IPSR_FORWARD(ipsr_blend_scan(at<float>(a, w.staged), at<float>(a, w.vmask), B, C, M, at<float>(a, w.y), a->wn, a->wo,
-                                 stream));
+    IPSR_FORWARD(ipsr_blend_scan(at<float>(a, w.staged), B, C, M, at<float>(a, w.y), a->wn, a->wo, stream));
   }
-  if (a->need_grad) {
-    IPSR_FORWARD(ipsr_build_routes(a->ind, a->flag, a->mask_idx, B, N, M, a->route_ptr, a->route_q, stream));
-    if (M > 1)
-      IPSR_FORWARD(ipsr_build_exceptions(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l,
-                                         a->exc_w, a->exc_total, a->exc_cap, stream));
-  }
+  if (a->need_grad)
+    return ipsr_paste_with_bookkeeping(a->x, at<float>(a, w.y), a->ind, a->rank, a->flag, a->mask_idx, a->wn, a->wo, B, C,
+                                       N, M, a->out, a->route_ptr, a->route_q, a->exc_start, a->exc_cnt, a->exc_l,
+                                       a->exc_w, a->exc_total, a->exc_cap, stream);
   return ipsr_paste(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream);
 }
 
@@ -184,8 +181,10 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   if (tensor) {
     int psplit = a->psplit;
     if (psplit <= 0) {
+      // one CTA per SM is resident (the ring + row tile fill shared memory): split the bank columns only
+      // while that still adds whole CTAs to a single wave
       const long long tiles = (long long)B * (N / kTileRows);
-      psplit = (int)((148 + tiles - 1) / tiles);
+      psplit = (int)(148 / tiles);
     }
     if (psplit > kMaxPsplit) psplit = kMaxPsplit;
     const int max_split = (ce - cb) / 128;
@@ -206,7 +205,7 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   }
   if (!tensor) IPSR_FORWARD(record(a->ev_corr_begin));
   IPSR_FORWARD(ipsr_correlate_argmax_fp32(a->x, a->ref, at<float>(a, w.inv_norm), B, C, N, cb, ce, list, nrecheck,
-                                          tensor ? 2 : (N + 63) / 64, packed, stream));
+                                          tensor ? 0 : (N + 63) / 64, packed, stream));
   if (!tensor) IPSR_FORWARD(record(a->ev_corr_end));
   if (a->nrecheck_out) {
     e = cudaMemcpyAsync(a->nrecheck_out, nrecheck, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);

@@ -11,9 +11,12 @@
 //                     C-vector state in registers, one shuffle reduction per step;
 //   ipsr_paste        out[b,c,q] = x[b,c,ind[q]] (row staged in shared memory, gather by index)
 //                     or y[b,rank[q],c] at masked positions; HBM traffic = read x + write out.
-#include "ipsr_common.cuh"
+#include "ipsr_bookkeeping.cuh"
 
 namespace ipsr {
+
+// one staged step: u_l [C], X[p_l] [C], then v_l, c_l = <u_l, X[p_{l-1}]> and 2 pad floats (16-byte sized)
+__host__ __device__ inline int staged_stride(int C) { return 2 * C + 4; }
 
 // ---------------------------------------------------------------------------------------------
 // stage
@@ -33,13 +36,21 @@ blend_stage_kernel(const float* __restrict__ xt, const float* __restrict__ r_mas
   const float* xq = xt + ((size_t)b * N + q) * C;
   const float* xp = xt + ((size_t)b * N + p) * C;
   const float* rq = r_masked + ((size_t)b * M + l) * C;
-  float* su = staged + (((size_t)b * M + l) * 2) * C;
+  // matched patch of the PREVIOUS masked position: c_l = <u_l, X[p_{l-1}]> feeds the two-step
+  // form of the recurrence used by the scan (a_l = wn_{l-1} <u_l, y_{l-2}> + wo_{l-1} c_l)
+  const float* xk = xt + ((size_t)b * N + (l > 0 ? ind[(size_t)b * N + mask_idx[l - 1]] : p)) * C;
+  float* su = staged + ((size_t)b * M + l) * staged_stride(C);
   float* sp = su + C;
-  float acc = 0.f;
+  float acc = 0.f, cacc = 0.f;
   for (int c = lane * 4; c < C; c += 128) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(xq + c));
     const float4 k = __ldg(reinterpret_cast<const float4*>(xp + c));
     const float4 r = __ldg(reinterpret_cast<const float4*>(rq + c));
+    const float4 kp = __ldg(reinterpret_cast<const float4*>(xk + c));
+    cacc = fmaf(__fmul_rn(a.x, inv_q), kp.x, cacc);
+    cacc = fmaf(__fmul_rn(a.y, inv_q), kp.y, cacc);
+    cacc = fmaf(__fmul_rn(a.z, inv_q), kp.z, cacc);
+    cacc = fmaf(__fmul_rn(a.w, inv_q), kp.w, cacc);
     // u = little_value * (1/(norm+1e-8))                          IPSRFunction.py:109
     *reinterpret_cast<float4*>(su + c) =
         make_float4(__fmul_rn(a.x, inv_q), __fmul_rn(a.y, inv_q), __fmul_rn(a.z, inv_q), __fmul_rn(a.w, inv_q));
@@ -51,7 +62,11 @@ blend_stage_kernel(const float* __restrict__ xt, const float* __restrict__ r_mas
     acc = fmaf(r.w, __fmul_rn(k.w, inv_p), acc);
   }
   acc = warp_sum(acc);
-  if (lane == 0) vmask[(size_t)b * M + l] = acc;
+  cacc = warp_sum(cacc);
+  if (lane == 0) {
+    *reinterpret_cast<float4*>(su + 2 * C) = make_float4(acc, cacc, 0.f, 0.f);
+    if (vmask) vmask[(size_t)b * M + l] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -64,7 +79,7 @@ constexpr int kScanStages = 8;
 // of `staged`, fetched by one bulk copy.
 template <int VPL>
 __global__ void __launch_bounds__(32)
-blend_scan_kernel(const float* __restrict__ staged, const float* __restrict__ vmask, int M, int steps_per_stage,
+blend_scan_kernel(const float* __restrict__ staged, int M, int steps_per_stage,
                   float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out) {
   extern __shared__ __align__(128) uint8_t scan_smem[];
   __shared__ __align__(8) unsigned long long bars[kScanStages];
@@ -72,10 +87,10 @@ blend_scan_kernel(const float* __restrict__ staged, const float* __restrict__ vm
   const int b = blockIdx.x;
   const int lane = threadIdx.x;
   const uint32_t ring = smem_u32(scan_smem);
-  const uint32_t step_bytes = 2u * C * sizeof(float);
+  constexpr int kStride = 2 * C + 4;
+  const uint32_t step_bytes = (uint32_t)kStride * sizeof(float);
   const uint32_t stage_bytes = step_bytes * steps_per_stage;
-  const float* src = staged + (size_t)b * M * 2 * C;
-  const float* vm = vmask + (size_t)b * M;
+  const float* src = staged + (size_t)b * M * kStride;
   float* yb = y + (size_t)b * M * C;
   const int nchunks = (M + steps_per_stage - 1) / steps_per_stage;
 
@@ -89,12 +104,22 @@ blend_scan_kernel(const float* __restrict__ staged, const float* __restrict__ vm
     const int l0 = chunk * steps_per_stage;
     const uint32_t bytes = step_bytes * (uint32_t)min(steps_per_stage, M - l0);
     mbar_expect_tx(smem_u32(&bars[s]), bytes);
-    bulk_g2s(ring + (uint32_t)s * stage_bytes, src + (size_t)l0 * 2 * C, bytes, smem_u32(&bars[s]));
+    bulk_g2s(ring + (uint32_t)s * stage_bytes, src + (size_t)l0 * kStride, bytes, smem_u32(&bars[s]));
   };
   if (lane == 0)
     for (int ch = 0; ch < min(nchunks, kScanStages); ++ch) issue(ch);
 
-  float yv[VPL];
+  // Two-step form of the recurrence.  The reference computes a_l = <u_l, y_{l-1}> (IPSRFunction.py:116)
+  // with y_{l-1} = wn_{l-1} y_{l-2} + wo_{l-1} X[p_{l-1}] (:122); by linearity
+  //     a_l = wn_{l-1} * <u_l, y_{l-2}> + wo_{l-1} * c_l,      c_l = <u_l, X[p_{l-1}]> (staged),
+  // so the 32-lane reduction of step l+1 (it only needs y_{l-1}) runs while step l resolves its
+  // scalar chain, instead of the two being serialised.  y_{-1} = 0, wn_0 = 0, wo_0 = 1 make l = 0 and
+  // l = 1 regular: y_0 = X[p_0], a_1 = c_1.  Differs from the one-step form by rounding only.
+  float y1[VPL];                       // y_{l-1}
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) y1[i] = 0.f;
+  float d = 0.f;                       // <u_l, y_{l-2}>
+  float wn_prev = 0.f, wo_prev = 1.f;
   for (int ch = 0; ch < nchunks; ++ch) {
     const int s = ch % kScanStages;
     mbar_wait(smem_u32(&bars[s]), (uint32_t)(ch / kScanStages) & 1u);
@@ -103,44 +128,53 @@ blend_scan_kernel(const float* __restrict__ staged, const float* __restrict__ vm
     const int nl = min(steps_per_stage, M - l0);
     for (int j = 0; j < nl; ++j) {
       const int l = l0 + j;
-      const float* u = st + (size_t)j * 2 * C;
+      const float* u = st + (size_t)j * kStride;
       const float* k = u + C;
-      float uv[VPL], kv[VPL];
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        uv[i] = u[lane + 32 * i];
-        kv[i] = k[lane + 32 * i];
+      // u of the NEXT step: same stage, or the first step of the next stage (it has landed or we wait)
+      const float* un = u + kStride;
+      if (j + 1 == nl) {
+        if (l + 1 < M) {
+          const int s2 = (ch + 1) % kScanStages;
+          mbar_wait(smem_u32(&bars[s2]), (uint32_t)((ch + 1) / kScanStages) & 1u);
+          un = reinterpret_cast<const float*>(scan_smem + (size_t)s2 * stage_bytes);
+        } else {
+          un = u;                                            // last step: value unused
+        }
       }
-      const float v = __ldg(vm + l);
+      // (1) independent of this step's weights: d_{l+1} = <u_{l+1}, y_{l-1}>
+      float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; i += 2) {
+        p0 = fmaf(un[lane + 32 * i], y1[i], p0);
+        if (i + 1 < VPL) p1 = fmaf(un[lane + 32 * (i + 1)], y1[i + 1], p1);
+      }
+      const float dn = warp_sum(p0 + p1);
+      // (2) scalar chain of step l
+      const float v = u[2 * C], c = u[2 * C + 1];
+      float wn, wo;
       if (l == 0) {
-        // first masked patch: plain copy of the matched patch          IPSRFunction.py:98-101
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) yv[i] = kv[i];
-        if (lane == 0) {
-          wn_out[(size_t)b * M] = 0.f;
-          wo_out[(size_t)b * M] = 1.f;
-        }
+        wn = 0.f;                                            // first masked patch: plain copy   :98-101
+        wo = 1.f;
       } else {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < VPL; i += 2) {
-          a0 = fmaf(uv[i], yv[i], a0);
-          if (i + 1 < VPL) a1 = fmaf(uv[i + 1], yv[i + 1], a1);
-        }
-        const float a = warp_sum(a0 + a1);                 // 1x1 conv == dot            :116
+        const float a = fmaf(wn_prev, d, __fmul_rn(wo_prev, c));
         const float den = __fadd_rn(a, v);
-        const float wn = __fdiv_rn(a, den);                // no clamp, inf/nan propagate :120
-        const float wo = __fdiv_rn(v, den);                //                              :121
-#pragma unroll
-        for (int i = 0; i < VPL; ++i)                       // two rounded products, one sum :122
-          yv[i] = __fadd_rn(__fmul_rn(wn, yv[i]), __fmul_rn(wo, kv[i]));
-        if (lane == 0) {
-          wn_out[(size_t)b * M + l] = wn;
-          wo_out[(size_t)b * M + l] = wo;
-        }
+        wn = __fdiv_rn(a, den);                              // no clamp, inf/nan propagate      :120
+        wo = __fdiv_rn(v, den);                              //                                    :121
       }
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) yb[(size_t)l * C + lane + 32 * i] = yv[i];
+      for (int i = 0; i < VPL; ++i) {                         // two rounded products, one sum      :122
+        const float kv = k[lane + 32 * i];
+        y1[i] = (l == 0) ? kv : __fadd_rn(__fmul_rn(wn, y1[i]), __fmul_rn(wo, kv));
+      }
+      if (lane == 0) {
+        wn_out[(size_t)b * M + l] = wn;
+        wo_out[(size_t)b * M + l] = wo;
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) yb[(size_t)l * C + lane + 32 * i] = y1[i];
+      d = dn;
+      wn_prev = wn;
+      wo_prev = wo;
     }
     __syncwarp();                                          // every lane is done reading stage s
     if (lane == 0 && ch + kScanStages < nchunks) issue(ch + kScanStages);
@@ -150,14 +184,13 @@ blend_scan_kernel(const float* __restrict__ staged, const float* __restrict__ vm
 // ---------------------------------------------------------------------------------------------
 // paste
 // ---------------------------------------------------------------------------------------------
-// grid = (C / CT, B); a CTA stages CT channel rows of x[b] (N floats each) in shared memory and
-// writes the CT output rows: coalesced reads, coalesced writes, gather inside the SM.
-__global__ void __launch_bounds__(256)
-paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ ind,
-             const int* __restrict__ rank, int C, int N, int M, int CT, float* __restrict__ out) {
-  extern __shared__ __align__(16) float rows[];          // [CT][N]
-  const int b = blockIdx.y;
-  const int c0 = blockIdx.x * CT;
+// A CTA stages CT channel rows of x[b] (N floats each) in shared memory and writes the CT output
+// rows: coalesced reads, coalesced writes, gather inside the SM.
+__device__ __forceinline__ void
+paste_cta(int cx, int b, float* rows, const float* __restrict__ x, const float* __restrict__ y,
+          const int* __restrict__ ind, const int* __restrict__ rank, int C, int N, int M, int CT,
+          float* __restrict__ out) {
+  const int c0 = cx * CT;
   const int ct = min(CT, C - c0);
   const float* xb = x + ((size_t)b * C + c0) * N;
   float* ob = out + ((size_t)b * C + c0) * N;
@@ -183,14 +216,61 @@ paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int
   }
 }
 
+// grid = (C / CT, B)
+__global__ void __launch_bounds__(256)
+paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ ind,
+             const int* __restrict__ rank, int C, int N, int M, int CT, float* __restrict__ out) {
+  extern __shared__ __align__(16) float rows[];          // [CT][N]
+  paste_cta(blockIdx.x, blockIdx.y, rows, x, y, ind, rank, C, N, M, CT, out);
+}
+
+// The paste and the two bookkeeping builders of the backward are independent once the scan is done:
+// one launch, block ranges = [routes: B CTAs][exceptions: B CTAs][paste: B * C/CT CTAs].
+// The latency-bound bookkeeping CTAs are scheduled first and overlap the bandwidth-bound paste.
+struct FusedPasteArgs {
+  const float* x; const float* y; const int* ind; const int* rank; float* out;
+  int B, C, N, M, CT, ctiles;
+  const int* flag; const int* mask_idx; int* route_ptr; int* route_q;
+  const float* wn; const float* wo; int* exc_start; int* exc_cnt; int* exc_l; float* exc_w; int* exc_total; int exc_cap;
+  int n_routes, n_exc, exc_per_img;
+};
+
+__global__ void __launch_bounds__(256) paste_fused_kernel(const FusedPasteArgs a) {
+  extern __shared__ __align__(16) float fsm[];
+  int blk = blockIdx.x;
+  if (blk < a.n_routes) {
+    build_routes_cta(blk, reinterpret_cast<int*>(fsm), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q);
+    return;
+  }
+  blk -= a.n_routes;
+  if (blk < a.n_exc) {
+    build_exceptions_cta(blk, fsm, a.ind, a.mask_idx, a.wn, a.wo, a.N, a.M, a.exc_start, a.exc_cnt, a.exc_l, a.exc_w,
+                         a.exc_total, a.exc_cap);
+    return;
+  }
+  blk -= a.n_exc;
+  paste_cta(blk % a.ctiles, blk / a.ctiles, fsm, a.x, a.y, a.ind, a.rank, a.C, a.N, a.M, a.CT, a.out);
+}
+
+static int paste_ct(int C, int N) {
+  // channel rows per CTA: ~64 KiB of shared memory, at least 1 row
+  int CT = (int)((64 * 1024) / ((size_t)N * sizeof(float)));
+  if (CT < 1) CT = 1;
+  if (CT > 16) CT = 16;
+  if (CT > C) CT = C;
+  return CT;
+}
+
 }  // namespace ipsr
+
+extern "C" int ipsr_staged_stride(int C) { return ipsr::staged_stride(C); }
 
 extern "C" int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
                                 const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
                                 float* staged, float* vmask, void* stream) {
   using namespace ipsr;
   if (M == 0) return IPSR_OK;
-  IPSR_REQUIRE(xt && r_masked && inv_norm && ind && mask_idx && staged && vmask, IPSR_ERR_INVALID_ARG,
+  IPSR_REQUIRE(xt && r_masked && inv_norm && ind && mask_idx && staged, IPSR_ERR_INVALID_ARG,
                "ipsr_blend_stage: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && M <= N, IPSR_ERR_INVALID_ARG, "ipsr_blend_stage: bad dims");
   IPSR_REQUIRE(C % 4 == 0, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d must be a multiple of 4", C);
@@ -201,10 +281,10 @@ extern "C" int ipsr_blend_stage(const float* xt, const float* r_masked, const fl
 
 namespace ipsr {
 template <int VPL>
-static int launch_scan(const float* staged, const float* vmask, int B, int M, float* y, float* wn, float* wo,
+static int launch_scan(const float* staged, int B, int M, float* y, float* wn, float* wo,
                        cudaStream_t st) {
   constexpr int C = VPL * 32;
-  const size_t step_bytes = 2 * (size_t)C * sizeof(float);
+  const size_t step_bytes = (size_t)staged_stride(C) * sizeof(float);
   int sps = (int)(8192 / step_bytes);                     // ~8 KiB per stage
   if (sps < 1) sps = 1;
   const size_t smem = (size_t)kScanStages * sps * step_bytes;
@@ -212,30 +292,30 @@ static int launch_scan(const float* staged, const float* vmask, int B, int M, fl
     cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
   }
-  blend_scan_kernel<VPL><<<B, 32, smem, st>>>(staged, vmask, M, sps, y, wn, wo);
+  blend_scan_kernel<VPL><<<B, 32, smem, st>>>(staged, M, sps, y, wn, wo);
   return check_launch("ipsr_blend_scan");
 }
 }  // namespace ipsr
 
-extern "C" int ipsr_blend_scan(const float* staged, const float* vmask, int B, int C, int M,
+extern "C" int ipsr_blend_scan(const float* staged, int B, int C, int M,
                                float* y, float* wn, float* wo, void* stream) {
   using namespace ipsr;
   if (M == 0) return IPSR_OK;
-  IPSR_REQUIRE(staged && vmask && y && wn && wo, IPSR_ERR_INVALID_ARG, "ipsr_blend_scan: null pointer");
+  IPSR_REQUIRE(staged && y && wn && wo, IPSR_ERR_INVALID_ARG, "ipsr_blend_scan: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && M > 0, IPSR_ERR_INVALID_ARG, "ipsr_blend_scan: bad dims");
   cudaStream_t st = as_stream(stream);
   IPSR_REQUIRE(C % 32 == 0, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d must be a multiple of 32", C);
   switch (C / 32) {
-    case 1: return launch_scan<1>(staged, vmask, B, M, y, wn, wo, st);
-    case 2: return launch_scan<2>(staged, vmask, B, M, y, wn, wo, st);
-    case 3: return launch_scan<3>(staged, vmask, B, M, y, wn, wo, st);
-    case 4: return launch_scan<4>(staged, vmask, B, M, y, wn, wo, st);
-    case 6: return launch_scan<6>(staged, vmask, B, M, y, wn, wo, st);
-    case 8: return launch_scan<8>(staged, vmask, B, M, y, wn, wo, st);
-    case 12: return launch_scan<12>(staged, vmask, B, M, y, wn, wo, st);
-    case 16: return launch_scan<16>(staged, vmask, B, M, y, wn, wo, st);
-    case 24: return launch_scan<24>(staged, vmask, B, M, y, wn, wo, st);
-    case 32: return launch_scan<32>(staged, vmask, B, M, y, wn, wo, st);
+    case 1: return launch_scan<1>(staged, B, M, y, wn, wo, st);
+    case 2: return launch_scan<2>(staged, B, M, y, wn, wo, st);
+    case 3: return launch_scan<3>(staged, B, M, y, wn, wo, st);
+    case 4: return launch_scan<4>(staged, B, M, y, wn, wo, st);
+    case 6: return launch_scan<6>(staged, B, M, y, wn, wo, st);
+    case 8: return launch_scan<8>(staged, B, M, y, wn, wo, st);
+    case 12: return launch_scan<12>(staged, B, M, y, wn, wo, st);
+    case 16: return launch_scan<16>(staged, B, M, y, wn, wo, st);
+    case 24: return launch_scan<24>(staged, B, M, y, wn, wo, st);
+    case 32: return launch_scan<32>(staged, B, M, y, wn, wo, st);
     default: break;
   }
   set_error("ipsr_blend_scan: C=%d not supported (C/32 must be one of 1,2,3,4,6,8,12,16,24,32)", C);
@@ -247,11 +327,7 @@ extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, co
   using namespace ipsr;
   IPSR_REQUIRE(x && ind && rank && out && (M == 0 || y), IPSR_ERR_INVALID_ARG, "ipsr_paste: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_paste: bad dims");
-  // channel rows per CTA: ~64 KiB of shared memory, at least 1 row
-  int CT = (int)((64 * 1024) / ((size_t)N * sizeof(float)));
-  if (CT < 1) CT = 1;
-  if (CT > 16) CT = 16;
-  if (CT > C) CT = C;
+  const int CT = paste_ct(C, N);
   const size_t smem = (size_t)CT * N * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste: N=%d too large", N);
   static size_t configured = 0;
@@ -262,4 +338,45 @@ extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, co
   }
   paste_kernel<<<dim3((C + CT - 1) / CT, B), 256, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, out);
   return check_launch("ipsr_paste");
+}
+
+extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
+                                           const int32_t* flag, const int32_t* mask_idx, const float* wn, const float* wo,
+                                           int B, int C, int N, int M, float* out,
+                                           int32_t* route_ptr, int32_t* route_q,
+                                           int32_t* exc_start, int32_t* exc_cnt, int32_t* exc_l, float* exc_w,
+                                           int32_t* exc_total, int exc_cap, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(x && ind && rank && out && flag && route_ptr && route_q && (M == 0 || (y && mask_idx)), IPSR_ERR_INVALID_ARG,
+               "ipsr_paste_with_bookkeeping: null pointer");
+  IPSR_REQUIRE(B > 0 && C > 0 && N > 0, IPSR_ERR_INVALID_ARG, "ipsr_paste_with_bookkeeping: bad dims");
+  IPSR_REQUIRE(N <= 16384, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: N=%d > 16384", N);
+  const bool exc = M > 1;
+  if (exc)
+    IPSR_REQUIRE(wn && wo && exc_start && exc_cnt && exc_l && exc_w && exc_total && exc_cap > 0, IPSR_ERR_INVALID_ARG,
+                 "ipsr_paste_with_bookkeeping: exception buffers missing");
+  FusedPasteArgs a;
+  a.x = x; a.y = y; a.ind = ind; a.rank = rank; a.out = out;
+  a.B = B; a.C = C; a.N = N; a.M = M; a.CT = paste_ct(C, N); a.ctiles = (C + a.CT - 1) / a.CT;
+  a.flag = flag; a.mask_idx = mask_idx; a.route_ptr = route_ptr; a.route_q = route_q;
+  a.wn = wn; a.wo = wo; a.exc_start = exc_start; a.exc_cnt = exc_cnt; a.exc_l = exc_l; a.exc_w = exc_w;
+  a.exc_total = exc_total; a.exc_cap = exc_cap;
+  a.n_routes = B;
+  a.exc_per_img = exc ? 1 : 0;
+  a.n_exc = B * a.exc_per_img;
+  size_t smem = (size_t)a.CT * N * sizeof(float);
+  const size_t smem_routes = (size_t)(2 * N + 1) * sizeof(int), smem_exc = ((size_t)N + 3 * kExcChunk) * sizeof(int);
+  if (smem_routes > smem) smem = smem_routes;
+  if (smem_exc > smem) smem = smem_exc;
+  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: N=%d too large", N);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(paste_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste_fused smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const long long ctas = (long long)a.n_routes + a.n_exc + (long long)B * a.ctiles;
+  IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: grid too large");
+  paste_fused_kernel<<<(unsigned)ctas, 256, smem, as_stream(stream)>>>(a);
+  return check_launch("ipsr_paste_with_bookkeeping");
 }

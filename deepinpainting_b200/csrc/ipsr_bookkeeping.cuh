@@ -1,0 +1,204 @@
+// Backward bookkeeping built in the forward: unit routes (stable counting sort by arg-max column)
+// and exception lists (attention entries of blended rows that survive the reference's int64 store).
+// Device bodies live here so that they can run as stand-alone kernels (ipsr_build_routes /
+// ipsr_build_exceptions) and as extra CTAs of the fused paste launch of ipsr_shift_forward.
+#pragma once
+#include "ipsr_common.cuh"
+
+namespace ipsr {
+
+// ---------------------------------------------------------------------------------------------
+// unit routes: stable counting sort of {q : unmasked or q == q_0} by p = ind[q]
+// ---------------------------------------------------------------------------------------------
+// one CTA of 256 threads per image; rsm: (2N+1) ints of shared memory
+__device__ __forceinline__ void
+build_routes_cta(int b, int* rsm, const int* __restrict__ ind, const int* __restrict__ flag, const int* __restrict__ mask_idx,
+                 int N, int M, int* __restrict__ route_ptr, int* __restrict__ route_q) {
+  int* cursor = rsm;            // [N+1] counts -> exclusive offsets -> running cursors
+  int* key = rsm + (N + 1);     // [N]   p = ind[q] for routed q, -1 otherwise
+  __shared__ int warp_tot[8];
+  __shared__ int carry;
+  const int* indb = ind + (size_t)b * N;
+  const int q_first = (M > 0) ? mask_idx[0] : -1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) cursor[i] = 0;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int q = threadIdx.x; q < N; q += blockDim.x) {
+    const bool routed = (flag[q] == 0) || (q == q_first);
+    const int p = routed ? indb[q] : -1;
+    key[q] = p;
+    if (routed) atomicAdd(&cursor[p], 1);
+  }
+  __syncthreads();
+  // exclusive scan of cursor[0..N) in chunks of 256, cursor[N] = total
+  for (int base = 0; base < N; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < N) ? cursor[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int off = carry;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (i < N) cursor[i] = off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += warp_tot[w];
+      carry += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cursor[N] = carry;
+  __syncthreads();
+  int* ptr = route_ptr + (size_t)b * (N + 1);
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) ptr[i] = cursor[i];
+  __syncthreads();
+  // stable fill by one warp: ascending q, duplicates inside a warp step ranked by lane
+  if (warp == 0) {
+    int* rq = route_q + (size_t)b * N;
+    for (int base = 0; base < N; base += 32) {
+      const int q = base + lane;
+      const int p = (q < N) ? key[q] : -1;
+      const bool active = p >= 0;
+      const int mkey = active ? p : -1 - lane;              // inactive lanes never match anybody
+      const unsigned peers = __match_any_sync(0xffffffffu, mkey);
+      const int rnk = __popc(peers & ((1u << lane) - 1u));
+      int start = 0;
+      if (active && rnk == 0) {
+        start = cursor[p];
+        cursor[p] = start + __popc(peers);
+      }
+      start = __shfl_sync(0xffffffffu, start, __ffs(peers) - 1);
+      if (active) rq[start + rnk] = q;
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exceptions: replay row_l[p] = row_{l-1}[p]*wn_l (+ wo_l if p == p_l) -- only columns that are the
+// match of some masked position can ever be non-zero, so the work is one thread per masked position
+// l0 that is the FIRST occurrence of its column p_{l0}, walking l = l0+1 .. M-1.
+// One CTA per image; shared memory: 3*kExcChunk words of staging.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExcChunk = 1024;
+constexpr int kExcThreads = 256;
+
+template <bool WRITE>
+__device__ __forceinline__ int replay_owner(int l0, int p, int M, int base, int n, const float* s_wn, const float* s_wo,
+                                            const int* s_p, float& e, int cnt, int* __restrict__ out_l,
+                                            float* __restrict__ out_w) {
+  // processes steps l in [max(base, l0), base+n) of this chunk
+  int i = max(0, l0 - base);
+  for (; i < n; ++i) {
+    const int l = base + i;
+    if (l == l0) {
+      e = (l0 == 0) ? 1.f : s_wo[i];                       // first appearance: row[p] = 0*wn + wo (or 1 at l = 0)
+    } else {
+      e = __fmul_rn(e, s_wn[i]);                            // row * wn                      :123
+      if (s_p[i] == p) e = __fadd_rn(e, s_wo[i]);           // row[p_l] += wo                :124
+    }
+    if (l >= 1 && !(fabsf(e) < 1.0f)) {                     // survives the int64 store      :134
+      if (WRITE) {
+        out_l[cnt] = l;
+        out_w[cnt] = trunc_as_reference(e);
+      }
+      ++cnt;
+    }
+  }
+  return cnt;
+}
+
+// fsm: first-occurrence table [N] ints, then 3*kExcChunk staging words
+__device__ __forceinline__ void
+build_exceptions_cta(int b, void* fsm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
+                     const float* __restrict__ wn, const float* __restrict__ wo, int N, int M,
+                     int* __restrict__ exc_start, int* __restrict__ exc_cnt, int* __restrict__ exc_l,
+                     float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap) {
+  int* first = reinterpret_cast<int*>(fsm);                 // [N] first masked step whose match is p, or INT_MAX
+  float* s_wn = reinterpret_cast<float*>(first + N);
+  float* s_wo = s_wn + kExcChunk;
+  int* s_p = reinterpret_cast<int*>(s_wo + kExcChunk);
+  const int* ind_b = ind + (size_t)b * N;
+  const float* wnb = wn + (size_t)b * M;
+  const float* wob = wo + (size_t)b * M;
+  for (int p = threadIdx.x; p < N; p += blockDim.x) first[p] = 0x7FFFFFFF;
+  __syncthreads();
+  for (int l = threadIdx.x; l < M; l += blockDim.x) atomicMin(&first[ind_b[mask_idx[l]]], l);
+  __syncthreads();
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {       // default: no exceptions in this column
+    exc_start[(size_t)b * N + p] = 0;
+    exc_cnt[(size_t)b * N + p] = 0;
+  }
+  // A non-finite weight turns EVERY column of the later rows into NaN (0 * inf), which the sparse
+  // "first occurrence" walk below cannot represent: flag the image as overflowed so that the backward
+  // replays the full recurrence per column (bit-faithful, slow, chaotic inputs only).
+  __shared__ int nonfinite_w;
+  if (threadIdx.x == 0) nonfinite_w = 0;
+  int cur_base = -1;                                        // chunk currently staged (uniform)
+  auto stage = [&](int base) {
+    if (base == cur_base) return;
+    __syncthreads();
+    const int n = min(kExcChunk, M - base);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float a = wnb[base + i], c = wob[base + i];
+      s_wn[i] = a;
+      s_wo[i] = c;
+      s_p[i] = ind_b[mask_idx[base + i]];
+      if (!(fabsf(a) <= 3.4028234e38f) || !(fabsf(c) <= 3.4028234e38f)) nonfinite_w = 1;
+    }
+    __syncthreads();
+    cur_base = base;
+  };
+  // owners are processed in rounds of blockDim.x masked positions
+  for (int round = 0; round < M; round += blockDim.x) {
+    const int l0 = round + threadIdx.x;
+    int p = -1;
+    if (l0 < M) {
+      p = ind_b[mask_idx[l0]];
+      if (first[p] != l0) p = -1;                           // not the first occurrence: another thread owns p
+    }
+    const int base0 = (round / kExcChunk) * kExcChunk;
+    // pass 0: count the surviving entries of this column
+    float e = 0.f;
+    int found = 0;
+    for (int base = base0; base < M; base += kExcChunk) {
+      stage(base);
+      if (p >= 0) found = replay_owner<false>(l0, p, M, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, found, nullptr, nullptr);
+    }
+    // reserve a contiguous slot range (placement is arbitrary, order inside is ascending l)
+    int start = 0;
+    bool fits = false;
+    if (p >= 0 && found > 0) {
+      start = atomicAdd(exc_total + b, found);
+      fits = (start + found <= exc_cap);
+      if (fits) {
+        exc_start[(size_t)b * N + p] = start;
+        exc_cnt[(size_t)b * N + p] = found;
+      }
+    }
+    // pass 1 (only when somebody in the CTA has something to write -- uniform decision)
+    if (__syncthreads_or(fits ? 1 : 0)) {
+      if (!fits) p = -1;
+      e = 0.f;
+      int cnt = 0;
+      for (int base = base0; base < M; base += kExcChunk) {
+        stage(base);
+        if (p >= 0)
+          cnt = replay_owner<true>(l0, p, M, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, cnt,
+                                   exc_l + (size_t)b * exc_cap + start, exc_w + (size_t)b * exc_cap + start);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && nonfinite_w) atomicMax(exc_total + b, 0x3FFFFFFF);
+}
+
+}  // namespace ipsr

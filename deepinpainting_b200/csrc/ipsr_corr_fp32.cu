@@ -9,13 +9,15 @@
 namespace ipsr {
 
 constexpr int kFpTile = 64;     // rows x cols per CTA tile
-constexpr int kFpKc = 16;       // channels per shared-memory slab
+constexpr int kFpKc = 32;       // channels per shared-memory slab
 constexpr int kFpThreads = 256;
+constexpr int kFpLd = kFpKc * kFpTile / kFpThreads;   // elements per thread per slab and operand (8)
 
 // grid = (column tiles, row_ctas, B).  A CTA walks the row list of its image in chunks of 64 rows
 // and, for each chunk, computes the 64 x 64 scores against its column tile with register-tiled
 // FFMA (4 x 4 per thread, channels in ascending order), then folds them into packed[b,q] with
-// one 64-bit atomicMax per (row, CTA).
+// one 64-bit atomicMax per (row, CTA).  The next 32-channel slab is fetched into registers while
+// the current one is multiplied (the sparse recheck lists make this kernel latency-bound).
 __global__ void __launch_bounds__(kFpThreads)
 corr_fp32_kernel(const float* __restrict__ x, const float* __restrict__ ref, const float* __restrict__ inv_norm,
                  int C, int N, int col_begin, int col_end,
@@ -23,19 +25,19 @@ corr_fp32_kernel(const float* __restrict__ x, const float* __restrict__ ref, con
   __shared__ __align__(16) float Rs[kFpKc][kFpTile];
   __shared__ __align__(16) float Xs[kFpKc][kFpTile];
   __shared__ int rows[kFpTile];
-  __shared__ float invs[kFpTile];
 
   const int b = blockIdx.z;
   const int nrows = min(nlist[b], N);
+  if ((int)blockIdx.y * kFpTile >= nrows) return;
   const int col0 = col_begin + blockIdx.x * kFpTile;
   const float* xb = x + (size_t)b * C * N;
   const float* rb = ref + (size_t)b * C * N;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-
-  if (threadIdx.x < kFpTile) {
-    const int p = col0 + threadIdx.x;
-    invs[threadIdx.x] = (p < col_end) ? inv_norm[(size_t)b * N + p] : 0.f;
-  }
+  // slab element e of this thread: channel kk = (tid + e*256) / 64 = tid/64 + 4e, column/row jj = tid % 64
+  const int jj = threadIdx.x & 63, kk0 = threadIdx.x >> 6;
+  const int pcol = col0 + jj;
+  const bool pok = pcol < col_end;
+  const float invp = pok ? inv_norm[(size_t)b * N + pcol] : 0.f;
 
   for (int rc = blockIdx.y; rc * kFpTile < nrows; rc += gridDim.y) {
     __syncthreads();
@@ -44,6 +46,7 @@ corr_fp32_kernel(const float* __restrict__ x, const float* __restrict__ ref, con
       rows[threadIdx.x] = (i < nrows) ? list[(size_t)b * N + i] : -1;
     }
     __syncthreads();
+    const int qrow = rows[jj];
 
     float acc[4][4];
 #pragma unroll
@@ -51,20 +54,25 @@ corr_fp32_kernel(const float* __restrict__ x, const float* __restrict__ ref, con
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int c0 = 0; c0 < C; c0 += kFpKc) {
-      // 16 x 64 slabs: 1024 elements each, 4 per thread
+    float rr[kFpLd], xr[kFpLd];
+    auto fetch = [&](int c0) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int id = threadIdx.x + e * kFpThreads;
-        const int kk = id >> 6, jj = id & 63;
-        const int c = c0 + kk;
-        const int q = rows[jj];
-        const int p = col0 + jj;
-        Rs[kk][jj] = (c < C && q >= 0) ? __ldg(rb + (size_t)c * N + q) : 0.f;
+      for (int e = 0; e < kFpLd; ++e) {
+        const int c = c0 + kk0 + 4 * e;
+        rr[e] = (c < C && qrow >= 0) ? __ldg(rb + (size_t)c * N + qrow) : 0.f;
+        xr[e] = (c < C && pok) ? __ldg(xb + (size_t)c * N + pcol) : 0.f;
+      }
+    };
+    fetch(0);
+    for (int c0 = 0; c0 < C; c0 += kFpKc) {
+#pragma unroll
+      for (int e = 0; e < kFpLd; ++e) {
+        Rs[kk0 + 4 * e][jj] = rr[e];
         // Xn = fl(X * inv_norm): the reference normalises the patch first (NPS:40), then correlates
-        Xs[kk][jj] = (c < C && p < col_end) ? __fmul_rn(__ldg(xb + (size_t)c * N + p), invs[jj]) : 0.f;
+        Xs[kk0 + 4 * e][jj] = __fmul_rn(xr[e], invp);
       }
       __syncthreads();
+      if (c0 + kFpKc < C) fetch(c0 + kFpKc);
 #pragma unroll
       for (int kk = 0; kk < kFpKc; ++kk) {
         const float4 rv = *reinterpret_cast<const float4*>(&Rs[kk][ty * 4]);
@@ -98,6 +106,86 @@ corr_fp32_kernel(const float* __restrict__ x, const float* __restrict__ ref, con
       }
       const int q = rows[ty * 4 + i];
       if (tx == 0 && q >= 0 && key != kPackedIdentity) atomicMax(packed + (size_t)b * N + q, key);
+    }
+  }
+}
+
+// Sparse variant for the recheck lists of the tensor mode (a handful of rows per image): the dense
+// kernel above would multiply 64-row tiles that are 95 % padding.  grid = (column tiles of 64, B);
+// 256 threads = 64 bank columns x 4 channel quarters; rows are taken 8 at a time (R rows staged in
+// shared memory, broadcast reads), the four quarter sums are added in fixed order.
+constexpr int kSkCols = 64;
+constexpr int kSkRows = 8;
+
+__global__ void __launch_bounds__(256)
+corr_fp32_sparse_kernel(const float* __restrict__ x, const float* __restrict__ ref, const float* __restrict__ inv_norm,
+                        int C, int N, int col_begin, int col_end,
+                        const int* __restrict__ list, const int* __restrict__ nlist, long long* __restrict__ packed) {
+  extern __shared__ __align__(16) float sk_smem[];
+  float* Rs = sk_smem;                                   // [C][8]
+  float* red = sk_smem + (size_t)C * kSkRows;            // [4][64][8]
+  __shared__ int rows[kSkRows];
+  const int b = blockIdx.y;
+  const int nrows = min(nlist[b], N);
+  if (nrows == 0) return;
+  const int j = threadIdx.x & 63, kg = threadIdx.x >> 6;
+  const int p = col_begin + blockIdx.x * kSkCols + j;
+  const bool pok = p < col_end;
+  const float* xb = x + (size_t)b * C * N;
+  const float* rb = ref + (size_t)b * C * N;
+  const float invp = pok ? inv_norm[(size_t)b * N + p] : 0.f;
+  const int cq = (C + 3) / 4;                            // channels per quarter
+  const int cbeg = kg * cq, cend = min(C, cbeg + cq);
+
+  for (int r0 = 0; r0 < nrows; r0 += kSkRows) {
+    __syncthreads();
+    if (threadIdx.x < kSkRows) rows[threadIdx.x] = (r0 + threadIdx.x < nrows) ? list[(size_t)b * N + r0 + threadIdx.x] : -1;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < C * kSkRows; idx += blockDim.x) {
+      const int c = idx >> 3, i = idx & 7;
+      const int q = rows[i];
+      Rs[idx] = (q >= 0) ? __ldg(rb + (size_t)c * N + q) : 0.f;
+    }
+    __syncthreads();
+    float acc[kSkRows];
+#pragma unroll
+    for (int i = 0; i < kSkRows; ++i) acc[i] = 0.f;
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+      float xv[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) xv[u] = (pok && c0 + u < cend) ? __ldg(xb + (size_t)(c0 + u) * N + p) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (c0 + u < cend) {
+          const float xn = __fmul_rn(xv[u], invp);       // Xn = fl(X * inv_norm)   (NPS:40)
+          const float4 ra = *reinterpret_cast<const float4*>(Rs + (size_t)(c0 + u) * kSkRows);
+          const float4 rc = *reinterpret_cast<const float4*>(Rs + (size_t)(c0 + u) * kSkRows + 4);
+          acc[0] = fmaf(ra.x, xn, acc[0]); acc[1] = fmaf(ra.y, xn, acc[1]);
+          acc[2] = fmaf(ra.z, xn, acc[2]); acc[3] = fmaf(ra.w, xn, acc[3]);
+          acc[4] = fmaf(rc.x, xn, acc[4]); acc[5] = fmaf(rc.y, xn, acc[5]);
+          acc[6] = fmaf(rc.z, xn, acc[6]); acc[7] = fmaf(rc.w, xn, acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kSkRows; ++i) red[((size_t)kg * kSkCols + j) * kSkRows + i] = acc[i];
+    __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+      for (int i = 0; i < kSkRows; ++i) {
+        float sum = red[(size_t)j * kSkRows + i];
+        sum += red[((size_t)1 * kSkCols + j) * kSkRows + i];
+        sum += red[((size_t)2 * kSkCols + j) * kSkRows + i];
+        sum += red[((size_t)3 * kSkCols + j) * kSkRows + i];
+        long long key = pok ? pack_maxidx(sum, p) : kPackedIdentity;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other > key ? other : key;
+        }
+        const int q = rows[i];
+        if ((threadIdx.x & 31) == 0 && q >= 0 && key != kPackedIdentity) atomicMax(packed + (size_t)b * N + q, key);
+      }
     }
   }
 }
@@ -196,8 +284,20 @@ extern "C" int ipsr_correlate_argmax_fp32(const float* x, const float* ref, cons
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && col_begin >= 0 && col_end <= N && col_begin < col_end, IPSR_ERR_INVALID_ARG,
                "ipsr_correlate_argmax_fp32: bad dims B=%d C=%d N=%d cols=[%d,%d)", B, C, N, col_begin, col_end);
   IPSR_REQUIRE(B <= 65535, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_fp32: B=%d > 65535", B);
+  if (row_ctas <= 0) {
+    // sparse row lists (tensor-mode recheck)
+    const size_t smem = ((size_t)C * kSkRows + 4 * (size_t)kSkCols * kSkRows) * sizeof(float);
+    IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_fp32: C=%d too large", C);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(corr_fp32_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_fp32_sparse smem attribute: %s", cudaGetErrorString(e));
+    }
+    dim3 grid((col_end - col_begin + kSkCols - 1) / kSkCols, B);
+    corr_fp32_sparse_kernel<<<grid, 256, smem, as_stream(stream)>>>(x, ref, inv_norm, C, N, col_begin, col_end, recheck_list,
+                                                                     nrecheck, reinterpret_cast<long long*>(packed));
+    return check_launch("ipsr_correlate_argmax_fp32");
+  }
   const int max_ctas = (N + kFpTile - 1) / kFpTile;
-  if (row_ctas < 1) row_ctas = 1;
   if (row_ctas > max_ctas) row_ctas = max_ctas;
   dim3 grid((col_end - col_begin + kFpTile - 1) / kFpTile, row_ctas, B);
   corr_fp32_kernel<<<grid, kFpThreads, 0, as_stream(stream)>>>(x, ref, inv_norm, C, N, col_begin, col_end,

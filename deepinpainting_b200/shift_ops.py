@@ -230,9 +230,7 @@ def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Opti
     n += 2                                  # correlate_fp32 + apply_recheck
     if M > 0:
         n += 2                              # blend_stage + blend_scan
-    if need_grad:
-        n += 1 + (1 if M > 1 else 0)        # build_routes (+ build_exceptions)
-    n += 1                                  # paste
+    n += 1                                  # paste (+ routes / exceptions builders in the same launch)
     if backward:
         n += 1                              # shift_bwd
     return n

@@ -112,7 +112,8 @@ int ipsr_select_all_rows(int B, int N, int32_t* recheck_list, int32_t* nrecheck,
  * fp32 arithmetic) for the rows in recheck_list over bank columns [col_begin, col_end):
  * packed[b,q] = max(packed[b,q], pack(score, col)) with the order-preserving packing of
  * ipsr_pack_maxidx (largest score wins, lowest index on ties, NaN wins -- torch.max).
- * row_ctas: CTAs cooperating over the row list of one image (1..N/64). */
+ * row_ctas >= 1: dense kernel (64 x 64 register tiles), that many CTAs cooperate over the row list of
+ * one image; row_ctas <= 0: sparse kernel for short lists (8 rows at a time against 64 columns). */
 int ipsr_correlate_argmax_fp32(const float* x, const float* ref, const float* inv_norm,
                                int B, int C, int N, int col_begin, int col_end,
                                const int32_t* recheck_list, const int32_t* nrecheck, int row_ctas,
@@ -142,18 +143,21 @@ int ipsr_maxcoord(const float* s, int P, int L, int64_t* ind_i64, float* vmax, v
 
 /* Stage the operands of the sequential blend, one warp per masked position l
  * (q_l = mask_idx[l], p_l = ind[b,q_l]):
- *   staged[b,l,0,:] = u_l = X[q_l] * inv_norm[q_l]      (IPSRFunction.py:109)
- *   staged[b,l,1,:] = X[p_l]                             (known_region, :95)
- *   vmask[b,l]      = <R[q_l], Xn[p_l]>  exact fp32      (vmax at masked positions, :70)  */
+ *   staged[b,l,0:C]    = u_l = X[q_l] * inv_norm[q_l]   (IPSRFunction.py:109)
+ *   staged[b,l,C:2C]   = X[p_l]                          (known_region, :95)
+ *   staged[b,l,2C]     = v_l = <R[q_l], Xn[p_l]>  exact fp32 (vmax at masked positions, :70)
+ * staged is [B][M][ipsr_staged_stride(C)]; vmask [B,M] (optional copy of v_l, may be NULL).  */
 int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
                      const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
                      float* staged, float* vmask, void* stream);
+/* floats per staged step: 2*C + 4 (u_l, X[p_l], then v_l and three pad floats) */
+int ipsr_staged_stride(int C);
 
 /* The recurrence itself: one warp per image, operands streamed through shared memory by bulk
  * async copies.  l=0: y_0 = X[p_0] (:98-101);  l>0: a = <u_l, y_{l-1}>; wn = a/(a+v);
  * wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).
  * Writes y [B,M,C], wn/wo [B,M] (wn[b,0] = 0, wo[b,0] = 1). */
-int ipsr_blend_scan(const float* staged, const float* vmask, int B, int C, int M,
+int ipsr_blend_scan(const float* staged, int B, int C, int M,
                     float* y, float* wn, float* wo, void* stream);
 
 /* out[b,:,q] = y[b,rank[q],:] for masked q, x[b,:,ind[b,q]] otherwise (replaces the dense
@@ -191,6 +195,16 @@ int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
                    const int32_t* exc_total, int exc_cap,
                    const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
                    float triple_w, float* gin, void* stream);
+
+/* ipsr_paste + ipsr_build_routes + ipsr_build_exceptions as ONE launch (the three are independent
+ * once the scan has finished; the latency-bound builders overlap the bandwidth-bound paste).
+ * exc_total must be zero on entry. */
+int ipsr_paste_with_bookkeeping(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
+                                const int32_t* flag, const int32_t* mask_idx, const float* wn, const float* wo,
+                                int B, int C, int N, int M, float* out,
+                                int32_t* route_ptr, int32_t* route_q,
+                                int32_t* exc_start, int32_t* exc_cnt, int32_t* exc_l, float* exc_w,
+                                int32_t* exc_total, int exc_cap, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * InnerCos / InnerCos2   (models/InnerCos.py:30-36, models/InnerCos2.py:34-41)

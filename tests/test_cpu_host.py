@@ -67,7 +67,7 @@ def test_argument_validation_without_gpu():
     """Launchers validate before touching the device: bad arguments give negative codes + a message."""
     from deepinpainting_b200 import _lib
     lib = _lib.load()
-    assert lib.ipsr_blend_scan(None, None, 1, 32, 4, None, None, None, None) == -1
+    assert lib.ipsr_blend_scan(None, 1, 32, 4, None, None, None, None) == -1
     assert "null" in _lib.last_error()
     args = _lib.FwdArgs()
     assert lib.ipsr_shift_forward(ctypes.byref(args), None) == -1
