@@ -356,16 +356,19 @@ def run_ours(args):
         e2e_step(i)
     sync_all()
     t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(s_in)                                         # first operation of the region: the first H2D copy
     for i in range(EK):
         e2e_step(i)
-    sync_all()                                              # every copy-out has landed in host memory
+    f1.record(s_out)                                        # last operation: the last D2H copy has landed
+    sync_all()
     wall = time.perf_counter() - t0
-    te = torch.tensor([wall], dtype=torch.float64, device=dev)
+    te = torch.tensor([f0.elapsed_time(f1) * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * EK / float(te.item())
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * B * C * N * 4, "d2h_bytes_per_step": 2 * B * C * N * 4,
-           "steps": EK, "wall_s": wall, "timing": "host wall clock around EK steps incl. final sync (3 streams overlap H2D / compute / D2H)",
+           "steps": EK, "wall_s": wall, "timing": "CUDA events: first H2D copy -> last D2H copy of the region, max over ranks (3 streams overlap H2D / compute / D2H)",
            "api": "IPSR_model.forward + autograd backward, pinned host buffers"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----

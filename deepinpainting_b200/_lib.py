@@ -56,6 +56,7 @@ SIGNATURES = {
     "ipsr_maxcoord": (_i, [_p, _i, _i, _p, _p, _p]),
     "ipsr_blend_stage": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "ipsr_staged_stride": (_i, [_i]),
+    "ipsr_padded_steps": (_i, [_i]),
     "ipsr_blend_scan": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "ipsr_paste_with_bookkeeping": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "ipsr_paste": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),

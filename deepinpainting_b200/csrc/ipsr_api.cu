@@ -62,7 +62,7 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
   w.r_masked = take(cur, BM * C * 4);
   w.staged = take(cur, BM * (size_t)(2 * C + 4) * 4);
   w.vmask = take(cur, BM * 4);
-  w.y = take(cur, BM * C * 4);
+  w.y = take(cur, (size_t)B * (size_t)((M + 7) & ~7) * C * 4 + 256);
   w.packed = take(cur, BN * 8);
   w.list = take(cur, BN * 4);
   w.tensor = (resolve_mode(mode, C, N) == IPSR_MODE_TENSOR);

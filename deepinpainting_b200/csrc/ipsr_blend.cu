@@ -17,6 +17,8 @@ namespace ipsr {
 
 // one staged step: u_l [C], X[p_l] [C], then v_l, c_l = <u_l, X[p_{l-1}]> and 2 pad floats (16-byte sized)
 __host__ __device__ inline int staged_stride(int C) { return 2 * C + 4; }
+// rows of y per image: M rounded up to the unroll depth of the scan (tail steps store into the padding)
+__host__ __device__ inline int padded_steps(int M) { return (M + 7) & ~7; }
 
 // ---------------------------------------------------------------------------------------------
 // stage
@@ -72,27 +74,45 @@ blend_stage_kernel(const float* __restrict__ xt, const float* __restrict__ r_mas
 // ---------------------------------------------------------------------------------------------
 // scan
 // ---------------------------------------------------------------------------------------------
-constexpr int kScanStages = 8;
+constexpr int kScanStages = 4;      // ring depth
+constexpr int kScanSteps = 8;       // recurrence steps per ring stage (the inner loop is fully unrolled)
 
-// VPL = C / 32 values per lane; lane owns channels lane + 32*i (conflict-free smem reads,
-// 128-byte coalesced y stores).  One stage = `steps_per_stage` consecutive steps = contiguous bytes
-// of `staged`, fetched by one bulk copy.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// VPL = C / 32 values per lane; lane owns channels lane + 32*i (conflict-free smem reads, 128-byte
+// coalesced y stores).  One warp per image; one ring stage = 8 consecutive steps = contiguous bytes of
+// `staged`, fetched by one bulk copy.
+//
+// The warp is alone on its scheduler, so every dependent instruction costs its full latency: the loop
+// body is branch-free straight-line code (8 steps unrolled) and uses the two-step form of the
+// recurrence so that independent work fills the latency of the 32-lane reductions.
+//   reference (IPSRFunction.py:116-122):  a_l = <u_l, y_{l-1}>,  y_l = wn_l y_{l-1} + wo_l X[p_l]
+//   by linearity:  a_l = wn_{l-1} <u_l, y_{l-2}> + wo_{l-1} c_l,   c_l = <u_l, X[p_{l-1}]>  (staged)
+// so the reduction for step l+1 (needs only y_{l-1}) overlaps the scalar chain of step l.  With
+// y_{-1} = 0, wn_0 = 0, wo_0 = 1 steps 0 and 1 are regular.  Differences to the one-step form are
+// rounding-level (and wn, wo use a * rcp(a+v): <= 2 ulp from the reference's IEEE divisions).
 template <int VPL>
 __global__ void __launch_bounds__(32)
-blend_scan_kernel(const float* __restrict__ staged, int M, int steps_per_stage,
+blend_scan_kernel(const float* __restrict__ staged, int M,
                   float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out) {
   extern __shared__ __align__(128) uint8_t scan_smem[];
   __shared__ __align__(8) unsigned long long bars[kScanStages];
   constexpr int C = VPL * 32;
+  constexpr int kStride = 2 * C + 4;
+  constexpr uint32_t kStepBytes = (uint32_t)kStride * sizeof(float);
+  constexpr uint32_t kStageBytes = kStepBytes * kScanSteps;
   const int b = blockIdx.x;
   const int lane = threadIdx.x;
   const uint32_t ring = smem_u32(scan_smem);
-  constexpr int kStride = 2 * C + 4;
-  const uint32_t step_bytes = (uint32_t)kStride * sizeof(float);
-  const uint32_t stage_bytes = step_bytes * steps_per_stage;
   const float* src = staged + (size_t)b * M * kStride;
-  float* yb = y + (size_t)b * M * C;
-  const int nchunks = (M + steps_per_stage - 1) / steps_per_stage;
+  float* yb = y + (size_t)b * padded_steps(M) * C;
+  float* wnb = wn_out + (size_t)b * M;
+  float* wob = wo_out + (size_t)b * M;
+  const int nchunks = (M + kScanSteps - 1) / kScanSteps;
 
   if (lane == 0) {
     for (int s = 0; s < kScanStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
@@ -101,47 +121,39 @@ blend_scan_kernel(const float* __restrict__ staged, int M, int steps_per_stage,
   __syncwarp();
   auto issue = [&](int chunk) {
     const int s = chunk % kScanStages;
-    const int l0 = chunk * steps_per_stage;
-    const uint32_t bytes = step_bytes * (uint32_t)min(steps_per_stage, M - l0);
+    const int l0 = chunk * kScanSteps;
+    const uint32_t bytes = kStepBytes * (uint32_t)min(kScanSteps, M - l0);
     mbar_expect_tx(smem_u32(&bars[s]), bytes);
-    bulk_g2s(ring + (uint32_t)s * stage_bytes, src + (size_t)l0 * kStride, bytes, smem_u32(&bars[s]));
+    bulk_g2s(ring + (uint32_t)s * kStageBytes, src + (size_t)l0 * kStride, bytes, smem_u32(&bars[s]));
   };
   if (lane == 0)
     for (int ch = 0; ch < min(nchunks, kScanStages); ++ch) issue(ch);
 
-  // Two-step form of the recurrence.  The reference computes a_l = <u_l, y_{l-1}> (IPSRFunction.py:116)
-  // with y_{l-1} = wn_{l-1} y_{l-2} + wo_{l-1} X[p_{l-1}] (:122); by linearity
-  //     a_l = wn_{l-1} * <u_l, y_{l-2}> + wo_{l-1} * c_l,      c_l = <u_l, X[p_{l-1}]> (staged),
-  // so the 32-lane reduction of step l+1 (it only needs y_{l-1}) runs while step l resolves its
-  // scalar chain, instead of the two being serialised.  y_{-1} = 0, wn_0 = 0, wo_0 = 1 make l = 0 and
-  // l = 1 regular: y_0 = X[p_0], a_1 = c_1.  Differs from the one-step form by rounding only.
   float y1[VPL];                       // y_{l-1}
 #pragma unroll
   for (int i = 0; i < VPL; ++i) y1[i] = 0.f;
   float d = 0.f;                       // <u_l, y_{l-2}>
   float wn_prev = 0.f, wo_prev = 1.f;
+  mbar_wait(smem_u32(&bars[0]), 0);
   for (int ch = 0; ch < nchunks; ++ch) {
     const int s = ch % kScanStages;
-    mbar_wait(smem_u32(&bars[s]), (uint32_t)(ch / kScanStages) & 1u);
-    const float* st = reinterpret_cast<const float*>(scan_smem + (size_t)s * stage_bytes);
-    const int l0 = ch * steps_per_stage;
-    const int nl = min(steps_per_stage, M - l0);
-    for (int j = 0; j < nl; ++j) {
+    const float* st = reinterpret_cast<const float*>(scan_smem + (size_t)s * kStageBytes);
+    // the last step of this chunk looks one step ahead: the next stage must have landed too
+    const float* st_next = st;
+    if (ch + 1 < nchunks) {
+      const int s2 = (ch + 1) % kScanStages;
+      mbar_wait(smem_u32(&bars[s2]), (uint32_t)((ch + 1) / kScanStages) & 1u);
+      st_next = reinterpret_cast<const float*>(scan_smem + (size_t)s2 * kStageBytes);
+    }
+    const int l0 = ch * kScanSteps;
+#pragma unroll
+    for (int j = 0; j < kScanSteps; ++j) {
       const int l = l0 + j;
-      const float* u = st + (size_t)j * kStride;
+      const bool live = l < M;                               // tail steps compute on stale smem into y's padding
+      const float* u = st + j * kStride;
       const float* k = u + C;
-      // u of the NEXT step: same stage, or the first step of the next stage (it has landed or we wait)
-      const float* un = u + kStride;
-      if (j + 1 == nl) {
-        if (l + 1 < M) {
-          const int s2 = (ch + 1) % kScanStages;
-          mbar_wait(smem_u32(&bars[s2]), (uint32_t)((ch + 1) / kScanStages) & 1u);
-          un = reinterpret_cast<const float*>(scan_smem + (size_t)s2 * stage_bytes);
-        } else {
-          un = u;                                            // last step: value unused
-        }
-      }
-      // (1) independent of this step's weights: d_{l+1} = <u_{l+1}, y_{l-1}>
+      const float* un = (j + 1 < kScanSteps) ? (u + kStride) : st_next;
+      // (1) d_{l+1} = <u_{l+1}, y_{l-1}>: independent of this step's weights
       float p0 = 0.f, p1 = 0.f;
 #pragma unroll
       for (int i = 0; i < VPL; i += 2) {
@@ -150,28 +162,20 @@ blend_scan_kernel(const float* __restrict__ staged, int M, int steps_per_stage,
       }
       const float dn = warp_sum(p0 + p1);
       // (2) scalar chain of step l
-      const float v = u[2 * C], c = u[2 * C + 1];
-      float wn, wo;
-      if (l == 0) {
-        wn = 0.f;                                            // first masked patch: plain copy   :98-101
-        wo = 1.f;
-      } else {
-        const float a = fmaf(wn_prev, d, __fmul_rn(wo_prev, c));
-        const float den = __fadd_rn(a, v);
-        wn = __fdiv_rn(a, den);                              // no clamp, inf/nan propagate      :120
-        wo = __fdiv_rn(v, den);                              //                                    :121
+      const float2 vc = *reinterpret_cast<const float2*>(u + 2 * C);     // v_l, c_l
+      const float a = fmaf(wn_prev, d, __fmul_rn(wo_prev, vc.y));
+      const float r = rcp_approx(__fadd_rn(a, vc.x));         // no clamp: inf / nan propagate      :120
+      const float wn = (l == 0) ? 0.f : __fmul_rn(a, r);      // first masked patch: plain copy      :98-101
+      const float wo = (l == 0) ? 1.f : __fmul_rn(vc.x, r);   //                                       :121
+      // (3) y_l = wn y_{l-1} + wo X[p_l]: two rounded products, one sum                              :122
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) y1[i] = __fadd_rn(__fmul_rn(wn, y1[i]), __fmul_rn(wo, k[lane + 32 * i]));
+      if (live && lane == 0) {
+        wnb[l] = wn;
+        wob[l] = wo;
       }
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {                         // two rounded products, one sum      :122
-        const float kv = k[lane + 32 * i];
-        y1[i] = (l == 0) ? kv : __fadd_rn(__fmul_rn(wn, y1[i]), __fmul_rn(wo, kv));
-      }
-      if (lane == 0) {
-        wn_out[(size_t)b * M + l] = wn;
-        wo_out[(size_t)b * M + l] = wo;
-      }
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) yb[(size_t)l * C + lane + 32 * i] = y1[i];
+      for (int i = 0; i < VPL; ++i) yb[(size_t)l * C + lane + 32 * i] = y1[i];    // y is padded to 8 steps
       d = dn;
       wn_prev = wn;
       wo_prev = wo;
@@ -210,7 +214,7 @@ paste_cta(int cx, int b, float* rows, const float* __restrict__ x, const float* 
       const int p = indb[q];
       for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = rows[ch * N + p];
     } else {
-      const float* yr = y + ((size_t)b * M + l) * C + c0;
+      const float* yr = y + ((size_t)b * padded_steps(M) + l) * C + c0;
       for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = __ldg(yr + ch);
     }
   }
@@ -264,6 +268,7 @@ static int paste_ct(int C, int N) {
 }  // namespace ipsr
 
 extern "C" int ipsr_staged_stride(int C) { return ipsr::staged_stride(C); }
+extern "C" int ipsr_padded_steps(int M) { return ipsr::padded_steps(M); }
 
 extern "C" int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
                                 const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
@@ -281,18 +286,15 @@ extern "C" int ipsr_blend_stage(const float* xt, const float* r_masked, const fl
 
 namespace ipsr {
 template <int VPL>
-static int launch_scan(const float* staged, int B, int M, float* y, float* wn, float* wo,
-                       cudaStream_t st) {
+static int launch_scan(const float* staged, int B, int M, float* y, float* wn, float* wo, cudaStream_t st) {
   constexpr int C = VPL * 32;
-  const size_t step_bytes = (size_t)staged_stride(C) * sizeof(float);
-  int sps = (int)(8192 / step_bytes);                     // ~8 KiB per stage
-  if (sps < 1) sps = 1;
-  const size_t smem = (size_t)kScanStages * sps * step_bytes;
+  const size_t smem = (size_t)kScanStages * kScanSteps * staged_stride(C) * sizeof(float);
+  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
   }
-  blend_scan_kernel<VPL><<<B, 32, smem, st>>>(staged, M, sps, y, wn, wo);
+  blend_scan_kernel<VPL><<<B, 32, smem, st>>>(staged, M, y, wn, wo);
   return check_launch("ipsr_blend_scan");
 }
 }  // namespace ipsr

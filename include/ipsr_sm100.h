@@ -152,15 +152,18 @@ int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_no
                      float* staged, float* vmask, void* stream);
 /* floats per staged step: 2*C + 4 (u_l, X[p_l], then v_l and three pad floats) */
 int ipsr_staged_stride(int C);
+/* rows of y per image: M rounded up to a multiple of 8 (the scan's unroll depth) */
+int ipsr_padded_steps(int M);
 
 /* The recurrence itself: one warp per image, operands streamed through shared memory by bulk
  * async copies.  l=0: y_0 = X[p_0] (:98-101);  l>0: a = <u_l, y_{l-1}>; wn = a/(a+v);
  * wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).
- * Writes y [B,M,C], wn/wo [B,M] (wn[b,0] = 0, wo[b,0] = 1). */
+ * Writes y [B][ipsr_padded_steps(M)][C], wn/wo [B,M] (wn[b,0] = 0, wo[b,0] = 1). */
 int ipsr_blend_scan(const float* staged, int B, int C, int M,
                     float* y, float* wn, float* wo, void* stream);
 
-/* out[b,:,q] = y[b,rank[q],:] for masked q, x[b,:,ind[b,q]] otherwise (replaces the dense
+/* out[b,:,q] = y[b,rank[q],:] (y laid out [B][ipsr_padded_steps(M)][C]) for masked q,
+ * x[b,:,ind[b,q]] otherwise (replaces the dense
  * conv_transpose of IPSRFunction.py:131). */
 int ipsr_paste(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
                int B, int C, int N, int M, float* out, void* stream);
