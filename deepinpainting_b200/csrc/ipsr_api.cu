@@ -60,7 +60,8 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
   w.counters = take(cur, (size_t)2 * B * 4);
   w.xt = take(cur, BN * C * 4);
   w.r_masked = take(cur, BM * C * 4);
-  w.staged = take(cur, BM * (size_t)(2 * C + 4) * 4);
+  w.staged = take(cur, (size_t)B * (size_t)((M + ipsr_scan_block_steps(C) - 1) / ipsr_scan_block_steps(C) + 1) *
+                            (size_t)ipsr_staged_block_floats(C) * 4);
   w.vmask = take(cur, BM * 4);
   w.y = take(cur, (size_t)B * (size_t)((M + 7) & ~7) * C * 4 + 256);
   w.packed = take(cur, BN * 8);

@@ -15,173 +15,279 @@
 
 namespace ipsr {
 
-// one staged step: u_l [C], X[p_l] [C], then v_l, c_l = <u_l, X[p_{l-1}]> and 2 pad floats (16-byte sized)
-__host__ __device__ inline int staged_stride(int C) { return 2 * C + 4; }
-// rows of y per image: M rounded up to the unroll depth of the scan (tail steps store into the padding)
+// Steps are processed in blocks of T consecutive masked positions (T = scan_block_steps(C)).  One staged
+// block = everything the scan needs for T steps, contiguous, so that ONE bulk copy fetches it:
+//   U  [T][C]  u_l = X[q_l] * inv_norm[q_l]                       (IPSRFunction.py:109)
+//   K  [T][C]  X[p_l], the matched bank patch                     (:95)
+//   Gt [T][T]  Gt[j][i] = <u_{l0+i}, X[p_{l0+j}>                  (in-block Gram matrix, transposed)
+//   v  [T]     v_l = <R[q_l], Xn[p_l]>  exact fp32                (vmax at masked positions, :70)
+__host__ __device__ inline int scan_block_steps(int C) { return C <= 256 ? 32 : (C <= 512 ? 16 : 8); }
+__host__ __device__ inline int staged_block_floats(int C) {
+  const int T = scan_block_steps(C);
+  return 2 * T * C + T * T + T;
+}
+// rows of y per image: M rounded up to a multiple of 8
 __host__ __device__ inline int padded_steps(int M) { return (M + 7) & ~7; }
 
 // ---------------------------------------------------------------------------------------------
-// stage
+// stage: grid = (ceil(M / T), B), 256 threads.
+//   phase 1  one warp per step: gather u_l, X[p_l] (to shared memory and to the staged block) and v_l;
+//   phase 2  the T x T Gram matrix of the block from shared memory, 2 x 2 register tiles, the channel
+//            range split over 256 / (T/2)^2 thread groups whose partial sums are added in fixed order.
 // ---------------------------------------------------------------------------------------------
+template <int T>
 __global__ void __launch_bounds__(256)
 blend_stage_kernel(const float* __restrict__ xt, const float* __restrict__ r_masked, const float* __restrict__ inv_norm,
                    const int* __restrict__ ind, const int* __restrict__ mask_idx, int C, int N, int M,
                    float* __restrict__ staged, float* __restrict__ vmask) {
+  extern __shared__ __align__(16) float stage_smem[];
+  constexpr int kTiles = (T / 2) * (T / 2);              // 2 x 2 output tiles
+  constexpr int kSplit = 256 / kTiles;                   // channel groups (1, 4 or 16)
+  const int ld = C + 4;                                  // padded row: conflict-free float4 reads across rows
+  float* Us = stage_smem;                                // [T][ld]
+  float* Ks = Us + (size_t)T * ld;                       // [T][ld]
+  float* red = Ks + (size_t)T * ld;                      // [kSplit][T*T] (kSplit > 1 only)
   const int b = blockIdx.y;
-  const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (l >= M) return;
-  const int q = mask_idx[l];
-  const int p = ind[(size_t)b * N + q];
-  const float inv_q = inv_norm[(size_t)b * N + q];
-  const float inv_p = inv_norm[(size_t)b * N + p];
-  const float* xq = xt + ((size_t)b * N + q) * C;
-  const float* xp = xt + ((size_t)b * N + p) * C;
-  const float* rq = r_masked + ((size_t)b * M + l) * C;
-  // matched patch of the PREVIOUS masked position: c_l = <u_l, X[p_{l-1}]> feeds the two-step
-  // form of the recurrence used by the scan (a_l = wn_{l-1} <u_l, y_{l-2}> + wo_{l-1} c_l)
-  const float* xk = xt + ((size_t)b * N + (l > 0 ? ind[(size_t)b * N + mask_idx[l - 1]] : p)) * C;
-  float* su = staged + ((size_t)b * M + l) * staged_stride(C);
-  float* sp = su + C;
-  float acc = 0.f, cacc = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(xq + c));
-    const float4 k = __ldg(reinterpret_cast<const float4*>(xp + c));
-    const float4 r = __ldg(reinterpret_cast<const float4*>(rq + c));
-    const float4 kp = __ldg(reinterpret_cast<const float4*>(xk + c));
-    cacc = fmaf(__fmul_rn(a.x, inv_q), kp.x, cacc);
-    cacc = fmaf(__fmul_rn(a.y, inv_q), kp.y, cacc);
-    cacc = fmaf(__fmul_rn(a.z, inv_q), kp.z, cacc);
-    cacc = fmaf(__fmul_rn(a.w, inv_q), kp.w, cacc);
-    // u = little_value * (1/(norm+1e-8))                          IPSRFunction.py:109
-    *reinterpret_cast<float4*>(su + c) =
-        make_float4(__fmul_rn(a.x, inv_q), __fmul_rn(a.y, inv_q), __fmul_rn(a.z, inv_q), __fmul_rn(a.w, inv_q));
-    *reinterpret_cast<float4*>(sp + c) = k;
-    // v = <R[q], Xn[p]> with Xn = fl(X * inv) as the encoder weights hold it (NPS:40)
-    acc = fmaf(r.x, __fmul_rn(k.x, inv_p), acc);
-    acc = fmaf(r.y, __fmul_rn(k.y, inv_p), acc);
-    acc = fmaf(r.z, __fmul_rn(k.z, inv_p), acc);
-    acc = fmaf(r.w, __fmul_rn(k.w, inv_p), acc);
+  const int nblocks = gridDim.x;
+  const int l0 = blockIdx.x * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* blk = staged + ((size_t)b * nblocks + blockIdx.x) * staged_block_floats(C);
+  float* gU = blk;
+  float* gK = blk + (size_t)T * C;
+  float* gG = gK + (size_t)T * C;
+  float* gV = gG + T * T;
+
+  for (int r = warp; r < T; r += 8) {
+    const int l = l0 + r;
+    float* su = Us + (size_t)r * ld;
+    float* sk = Ks + (size_t)r * ld;
+    if (l >= M) {                                        // tail of the last block: inert steps
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(su + c) = z4;
+        *reinterpret_cast<float4*>(sk + c) = z4;
+        *reinterpret_cast<float4*>(gU + (size_t)r * C + c) = z4;
+        *reinterpret_cast<float4*>(gK + (size_t)r * C + c) = z4;
+      }
+      if (lane == 0) gV[r] = 1.f;
+      continue;
+    }
+    const int q = mask_idx[l];
+    const int p = ind[(size_t)b * N + q];
+    const float inv_q = inv_norm[(size_t)b * N + q];
+    const float inv_p = inv_norm[(size_t)b * N + p];
+    const float* xq = xt + ((size_t)b * N + q) * C;
+    const float* xp = xt + ((size_t)b * N + p) * C;
+    const float* rq = r_masked + ((size_t)b * M + l) * C;
+    float acc = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xq + c));
+      const float4 k = __ldg(reinterpret_cast<const float4*>(xp + c));
+      const float4 rr = __ldg(reinterpret_cast<const float4*>(rq + c));
+      // u = little_value * (1/(norm+1e-8))                          IPSRFunction.py:109
+      const float4 u = make_float4(__fmul_rn(a.x, inv_q), __fmul_rn(a.y, inv_q), __fmul_rn(a.z, inv_q), __fmul_rn(a.w, inv_q));
+      *reinterpret_cast<float4*>(su + c) = u;
+      *reinterpret_cast<float4*>(sk + c) = k;
+      *reinterpret_cast<float4*>(gU + (size_t)r * C + c) = u;
+      *reinterpret_cast<float4*>(gK + (size_t)r * C + c) = k;
+      // v = <R[q], Xn[p]> with Xn = fl(X * inv) as the encoder weights hold it (NPS:40)
+      acc = fmaf(rr.x, __fmul_rn(k.x, inv_p), acc);
+      acc = fmaf(rr.y, __fmul_rn(k.y, inv_p), acc);
+      acc = fmaf(rr.z, __fmul_rn(k.z, inv_p), acc);
+      acc = fmaf(rr.w, __fmul_rn(k.w, inv_p), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      gV[r] = acc;
+      if (vmask) vmask[(size_t)b * M + l] = acc;
+    }
   }
-  acc = warp_sum(acc);
-  cacc = warp_sum(cacc);
-  if (lane == 0) {
-    *reinterpret_cast<float4*>(su + 2 * C) = make_float4(acc, cacc, 0.f, 0.f);
-    if (vmask) vmask[(size_t)b * M + l] = acc;
+  __syncthreads();
+
+  // Gram: tile (ti, tj) -> rows i = 2ti, 2ti+1 of U against rows j = 2tj, 2tj+1 of K
+  const int tile = threadIdx.x % kTiles, ks = threadIdx.x / kTiles;
+  const int ti = tile / (T / 2), tj = tile % (T / 2);
+  const int cper = ((C / 4 + kSplit - 1) / kSplit) * 4;
+  const int cbeg = ks * cper, cend = min(C, cbeg + cper);
+  const float* u0 = Us + (size_t)(2 * ti) * ld;
+  const float* u1 = u0 + ld;
+  const float* k0 = Ks + (size_t)(2 * tj) * ld;
+  const float* k1 = k0 + ld;
+  float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
+#pragma unroll 4
+  for (int c = cbeg; c < cend; c += 4) {
+    const float4 a0 = *reinterpret_cast<const float4*>(u0 + c);
+    const float4 a1 = *reinterpret_cast<const float4*>(u1 + c);
+    const float4 b0 = *reinterpret_cast<const float4*>(k0 + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(k1 + c);
+    g00 = fmaf(a0.x, b0.x, g00); g00 = fmaf(a0.y, b0.y, g00); g00 = fmaf(a0.z, b0.z, g00); g00 = fmaf(a0.w, b0.w, g00);
+    g01 = fmaf(a0.x, b1.x, g01); g01 = fmaf(a0.y, b1.y, g01); g01 = fmaf(a0.z, b1.z, g01); g01 = fmaf(a0.w, b1.w, g01);
+    g10 = fmaf(a1.x, b0.x, g10); g10 = fmaf(a1.y, b0.y, g10); g10 = fmaf(a1.z, b0.z, g10); g10 = fmaf(a1.w, b0.w, g10);
+    g11 = fmaf(a1.x, b1.x, g11); g11 = fmaf(a1.y, b1.y, g11); g11 = fmaf(a1.z, b1.z, g11); g11 = fmaf(a1.w, b1.w, g11);
+  }
+  const int i0 = 2 * ti, j0 = 2 * tj;
+  if (kSplit == 1) {
+    gG[(j0) * T + i0] = g00;
+    gG[(j0 + 1) * T + i0] = g01;
+    gG[(j0) * T + i0 + 1] = g10;
+    gG[(j0 + 1) * T + i0 + 1] = g11;
+  } else {
+    float* mine = red + (size_t)ks * T * T;
+    mine[(j0) * T + i0] = g00;
+    mine[(j0 + 1) * T + i0] = g01;
+    mine[(j0) * T + i0 + 1] = g10;
+    mine[(j0 + 1) * T + i0 + 1] = g11;
+    __syncthreads();
+    for (int e = threadIdx.x; e < T * T; e += 256) {
+      float s = red[e];
+      for (int k2 = 1; k2 < kSplit; ++k2) s += red[(size_t)k2 * T * T + e];
+      gG[e] = s;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // scan
 // ---------------------------------------------------------------------------------------------
-constexpr int kScanStages = 4;      // ring depth
-constexpr int kScanSteps = 8;       // recurrence steps per ring stage (the inner loop is fully unrolled)
-
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
-// VPL = C / 32 values per lane; lane owns channels lane + 32*i (conflict-free smem reads, 128-byte
-// coalesced y stores).  One warp per image; one ring stage = 8 consecutive steps = contiguous bytes of
-// `staged`, fetched by one bulk copy.
-//
-// The warp is alone on its scheduler, so every dependent instruction costs its full latency: the loop
-// body is branch-free straight-line code (8 steps unrolled) and uses the two-step form of the
-// recurrence so that independent work fills the latency of the 32-lane reductions.
-//   reference (IPSRFunction.py:116-122):  a_l = <u_l, y_{l-1}>,  y_l = wn_l y_{l-1} + wo_l X[p_l]
-//   by linearity:  a_l = wn_{l-1} <u_l, y_{l-2}> + wo_{l-1} c_l,   c_l = <u_l, X[p_{l-1}]>  (staged)
-// so the reduction for step l+1 (needs only y_{l-1}) overlaps the scalar chain of step l.  With
-// y_{-1} = 0, wn_0 = 0, wo_0 = 1 steps 0 and 1 are regular.  Differences to the one-step form are
-// rounding-level (and wn, wo use a * rcp(a+v): <= 2 ulp from the reference's IEEE divisions).
-template <int VPL>
-__global__ void __launch_bounds__(32)
-blend_scan_kernel(const float* __restrict__ staged, int M,
+// The recurrence of IPSRFunction.py:104-122,
+//     a_l = <u_l, y_{l-1}>,  wn_l = a_l/(a_l+v_l),  wo_l = v_l/(a_l+v_l),  y_l = wn_l y_{l-1} + wo_l X[p_l],
+// is sequential in l, but only through ONE scalar per step.  By linearity the scalars
+//     z_i = <u_i, y_cur>   (i = the steps still ahead inside the block)
+// follow y:  z_i <- wn_l z_i + wo_l <u_i, X[p_l]> = wn_l z_i + wo_l Gt[l][i],  so that a_l is simply z_l by the
+// time step l is reached.  One CTA per image, per block of T steps:
+//   B  all warps : z_i = <u_i, y_prev> for the T rows of the block (re-anchors z on the real y every T
+//                  steps, so rounding differences to the reference's dot product cannot accumulate)
+//   C  warp 0    : the T dependent steps on scalars only -- lane i owns z_i, one shuffle broadcast,
+//                  one reciprocal and one fma per step (~60 cycles instead of a C-wide reduction)
+//   D  all threads: y_l = wn_l y_{l-1} + wo_l X[p_l] channel-parallel, exactly the reference's two rounded
+//                  products and one sum (:122), T rows of y written out coalesced
+// Staged blocks stream through a two-stage shared-memory ring of bulk async copies.
+// wn, wo use a * rcp(a+v): <= 2 ulp from the reference's IEEE divisions.
+constexpr int kScanThreads = 256;
+constexpr int kScanMaxCpt = 4;           // channels per thread: C <= 1024
+
+template <int T>
+__global__ void __launch_bounds__(kScanThreads)
+blend_scan_kernel(const float* __restrict__ staged, int C, int M,
                   float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out) {
   extern __shared__ __align__(128) uint8_t scan_smem[];
-  __shared__ __align__(8) unsigned long long bars[kScanStages];
-  constexpr int C = VPL * 32;
-  constexpr int kStride = 2 * C + 4;
-  constexpr uint32_t kStepBytes = (uint32_t)kStride * sizeof(float);
-  constexpr uint32_t kStageBytes = kStepBytes * kScanSteps;
+  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ float zs[T], wn_s[T], wo_s[T];
+  const int blk_floats = 2 * T * C + T * T + T;
+  const uint32_t blk_bytes = (uint32_t)blk_floats * sizeof(float);
+  const uint32_t stage_bytes = (blk_bytes + 127u) & ~127u;
+  float* ysm = reinterpret_cast<float*>(scan_smem + 2 * (size_t)stage_bytes);     // [C] y at the end of the previous block
   const int b = blockIdx.x;
-  const int lane = threadIdx.x;
-  const uint32_t ring = smem_u32(scan_smem);
-  const float* src = staged + (size_t)b * M * kStride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblocks = (M + T - 1) / T;
+  const float* src = staged + (size_t)b * nblocks * blk_floats;
   float* yb = y + (size_t)b * padded_steps(M) * C;
   float* wnb = wn_out + (size_t)b * M;
   float* wob = wo_out + (size_t)b * M;
-  const int nchunks = (M + kScanSteps - 1) / kScanSteps;
 
-  if (lane == 0) {
-    for (int s = 0; s < kScanStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
     mbar_fence_init();
   }
-  __syncwarp();
-  auto issue = [&](int chunk) {
-    const int s = chunk % kScanStages;
-    const int l0 = chunk * kScanSteps;
-    const uint32_t bytes = kStepBytes * (uint32_t)min(kScanSteps, M - l0);
-    mbar_expect_tx(smem_u32(&bars[s]), bytes);
-    bulk_g2s(ring + (uint32_t)s * kStageBytes, src + (size_t)l0 * kStride, bytes, smem_u32(&bars[s]));
+  for (int c = tid; c < C; c += kScanThreads) ysm[c] = 0.f;
+  __syncthreads();
+  auto issue = [&](int k) {
+    const int s = k & 1;
+    mbar_expect_tx(smem_u32(&bars[s]), blk_bytes);
+    bulk_g2s(smem_u32(scan_smem) + (uint32_t)s * stage_bytes, src + (size_t)k * blk_floats, blk_bytes, smem_u32(&bars[s]));
   };
-  if (lane == 0)
-    for (int ch = 0; ch < min(nchunks, kScanStages); ++ch) issue(ch);
+  if (tid == 0) {
+    issue(0);
+    if (nblocks > 1) issue(1);
+  }
 
-  float y1[VPL];                       // y_{l-1}
+  float yreg[kScanMaxCpt];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) y1[i] = 0.f;
-  float d = 0.f;                       // <u_l, y_{l-2}>
-  float wn_prev = 0.f, wo_prev = 1.f;
-  mbar_wait(smem_u32(&bars[0]), 0);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int s = ch % kScanStages;
-    const float* st = reinterpret_cast<const float*>(scan_smem + (size_t)s * kStageBytes);
-    // the last step of this chunk looks one step ahead: the next stage must have landed too
-    const float* st_next = st;
-    if (ch + 1 < nchunks) {
-      const int s2 = (ch + 1) % kScanStages;
-      mbar_wait(smem_u32(&bars[s2]), (uint32_t)((ch + 1) / kScanStages) & 1u);
-      st_next = reinterpret_cast<const float*>(scan_smem + (size_t)s2 * kStageBytes);
-    }
-    const int l0 = ch * kScanSteps;
-#pragma unroll
-    for (int j = 0; j < kScanSteps; ++j) {
-      const int l = l0 + j;
-      const bool live = l < M;                               // tail steps compute on stale smem into y's padding
-      const float* u = st + j * kStride;
-      const float* k = u + C;
-      const float* un = (j + 1 < kScanSteps) ? (u + kStride) : st_next;
-      // (1) d_{l+1} = <u_{l+1}, y_{l-1}>: independent of this step's weights
+  for (int m = 0; m < kScanMaxCpt; ++m) yreg[m] = 0.f;
+
+  for (int k = 0; k < nblocks; ++k) {
+    const int s = k & 1;
+    mbar_wait(smem_u32(&bars[s]), (uint32_t)(k >> 1) & 1u);
+    const float* U = reinterpret_cast<const float*>(scan_smem + (size_t)s * stage_bytes);
+    const float* K = U + (size_t)T * C;
+    const float* Gt = K + (size_t)T * C;
+    const float* V = Gt + T * T;
+    const int l0 = k * T;
+
+    // ---- B: z_i = <u_i, y_prev> ----
+    for (int i = warp; i < T; i += kScanThreads / 32) {
+      const float* u = U + (size_t)i * C;
       float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < VPL; i += 2) {
-        p0 = fmaf(un[lane + 32 * i], y1[i], p0);
-        if (i + 1 < VPL) p1 = fmaf(un[lane + 32 * (i + 1)], y1[i + 1], p1);
+      for (int c = lane; c < C; c += 64) {
+        p0 = fmaf(u[c], ysm[c], p0);
+        if (c + 32 < C) p1 = fmaf(u[c + 32], ysm[c + 32], p1);
       }
-      const float dn = warp_sum(p0 + p1);
-      // (2) scalar chain of step l
-      const float2 vc = *reinterpret_cast<const float2*>(u + 2 * C);     // v_l, c_l
-      const float a = fmaf(wn_prev, d, __fmul_rn(wo_prev, vc.y));
-      const float r = rcp_approx(__fadd_rn(a, vc.x));         // no clamp: inf / nan propagate      :120
-      const float wn = (l == 0) ? 0.f : __fmul_rn(a, r);      // first masked patch: plain copy      :98-101
-      const float wo = (l == 0) ? 1.f : __fmul_rn(vc.x, r);   //                                       :121
-      // (3) y_l = wn y_{l-1} + wo X[p_l]: two rounded products, one sum                              :122
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) y1[i] = __fadd_rn(__fmul_rn(wn, y1[i]), __fmul_rn(wo, k[lane + 32 * i]));
-      if (live && lane == 0) {
-        wnb[l] = wn;
-        wob[l] = wo;
-      }
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) yb[(size_t)l * C + lane + 32 * i] = y1[i];    // y is padded to 8 steps
-      d = dn;
-      wn_prev = wn;
-      wo_prev = wo;
+      const float zz = warp_sum(p0 + p1);
+      if (lane == 0) zs[i] = zz;
     }
-    __syncwarp();                                          // every lane is done reading stage s
-    if (lane == 0 && ch + kScanStages < nchunks) issue(ch + kScanStages);
+    __syncthreads();
+
+    // ---- C: T scalar steps ----
+    if (warp == 0) {
+      const int li = lane < T ? lane : T - 1;
+      float z = zs[li];
+      const float v = V[li];
+      float my_wn = 0.f, my_wo = 1.f;
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        const float g = Gt[j * T + li];
+        const float zj = __shfl_sync(0xffffffffu, z, j);
+        const float vj = __shfl_sync(0xffffffffu, v, j);
+        const float r = rcp_approx(__fadd_rn(zj, vj));          // no clamp: inf / nan propagate      :120
+        float wn = __fmul_rn(zj, r);
+        float wo = __fmul_rn(vj, r);                            //                                     :121
+        if (k == 0 && j == 0) {                                 // first masked patch: plain copy      :98-101
+          wn = 0.f;
+          wo = 1.f;
+        }
+        z = fmaf(wn, z, __fmul_rn(wo, g));
+        if (lane == j) {
+          my_wn = wn;
+          my_wo = wo;
+        }
+      }
+      if (lane < T) {
+        wn_s[lane] = my_wn;
+        wo_s[lane] = my_wo;
+        if (l0 + lane < M) {
+          wnb[l0 + lane] = my_wn;
+          wob[l0 + lane] = my_wo;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- D: y rows of the block ----
+    const int nvalid = min(T, M - l0);
+#pragma unroll
+    for (int m = 0; m < kScanMaxCpt; ++m) {
+      const int c = tid + m * kScanThreads;
+      if (c < C) {
+        float yy = yreg[m];
+        float* yrow = yb + (size_t)l0 * C + c;
+#pragma unroll 8
+        for (int j = 0; j < nvalid; ++j) {
+          yy = __fadd_rn(__fmul_rn(wn_s[j], yy), __fmul_rn(wo_s[j], K[(size_t)j * C + c]));     // :122
+          yrow[(size_t)j * C] = yy;
+        }
+        yreg[m] = yy;
+        ysm[c] = yy;
+      }
+    }
+    __syncthreads();                                       // ysm complete; stage s no longer read
+    if (tid == 0 && k + 2 < nblocks) issue(k + 2);
   }
 }
 
@@ -267,8 +373,42 @@ static int paste_ct(int C, int N) {
 
 }  // namespace ipsr
 
-extern "C" int ipsr_staged_stride(int C) { return ipsr::staged_stride(C); }
+extern "C" int ipsr_scan_block_steps(int C) { return ipsr::scan_block_steps(C); }
+extern "C" int ipsr_staged_block_floats(int C) { return ipsr::staged_block_floats(C); }
 extern "C" int ipsr_padded_steps(int M) { return ipsr::padded_steps(M); }
+
+namespace ipsr {
+template <int T>
+static int launch_stage(const float* xt, const float* r_masked, const float* inv_norm, const int32_t* ind,
+                        const int32_t* mask_idx, int B, int C, int N, int M, float* staged, float* vmask, cudaStream_t st) {
+  constexpr int kSplit = 256 / ((T / 2) * (T / 2));
+  const size_t smem = ((size_t)2 * T * (C + 4) + (kSplit > 1 ? (size_t)kSplit * T * T : 0)) * sizeof(float);
+  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d too large", C);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(blend_stage_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_stage smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  blend_stage_kernel<T><<<dim3((M + T - 1) / T, B), 256, smem, st>>>(xt, r_masked, inv_norm, ind, mask_idx, C, N, M, staged, vmask);
+  return check_launch("ipsr_blend_stage");
+}
+
+template <int T>
+static int launch_scan(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, cudaStream_t st) {
+  const size_t blk_bytes = (size_t)staged_block_floats(C) * sizeof(float);
+  const size_t smem = 2 * ((blk_bytes + 127) & ~(size_t)127) + (size_t)C * sizeof(float);
+  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  blend_scan_kernel<T><<<B, kScanThreads, smem, st>>>(staged, C, M, y, wn, wo);
+  return check_launch("ipsr_blend_scan");
+}
+}  // namespace ipsr
 
 extern "C" int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
                                 const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
@@ -277,27 +417,15 @@ extern "C" int ipsr_blend_stage(const float* xt, const float* r_masked, const fl
   if (M == 0) return IPSR_OK;
   IPSR_REQUIRE(xt && r_masked && inv_norm && ind && mask_idx && staged, IPSR_ERR_INVALID_ARG,
                "ipsr_blend_stage: null pointer");
-  IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && M <= N, IPSR_ERR_INVALID_ARG, "ipsr_blend_stage: bad dims");
-  IPSR_REQUIRE(C % 4 == 0, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d must be a multiple of 4", C);
-  blend_stage_kernel<<<dim3((M + 7) / 8, B), 256, 0, as_stream(stream)>>>(xt, r_masked, inv_norm, ind, mask_idx, C, N, M,
-                                                                          staged, vmask);
-  return check_launch("ipsr_blend_stage");
-}
-
-namespace ipsr {
-template <int VPL>
-static int launch_scan(const float* staged, int B, int M, float* y, float* wn, float* wo, cudaStream_t st) {
-  constexpr int C = VPL * 32;
-  const size_t smem = (size_t)kScanStages * kScanSteps * staged_stride(C) * sizeof(float);
-  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
+  IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && M <= N && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_blend_stage: bad dims");
+  IPSR_REQUIRE(C % 32 == 0 && C <= 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d must be a multiple of 32, <= 1024", C);
+  cudaStream_t st = as_stream(stream);
+  switch (scan_block_steps(C)) {
+    case 32: return launch_stage<32>(xt, r_masked, inv_norm, ind, mask_idx, B, C, N, M, staged, vmask, st);
+    case 16: return launch_stage<16>(xt, r_masked, inv_norm, ind, mask_idx, B, C, N, M, staged, vmask, st);
+    default: return launch_stage<8>(xt, r_masked, inv_norm, ind, mask_idx, B, C, N, M, staged, vmask, st);
   }
-  blend_scan_kernel<VPL><<<B, 32, smem, st>>>(staged, M, y, wn, wo);
-  return check_launch("ipsr_blend_scan");
 }
-}  // namespace ipsr
 
 extern "C" int ipsr_blend_scan(const float* staged, int B, int C, int M,
                                float* y, float* wn, float* wo, void* stream) {
@@ -305,23 +433,13 @@ extern "C" int ipsr_blend_scan(const float* staged, int B, int C, int M,
   if (M == 0) return IPSR_OK;
   IPSR_REQUIRE(staged && y && wn && wo, IPSR_ERR_INVALID_ARG, "ipsr_blend_scan: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && M > 0, IPSR_ERR_INVALID_ARG, "ipsr_blend_scan: bad dims");
+  IPSR_REQUIRE(C % 32 == 0 && C <= 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d must be a multiple of 32, <= 1024", C);
   cudaStream_t st = as_stream(stream);
-  IPSR_REQUIRE(C % 32 == 0, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d must be a multiple of 32", C);
-  switch (C / 32) {
-    case 1: return launch_scan<1>(staged, B, M, y, wn, wo, st);
-    case 2: return launch_scan<2>(staged, B, M, y, wn, wo, st);
-    case 3: return launch_scan<3>(staged, B, M, y, wn, wo, st);
-    case 4: return launch_scan<4>(staged, B, M, y, wn, wo, st);
-    case 6: return launch_scan<6>(staged, B, M, y, wn, wo, st);
-    case 8: return launch_scan<8>(staged, B, M, y, wn, wo, st);
-    case 12: return launch_scan<12>(staged, B, M, y, wn, wo, st);
-    case 16: return launch_scan<16>(staged, B, M, y, wn, wo, st);
-    case 24: return launch_scan<24>(staged, B, M, y, wn, wo, st);
-    case 32: return launch_scan<32>(staged, B, M, y, wn, wo, st);
-    default: break;
+  switch (scan_block_steps(C)) {
+    case 32: return launch_scan<32>(staged, B, C, M, y, wn, wo, st);
+    case 16: return launch_scan<16>(staged, B, C, M, y, wn, wo, st);
+    default: return launch_scan<8>(staged, B, C, M, y, wn, wo, st);
   }
-  set_error("ipsr_blend_scan: C=%d not supported (C/32 must be one of 1,2,3,4,6,8,12,16,24,32)", C);
-  return IPSR_ERR_UNSUPPORTED;
 }
 
 extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, const int32_t* rank,

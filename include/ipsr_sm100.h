@@ -141,23 +141,27 @@ int ipsr_maxcoord(const float* s, int P, int L, int64_t* ind_i64, float* vmax, v
  * (d) coherent blend over masked positions + gather-paste   (models/IPSRFunction.py:70-133)
  * ------------------------------------------------------------------------------------------- */
 
-/* Stage the operands of the sequential blend, one warp per masked position l
- * (q_l = mask_idx[l], p_l = ind[b,q_l]):
- *   staged[b,l,0:C]    = u_l = X[q_l] * inv_norm[q_l]   (IPSRFunction.py:109)
- *   staged[b,l,C:2C]   = X[p_l]                          (known_region, :95)
- *   staged[b,l,2C]     = v_l = <R[q_l], Xn[p_l]>  exact fp32 (vmax at masked positions, :70)
- * staged is [B][M][ipsr_staged_stride(C)]; vmask [B,M] (optional copy of v_l, may be NULL).  */
+/* Stage the operands of the sequential blend.  Steps l = 0..M-1 (q_l = mask_idx[l], p_l = ind[b,q_l]) are
+ * grouped in blocks of T = ipsr_scan_block_steps(C) consecutive steps; one staged block is contiguous:
+ *   U  [T][C]  u_l = X[q_l] * inv_norm[q_l]                      (IPSRFunction.py:109)
+ *   K  [T][C]  X[p_l]                                            (known_region, :95)
+ *   Gt [T][T]  Gt[j][i] = <u_{l0+i}, X[p_{l0+j}]>                (in-block Gram matrix)
+ *   v  [T]     v_l = <R[q_l], Xn[p_l]>  exact fp32               (vmax at masked positions, :70)
+ * staged is [B][ceil(M/T)][ipsr_staged_block_floats(C)]; vmask [B,M] (optional copy of v_l, may be NULL).
+ * C % 32 == 0, C <= 1024. */
 int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
                      const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
                      float* staged, float* vmask, void* stream);
-/* floats per staged step: 2*C + 4 (u_l, X[p_l], then v_l and three pad floats) */
-int ipsr_staged_stride(int C);
-/* rows of y per image: M rounded up to a multiple of 8 (the scan's unroll depth) */
+/* steps per staged block (32 for C <= 256, 16 for C <= 512, else 8) and floats per staged block */
+int ipsr_scan_block_steps(int C);
+int ipsr_staged_block_floats(int C);
+/* rows of y per image: M rounded up to a multiple of 8 */
 int ipsr_padded_steps(int M);
 
-/* The recurrence itself: one warp per image, operands streamed through shared memory by bulk
- * async copies.  l=0: y_0 = X[p_0] (:98-101);  l>0: a = <u_l, y_{l-1}>; wn = a/(a+v);
- * wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).
+/* The recurrence itself, one CTA per image.  l=0: y_0 = X[p_0] (:98-101);  l>0: a = <u_l, y_{l-1}>;
+ * wn = a/(a+v); wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).  Inside a block the
+ * scalars a_l are tracked by linearity (a_i <- wn_l a_i + wo_l Gt[l][i]) so that the dependent chain
+ * is one scalar step per masked position; y is re-anchored at every block boundary.
  * Writes y [B][ipsr_padded_steps(M)][C], wn/wo [B,M] (wn[b,0] = 0, wo[b,0] = 1). */
 int ipsr_blend_scan(const float* staged, int B, int C, int M,
                     float* y, float* wn, float* wo, void* stream);
