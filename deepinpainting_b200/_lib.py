@@ -55,6 +55,7 @@ SIGNATURES = {
     "ipsr_unpack_maxidx": (_i, [_p, _i64, _p, _p, _p]),
     "ipsr_maxcoord": (_i, [_p, _i, _i, _p, _p, _p]),
     "ipsr_blend_stage": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "ipsr_blend_stage_with_routes": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ipsr_scan_block_steps": (_i, [_i]),
     "ipsr_staged_block_floats": (_i, [_i]),
     "ipsr_padded_steps": (_i, [_i]),

@@ -120,14 +120,15 @@ static int validate(const ipsr_fwd_args* a, Workspace* w, int* mode_out) {
 // (d) and the backward bookkeeping; ind[b,q] must be final.
 static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void* stream) {
   const int B = a->B, C = a->C, N = a->H * a->W, M = a->M;
-  if (M > 0) {
-    IPSR_FORWARD(ipsr_blend_stage(at<float>(a, w.xt), at<float>(a, w.r_masked), at<float>(a, w.inv_norm), a->ind,
-                                  a->mask_idx, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask), stream));
-    IPSR_FORWARD(ipsr_blend_scan(at<float>(a, w.staged), B, C, M, at<float>(a, w.y), a->wn, a->wo, stream));
-  }
-  if (a->need_grad)
+  const bool grad = a->need_grad != 0;
+  // the route builders depend on ind only: they ride in the stage launch
+  IPSR_FORWARD(ipsr_blend_stage_with_routes(at<float>(a, w.xt), at<float>(a, w.r_masked), at<float>(a, w.inv_norm), a->ind,
+                                            a->mask_idx, a->flag, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask),
+                                            grad ? a->route_ptr : nullptr, grad ? a->route_q : nullptr, stream));
+  if (M > 0) IPSR_FORWARD(ipsr_blend_scan(at<float>(a, w.staged), B, C, M, at<float>(a, w.y), a->wn, a->wo, stream));
+  if (grad && M > 1)
     return ipsr_paste_with_bookkeeping(a->x, at<float>(a, w.y), a->ind, a->rank, a->flag, a->mask_idx, a->wn, a->wo, B, C,
-                                       N, M, a->out, a->route_ptr, a->route_q, a->exc_start, a->exc_cnt, a->exc_l,
+                                       N, M, a->out, nullptr, nullptr, a->exc_start, a->exc_cnt, a->exc_l,
                                        a->exc_w, a->exc_total, a->exc_cap, stream);
   return ipsr_paste(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream);
 }

@@ -35,23 +35,28 @@ __host__ __device__ inline int padded_steps(int M) { return (M + 7) & ~7; }
 //   phase 2  the T x T Gram matrix of the block from shared memory, 2 x 2 register tiles, the channel
 //            range split over 256 / (T/2)^2 thread groups whose partial sums are added in fixed order.
 // ---------------------------------------------------------------------------------------------
+struct StageArgs {
+  const float* xt; const float* r_masked; const float* inv_norm; const int* ind; const int* mask_idx;
+  int B, C, N, M, nblocks;
+  float* staged; float* vmask;
+  // optional routes builders riding in the same launch (they depend on ind only): CTAs [0, n_routes)
+  int n_routes; const int* flag; int* route_ptr; int* route_q;
+};
+
 template <int T>
-__global__ void __launch_bounds__(256)
-blend_stage_kernel(const float* __restrict__ xt, const float* __restrict__ r_masked, const float* __restrict__ inv_norm,
-                   const int* __restrict__ ind, const int* __restrict__ mask_idx, int C, int N, int M,
-                   float* __restrict__ staged, float* __restrict__ vmask) {
-  extern __shared__ __align__(16) float stage_smem[];
+__device__ __forceinline__ void
+blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt, const float* __restrict__ r_masked,
+                const float* __restrict__ inv_norm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
+                int C, int N, int M, int nblocks, float* __restrict__ staged, float* __restrict__ vmask) {
   constexpr int kTiles = (T / 2) * (T / 2);              // 2 x 2 output tiles
   constexpr int kSplit = 256 / kTiles;                   // channel groups (1, 4 or 16)
   const int ld = C + 4;                                  // padded row: conflict-free float4 reads across rows
   float* Us = stage_smem;                                // [T][ld]
   float* Ks = Us + (size_t)T * ld;                       // [T][ld]
   float* red = Ks + (size_t)T * ld;                      // [kSplit][T*T] (kSplit > 1 only)
-  const int b = blockIdx.y;
-  const int nblocks = gridDim.x;
-  const int l0 = blockIdx.x * T;
+  const int l0 = kblk * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* blk = staged + ((size_t)b * nblocks + blockIdx.x) * staged_block_floats(C);
+  float* blk = staged + ((size_t)b * nblocks + kblk) * staged_block_floats(C);
   float* gU = blk;
   float* gK = blk + (size_t)T * C;
   float* gG = gK + (size_t)T * C;
@@ -144,6 +149,20 @@ blend_stage_kernel(const float* __restrict__ xt, const float* __restrict__ r_mas
       gG[e] = s;
     }
   }
+}
+
+// grid = n_routes + ceil(M / T) * B CTAs; the latency-bound route builders are scheduled first
+template <int T>
+__global__ void __launch_bounds__(256) blend_stage_kernel(const StageArgs a) {
+  extern __shared__ __align__(16) float stage_smem[];
+  int blk = blockIdx.x;
+  if (blk < a.n_routes) {
+    build_routes_cta(blk, reinterpret_cast<int*>(stage_smem), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q);
+    return;
+  }
+  blk -= a.n_routes;
+  blend_stage_cta<T>(blk % a.nblocks, blk / a.nblocks, stage_smem, a.xt, a.r_masked, a.inv_norm, a.ind, a.mask_idx, a.C, a.N,
+                     a.M, a.nblocks, a.staged, a.vmask);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,8 +373,8 @@ __global__ void __launch_bounds__(256) paste_fused_kernel(const FusedPasteArgs a
   }
   blk -= a.n_routes;
   if (blk < a.n_exc) {
-    build_exceptions_cta(blk, fsm, a.ind, a.mask_idx, a.wn, a.wo, a.N, a.M, a.exc_start, a.exc_cnt, a.exc_l, a.exc_w,
-                         a.exc_total, a.exc_cap);
+    build_exceptions_cta(blk / a.exc_per_img, blk % a.exc_per_img, a.exc_per_img, fsm, a.ind, a.mask_idx, a.wn, a.wo, a.N, a.M,
+                         a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total, a.exc_cap);
     return;
   }
   blk -= a.n_exc;
@@ -379,19 +398,33 @@ extern "C" int ipsr_padded_steps(int M) { return ipsr::padded_steps(M); }
 
 namespace ipsr {
 template <int T>
-static int launch_stage(const float* xt, const float* r_masked, const float* inv_norm, const int32_t* ind,
-                        const int32_t* mask_idx, int B, int C, int N, int M, float* staged, float* vmask, cudaStream_t st) {
+static int launch_stage(StageArgs a, cudaStream_t st) {
   constexpr int kSplit = 256 / ((T / 2) * (T / 2));
-  const size_t smem = ((size_t)2 * T * (C + 4) + (kSplit > 1 ? (size_t)kSplit * T * T : 0)) * sizeof(float);
-  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d too large", C);
+  size_t smem = ((size_t)2 * T * (a.C + 4) + (kSplit > 1 ? (size_t)kSplit * T * T : 0)) * sizeof(float);
+  if (a.n_routes > 0) {
+    const size_t smem_routes = (size_t)(2 * a.N + 1) * sizeof(int);
+    if (smem_routes > smem) smem = smem_routes;
+  }
+  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d / N=%d too large", a.C, a.N);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(blend_stage_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_stage smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  blend_stage_kernel<T><<<dim3((M + T - 1) / T, B), 256, smem, st>>>(xt, r_masked, inv_norm, ind, mask_idx, C, N, M, staged, vmask);
+  a.nblocks = (a.M + T - 1) / T;
+  const long long ctas = (long long)a.n_routes + (long long)a.nblocks * a.B;
+  IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: grid too large");
+  blend_stage_kernel<T><<<(unsigned)ctas, 256, smem, st>>>(a);
   return check_launch("ipsr_blend_stage");
+}
+
+static int dispatch_stage(const StageArgs& a, cudaStream_t st) {
+  switch (scan_block_steps(a.C)) {
+    case 32: return launch_stage<32>(a, st);
+    case 16: return launch_stage<16>(a, st);
+    default: return launch_stage<8>(a, st);
+  }
 }
 
 template <int T>
@@ -413,18 +446,32 @@ static int launch_scan(const float* staged, int B, int C, int M, float* y, float
 extern "C" int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
                                 const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
                                 float* staged, float* vmask, void* stream) {
+  return ipsr_blend_stage_with_routes(xt, r_masked, inv_norm, ind, mask_idx, nullptr, B, C, N, M, staged, vmask, nullptr,
+                                      nullptr, stream);
+}
+
+extern "C" int ipsr_blend_stage_with_routes(const float* xt, const float* r_masked, const float* inv_norm,
+                                            const int32_t* ind, const int32_t* mask_idx, const int32_t* flag,
+                                            int B, int C, int N, int M, float* staged, float* vmask,
+                                            int32_t* route_ptr, int32_t* route_q, void* stream) {
   using namespace ipsr;
-  if (M == 0) return IPSR_OK;
+  const bool routes = route_ptr != nullptr;
+  if (M == 0) {
+    if (routes) return ipsr_build_routes(ind, flag, mask_idx, B, N, M, route_ptr, route_q, stream);
+    return IPSR_OK;
+  }
   IPSR_REQUIRE(xt && r_masked && inv_norm && ind && mask_idx && staged, IPSR_ERR_INVALID_ARG,
                "ipsr_blend_stage: null pointer");
-  IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && M <= N && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_blend_stage: bad dims");
+  IPSR_REQUIRE(!routes || (flag && route_q), IPSR_ERR_INVALID_ARG, "ipsr_blend_stage_with_routes: flag / route_q missing");
+  IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && M > 0 && M <= N, IPSR_ERR_INVALID_ARG, "ipsr_blend_stage: bad dims");
   IPSR_REQUIRE(C % 32 == 0 && C <= 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d must be a multiple of 32, <= 1024", C);
-  cudaStream_t st = as_stream(stream);
-  switch (scan_block_steps(C)) {
-    case 32: return launch_stage<32>(xt, r_masked, inv_norm, ind, mask_idx, B, C, N, M, staged, vmask, st);
-    case 16: return launch_stage<16>(xt, r_masked, inv_norm, ind, mask_idx, B, C, N, M, staged, vmask, st);
-    default: return launch_stage<8>(xt, r_masked, inv_norm, ind, mask_idx, B, C, N, M, staged, vmask, st);
-  }
+  IPSR_REQUIRE(!routes || N <= 16384, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage_with_routes: N=%d > 16384", N);
+  StageArgs a;
+  a.xt = xt; a.r_masked = r_masked; a.inv_norm = inv_norm; a.ind = ind; a.mask_idx = mask_idx;
+  a.B = B; a.C = C; a.N = N; a.M = M; a.nblocks = 0;
+  a.staged = staged; a.vmask = vmask;
+  a.n_routes = routes ? B : 0; a.flag = flag; a.route_ptr = route_ptr; a.route_q = route_q;
+  return dispatch_stage(a, as_stream(stream));
 }
 
 extern "C" int ipsr_blend_scan(const float* staged, int B, int C, int M,
@@ -467,7 +514,8 @@ extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const
                                            int32_t* exc_start, int32_t* exc_cnt, int32_t* exc_l, float* exc_w,
                                            int32_t* exc_total, int exc_cap, void* stream) {
   using namespace ipsr;
-  IPSR_REQUIRE(x && ind && rank && out && flag && route_ptr && route_q && (M == 0 || (y && mask_idx)), IPSR_ERR_INVALID_ARG,
+  const bool routes = route_ptr != nullptr;       // NULL: already built (ipsr_blend_stage_with_routes)
+  IPSR_REQUIRE(x && ind && rank && out && (!routes || (flag && route_q)) && (M == 0 || (y && mask_idx)), IPSR_ERR_INVALID_ARG,
                "ipsr_paste_with_bookkeeping: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0, IPSR_ERR_INVALID_ARG, "ipsr_paste_with_bookkeeping: bad dims");
   IPSR_REQUIRE(N <= 16384, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: N=%d > 16384", N);
@@ -481,13 +529,13 @@ extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const
   a.flag = flag; a.mask_idx = mask_idx; a.route_ptr = route_ptr; a.route_q = route_q;
   a.wn = wn; a.wo = wo; a.exc_start = exc_start; a.exc_cnt = exc_cnt; a.exc_l = exc_l; a.exc_w = exc_w;
   a.exc_total = exc_total; a.exc_cap = exc_cap;
-  a.n_routes = B;
-  a.exc_per_img = exc ? 1 : 0;
+  a.n_routes = routes ? B : 0;
+  a.exc_per_img = exc ? exc_parts(M) : 0;
   a.n_exc = B * a.exc_per_img;
   size_t smem = (size_t)a.CT * N * sizeof(float);
   const size_t smem_routes = (size_t)(2 * N + 1) * sizeof(int), smem_exc = ((size_t)N + 3 * kExcChunk) * sizeof(int);
-  if (smem_routes > smem) smem = smem_routes;
-  if (smem_exc > smem) smem = smem_exc;
+  if (routes && smem_routes > smem) smem = smem_routes;
+  if (exc && smem_exc > smem) smem = smem_exc;
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: N=%d too large", N);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {

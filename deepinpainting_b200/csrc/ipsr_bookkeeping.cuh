@@ -90,24 +90,36 @@ build_routes_cta(int b, int* rsm, const int* __restrict__ ind, const int* __rest
 // ---------------------------------------------------------------------------------------------
 constexpr int kExcChunk = 1024;
 constexpr int kExcThreads = 256;
+// CTAs per image: one per 256 masked steps (every owner thread then walks the whole tail of the recurrence once)
+__host__ __device__ inline int exc_parts(int M) { return M <= kExcThreads ? 1 : (M + kExcThreads - 1) / kExcThreads; }
 
 template <bool WRITE>
-__device__ __forceinline__ int replay_owner(int l0, int p, int M, int base, int n, const float* s_wn, const float* s_wo,
+__device__ __forceinline__ int replay_owner(int l0, int p, int base, int n, const float* s_wn, const float* s_wo,
                                             const int* s_p, float& e, int cnt, int* __restrict__ out_l,
                                             float* __restrict__ out_w) {
   // processes steps l in [max(base, l0), base+n) of this chunk
-  int i = max(0, l0 - base);
-  for (; i < n; ++i) {
-    const int l = base + i;
-    if (l == l0) {
-      e = (l0 == 0) ? 1.f : s_wo[i];                       // first appearance: row[p] = 0*wn + wo (or 1 at l = 0)
-    } else {
-      e = __fmul_rn(e, s_wn[i]);                            // row * wn                      :123
-      if (s_p[i] == p) e = __fadd_rn(e, s_wo[i]);           // row[p_l] += wo                :124
-    }
-    if (l >= 1 && !(fabsf(e) < 1.0f)) {                     // survives the int64 store      :134
+  int i = l0 - base;
+  if (i >= n) return cnt;
+  if (i >= 0) {                                             // first appearance: row[p] = 0*wn + wo (or 1 at l = 0)
+    e = (l0 == 0) ? 1.f : s_wo[i];
+    if (l0 >= 1 && !(fabsf(e) < 1.0f)) {
       if (WRITE) {
-        out_l[cnt] = l;
+        out_l[cnt] = l0;
+        out_w[cnt] = trunc_as_reference(e);
+      }
+      ++cnt;
+    }
+    ++i;
+  } else {
+    i = 0;
+  }
+#pragma unroll 4
+  for (; i < n; ++i) {
+    e = __fmul_rn(e, s_wn[i]);                              // row * wn                      :123
+    if (s_p[i] == p) e = __fadd_rn(e, s_wo[i]);             // row[p_l] += wo                :124
+    if (!(fabsf(e) < 1.0f)) {                               // survives the int64 store      :134
+      if (WRITE) {
+        out_l[cnt] = base + i;
         out_w[cnt] = trunc_as_reference(e);
       }
       ++cnt;
@@ -116,9 +128,10 @@ __device__ __forceinline__ int replay_owner(int l0, int p, int M, int base, int 
   return cnt;
 }
 
+// CTA `part` of `nparts` of image b owns the masked steps l0 = part + nparts * k.
 // fsm: first-occurrence table [N] ints, then 3*kExcChunk staging words
 __device__ __forceinline__ void
-build_exceptions_cta(int b, void* fsm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
+build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                      const float* __restrict__ wn, const float* __restrict__ wo, int N, int M,
                      int* __restrict__ exc_start, int* __restrict__ exc_cnt, int* __restrict__ exc_l,
                      float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap) {
@@ -133,9 +146,15 @@ build_exceptions_cta(int b, void* fsm, const int* __restrict__ ind, const int* _
   __syncthreads();
   for (int l = threadIdx.x; l < M; l += blockDim.x) atomicMin(&first[ind_b[mask_idx[l]]], l);
   __syncthreads();
-  for (int p = threadIdx.x; p < N; p += blockDim.x) {       // default: no exceptions in this column
-    exc_start[(size_t)b * N + p] = 0;
-    exc_cnt[(size_t)b * N + p] = 0;
+  // default: no exceptions in this column.  Columns are zeroed by the part that owns their first occurrence
+  // (or, for columns never matched by a masked position, by part 0), so no two CTAs write the same entry.
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    const int f = first[p];
+    const int owner_part = (f == 0x7FFFFFFF) ? 0 : (f % nparts);
+    if (owner_part == part) {
+      exc_start[(size_t)b * N + p] = 0;
+      exc_cnt[(size_t)b * N + p] = 0;
+    }
   }
   // A non-finite weight turns EVERY column of the later rows into NaN (0 * inf), which the sparse
   // "first occurrence" walk below cannot represent: flag the image as overflowed so that the backward
@@ -157,9 +176,10 @@ build_exceptions_cta(int b, void* fsm, const int* __restrict__ ind, const int* _
     __syncthreads();
     cur_base = base;
   };
-  // owners are processed in rounds of blockDim.x masked positions
-  for (int round = 0; round < M; round += blockDim.x) {
-    const int l0 = round + threadIdx.x;
+  // owners are processed in rounds of blockDim.x masked positions of this part
+  const int span = (int)blockDim.x * nparts;
+  for (int round = 0; round < M; round += span) {
+    const int l0 = round + (int)threadIdx.x * nparts + part;
     int p = -1;
     if (l0 < M) {
       p = ind_b[mask_idx[l0]];
@@ -171,7 +191,7 @@ build_exceptions_cta(int b, void* fsm, const int* __restrict__ ind, const int* _
     int found = 0;
     for (int base = base0; base < M; base += kExcChunk) {
       stage(base);
-      if (p >= 0) found = replay_owner<false>(l0, p, M, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, found, nullptr, nullptr);
+      if (p >= 0) found = replay_owner<false>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, found, nullptr, nullptr);
     }
     // reserve a contiguous slot range (placement is arbitrary, order inside is ascending l)
     int start = 0;
@@ -192,7 +212,7 @@ build_exceptions_cta(int b, void* fsm, const int* __restrict__ ind, const int* _
       for (int base = base0; base < M; base += kExcChunk) {
         stage(base);
         if (p >= 0)
-          cnt = replay_owner<true>(l0, p, M, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, cnt,
+          cnt = replay_owner<true>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, cnt,
                                    exc_l + (size_t)b * exc_cap + start, exc_w + (size_t)b * exc_cap + start);
       }
     }

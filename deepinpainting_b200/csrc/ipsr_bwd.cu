@@ -20,20 +20,23 @@ build_routes_kernel(const int* __restrict__ ind, const int* __restrict__ flag, c
 __global__ void __launch_bounds__(kExcThreads)
 build_exceptions_kernel(const int* __restrict__ ind, const int* __restrict__ mask_idx, const float* __restrict__ wn,
                         const float* __restrict__ wo, int N, int M, int* __restrict__ exc_start, int* __restrict__ exc_cnt,
-                        int* __restrict__ exc_l, float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap) {
+                        int* __restrict__ exc_l, float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap,
+                        int nparts) {
   extern __shared__ int esm[];                             // [N] + 3*kExcChunk words
-  build_exceptions_cta(blockIdx.x, esm, ind, mask_idx, wn, wo, N, M, exc_start, exc_cnt, exc_l, exc_w, exc_total, exc_cap);
+  build_exceptions_cta(blockIdx.x / nparts, blockIdx.x % nparts, nparts, esm, ind, mask_idx, wn, wo, N, M, exc_start,
+                       exc_cnt, exc_l, exc_w, exc_total, exc_cap);
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward proper
 // ---------------------------------------------------------------------------------------------
-// grid = (C / CT, B): the CTA stages CT rows of g[b] in shared memory.  Light bank columns (few
-// routes) are summed by their own thread; heavy ones -- a non-negative reference makes a few "hub"
-// patches the best match of hundreds of positions -- are queued and summed by whole warps
-// (lane-strided partial sums in ascending q, then a fixed xor tree: deterministic).  If the exception
-// lists overflowed (exc_total > exc_cap, chaotic inputs only) the column replays the recurrence.
-constexpr int kBwdLight = 8;
+// grid = (C / CT, B): the CTA stages CT rows of g[b] (C % CT == 0) and the CSR of the image in shared
+// memory.  Light bank columns (few routes) are summed by their own thread, in a loop of exactly their
+// route count; heavy ones -- a non-negative reference makes a few "hub" patches the best match of
+// hundreds of positions -- are queued and summed by whole warps (lane-strided partial sums in ascending q,
+// then a fixed xor tree: deterministic).  If the exception lists overflowed (exc_total > exc_cap, chaotic
+// inputs only) the column replays the recurrence.
+constexpr int kBwdLight = 12;
 
 template <int CT>
 __global__ void __launch_bounds__(256)
@@ -49,36 +52,37 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
   int* rq = ptr + (N + 1);                                       // [N]
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * CT;
-  const int ct = min(CT, C - c0);
   const float* gb = g + ((size_t)b * C + c0) * N;
   float* ob = gin + ((size_t)b * C + c0) * N;
-  const int total = ct * N;
+  const int total = CT * N;
   if (threadIdx.x == 0) nheavy = 0;
   if ((N & 3) == 0) {
     const float4* s4 = reinterpret_cast<const float4*>(gb);
     float4* d4 = reinterpret_cast<float4*>(grow);
-    for (int i = threadIdx.x; i < total / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < total / 4; i += 256) d4[i] = __ldg(s4 + i);
   } else {
-    for (int i = threadIdx.x; i < total; i += blockDim.x) grow[i] = __ldg(gb + i);
+    for (int i = threadIdx.x; i < total; i += 256) grow[i] = __ldg(gb + i);
   }
   {
     // the index lists are shared by all channels: one coalesced copy replaces dependent global loads
     const int* gptr = route_ptr + (size_t)b * (N + 1);
     const int* grq = route_q + (size_t)b * N;
-    for (int i = threadIdx.x; i <= N; i += blockDim.x) ptr[i] = __ldg(gptr + i);
-    for (int i = threadIdx.x; i < N; i += blockDim.x) rq[i] = __ldg(grq + i);
+    for (int i = threadIdx.x; i <= N; i += 256) ptr[i] = __ldg(gptr + i);
+    for (int i = threadIdx.x; i < N; i += 256) rq[i] = __ldg(grq + i);
   }
-  __syncthreads();
-  const bool has_exc = (M > 1) && exc_cnt;
-  const bool overflow = has_exc && exc_total && (exc_total[b] > exc_cap);
+  const bool has_exc = (M > 1) && exc_cnt && exc_total && (exc_total[b] != 0);
+  const bool overflow = has_exc && (exc_total[b] > exc_cap);
+  const bool lists = has_exc && !overflow;
   const int* ecnt = exc_cnt + (size_t)b * N;
   const int* estart = exc_start + (size_t)b * N;
   const int* el = exc_l + (size_t)b * exc_cap;
   const float* ew = exc_w + (size_t)b * exc_cap;
+  __syncthreads();
 
-  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+  for (int p = threadIdx.x; p < N; p += 256) {
     const int r0 = ptr[p], r1 = ptr[p + 1];
-    const int ne = (has_exc && !overflow) ? ecnt[p] : 0;
+    const int ne = lists ? ecnt[p] : 0;
     if ((r1 - r0) + ne > kBwdLight) {
       heavy[atomicAdd(&nheavy, 1)] = p;                    // queue order does not affect any sum
       continue;
@@ -86,16 +90,10 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
     float acc[CT];
 #pragma unroll
     for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
-    int qs[kBwdLight];
+    for (int r = r0; r < r1; ++r) {
+      const int q = rq[r];
 #pragma unroll
-    for (int i = 0; i < kBwdLight; ++i) qs[i] = (r0 + i < r1) ? rq[r0 + i] : -1;   // independent loads first
-#pragma unroll
-    for (int i = 0; i < kBwdLight; ++i) {
-      if (qs[i] >= 0) {
-#pragma unroll
-        for (int ch = 0; ch < CT; ++ch)
-          if (ch < ct) acc[ch] += grow[ch * N + qs[i]];
-      }
+      for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
     }
     if (ne > 0) {
       const int s = estart[p];
@@ -103,8 +101,7 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
         const int q = mask_idx[el[s + e]];
         const float w = ew[s + e];
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch)
-          if (ch < ct) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
       }
     }
     if (overflow) {
@@ -116,21 +113,20 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
         if (!(fabsf(e) < 1.0f)) {
           const float w = trunc_as_reference(e);
 #pragma unroll
-          for (int ch = 0; ch < CT; ++ch)
-            if (ch < ct) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
+          for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
         }
       }
     }
 #pragma unroll
     for (int ch = 0; ch < CT; ++ch)                          // g + weighted * triple_w           :173
-      if (ch < ct) ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
+      ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
   }
   __syncthreads();
 
   // heavy columns: one warp each
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nh = nheavy;
-  for (int h = warp; h < nh; h += nwarps) {
+  for (int h = warp; h < nh; h += 8) {
     const int p = heavy[h];
     const int r0 = ptr[p], r1 = ptr[p + 1];
     float acc[CT];
@@ -139,17 +135,15 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
     for (int r = r0 + lane; r < r1; r += 32) {
       const int q = rq[r];
 #pragma unroll
-      for (int ch = 0; ch < CT; ++ch)
-        if (ch < ct) acc[ch] += grow[ch * N + q];
+      for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
     }
-    if (has_exc && !overflow) {
+    if (lists) {
       const int ne = ecnt[p], s = estart[p];
       for (int e = lane; e < ne; e += 32) {
         const int q = mask_idx[el[s + e]];
         const float w = ew[s + e];
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch)
-          if (ch < ct) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
       }
     }
     if (overflow) {                                          // lane 0 replays (rare path)
@@ -162,8 +156,7 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
           if (!(fabsf(e) < 1.0f)) {
             const float w = trunc_as_reference(e);
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch)
-              if (ch < ct) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
+            for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
           }
         }
       }
@@ -172,8 +165,7 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
     for (int ch = 0; ch < CT; ++ch) acc[ch] = warp_sum(acc[ch]);
     if (lane == 0) {
 #pragma unroll
-      for (int ch = 0; ch < CT; ++ch)
-        if (ch < ct) ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
+      for (int ch = 0; ch < CT; ++ch) ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
     }
   }
 }
@@ -211,8 +203,9 @@ extern "C" int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx
     cudaError_t e = cudaFuncSetAttribute(build_exceptions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "build_exceptions smem attribute: %s", cudaGetErrorString(e));
   }
-  build_exceptions_kernel<<<B, kExcThreads, smem, as_stream(stream)>>>(ind, mask_idx, wn, wo, N, M, exc_start, exc_cnt, exc_l,
-                                                                      exc_w, exc_total, exc_cap);
+  const int nparts = exc_parts(M);
+  build_exceptions_kernel<<<B * nparts, kExcThreads, smem, as_stream(stream)>>>(ind, mask_idx, wn, wo, N, M, exc_start, exc_cnt,
+                                                                               exc_l, exc_w, exc_total, exc_cap, nparts);
   return check_launch("ipsr_build_exceptions");
 }
 
@@ -228,9 +221,9 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   if (M > 1)
     IPSR_REQUIRE(exc_start && exc_cnt && exc_l && exc_w && exc_total && ind && mask_idx && wn && wo, IPSR_ERR_INVALID_ARG,
                  "ipsr_shift_bwd: exception lists / replay operands missing");
-  // channel rows per CTA: 8 while 8*N floats fit in ~64 KiB, else 4, 2, 1
+  // channel rows per CTA: the largest of 8, 4, 2, 1 that divides C and keeps the CTA near 112 KiB of shared memory
   int CT = 8;
-  while (CT > 1 && (size_t)(CT + 3) * N * sizeof(float) > 80 * 1024) CT >>= 1;
+  while (CT > 1 && (C % CT != 0 || (size_t)(CT + 3) * N * sizeof(float) > 112 * 1024)) CT >>= 1;
   const size_t smem = (size_t)CT * N * sizeof(float) + (size_t)(3 * N + 2) * sizeof(int);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
   void (*kern)(const float*, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
@@ -245,7 +238,7 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "shift_bwd smem attribute: %s", cudaGetErrorString(e));
   }
-  kern<<<dim3((C + CT - 1) / CT, B), 256, smem, as_stream(stream)>>>(g, C, N, M, route_ptr, route_q, exc_start, exc_cnt,
+  kern<<<dim3(C / CT, B), 256, smem, as_stream(stream)>>>(g, C, N, M, route_ptr, route_q, exc_start, exc_cnt,
                                                                      exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn,
                                                                      wo, triple_w, gin);
   return check_launch("ipsr_shift_bwd");

@@ -152,6 +152,13 @@ int ipsr_maxcoord(const float* s, int P, int L, int64_t* ind_i64, float* vmax, v
 int ipsr_blend_stage(const float* xt, const float* r_masked, const float* inv_norm,
                      const int32_t* ind, const int32_t* mask_idx, int B, int C, int N, int M,
                      float* staged, float* vmask, void* stream);
+/* ipsr_blend_stage + ipsr_build_routes as ONE launch (the route builders depend on ind only and are
+ * latency-bound; they overlap the gather / Gram work).  route_ptr == NULL: plain ipsr_blend_stage.
+ * M == 0: only the routes are built. */
+int ipsr_blend_stage_with_routes(const float* xt, const float* r_masked, const float* inv_norm,
+                                 const int32_t* ind, const int32_t* mask_idx, const int32_t* flag,
+                                 int B, int C, int N, int M, float* staged, float* vmask,
+                                 int32_t* route_ptr, int32_t* route_q, void* stream);
 /* steps per staged block (32 for C <= 256, 16 for C <= 512, else 8) and floats per staged block */
 int ipsr_scan_block_steps(int C);
 int ipsr_staged_block_floats(int C);
@@ -203,9 +210,9 @@ int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
                    const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
                    float triple_w, float* gin, void* stream);
 
-/* ipsr_paste + ipsr_build_routes + ipsr_build_exceptions as ONE launch (the three are independent
- * once the scan has finished; the latency-bound builders overlap the bandwidth-bound paste).
- * exc_total must be zero on entry. */
+/* ipsr_paste (+ ipsr_build_routes) + ipsr_build_exceptions as ONE launch (independent once the scan has
+ * finished; the latency-bound builders overlap the bandwidth-bound paste).  route_ptr == NULL: the routes
+ * were already built (ipsr_blend_stage_with_routes).  exc_total must be zero on entry. */
 int ipsr_paste_with_bookkeeping(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
                                 const int32_t* flag, const int32_t* mask_idx, const float* wn, const float* wo,
                                 int B, int C, int N, int M, float* out,
