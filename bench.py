@@ -299,9 +299,15 @@ def run_ours(args):
     tensor_mode = args.mode == "tensor" or (args.mode == "auto" and C % 64 == 0 and N % 128 == 0)
     flops = 2.0 * N * N * C * B                                    # algorithmic: one N x N x C correlation per image
     achieved = flops / (corr_ms * 1e-3) / 1e12
+    traffic = None                                                 # DRAM bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath) and (B, C, H) == (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"]):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic = next((v for k, v in tj.items() if "corr_tc" in k), None) if tensor_mode else None
     roofline = {"bound": "tensor", "kernel": "corr_tc_kernel (tcgen05, 3 x bf16 split)" if tensor_mode else "corr_fp32_kernel (FFMA)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": None, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
+                "traffic": traffic, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
                 "peak_source": pk["source"] + " bf16 dense, sustained",
                 "note": "algorithmic FLOPs = 2*N^2*C per image (the 3 split passes are not counted: ceiling = 1/3 of peak)"}
 
@@ -374,7 +380,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_img = args.cpu_images or (24 if H <= 32 else 6)
+        n_img = args.cpu_images or (1200 if H <= 32 else 40)        # ~10-20 s of CPU work
         ips, threads, secs = cpu_path_images_per_sec(C, H, H, n_img)
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d images of the workload (B=1 each), fwd+bwd, fp32, %.1f s" % (n_img, secs)}
