@@ -311,6 +311,17 @@ def run_ours(args):
                 "peak_source": pk["source"] + " bf16 dense, sustained",
                 "note": "algorithmic FLOPs = 2*N^2*C per image (the 3 split passes are not counted: ceiling = 1/3 of peak)"}
 
+    # ---- workload diagnostics (one eager step): rows deferred to the exact path, attention entries that survive the
+    # reference's int64 truncation ("exceptions" of the backward), hub columns
+    _, dsaved = shift_ops.shift_forward(sets[0][0], sets[0][1], mi, need_grad=True, diagnostics=True)
+    torch.cuda.synchronize()
+    rp = dsaved.route_ptr.long()
+    diag = {"recheck_rows_per_image": float(dsaved.nrecheck.float().mean()),
+            "exceptions_per_image_mean": float(dsaved.exc_total.float().mean()) if dsaved.exc_total is not None else 0.0,
+            "exceptions_per_image_max": int(dsaved.exc_total.max()) if dsaved.exc_total is not None else 0,
+            "exception_columns_per_image": float((dsaved.exc_cnt > 0).float().sum(1).mean()) if dsaved.exc_cnt is not None else 0.0,
+            "max_routes_per_column": int((rp[:, 1:] - rp[:, :-1]).max())}
+
     # ---- e2e: reference-shaped module API, host pinned buffers, H2D + D2H inside the timed region ----
     Ref = collections.namedtuple("Ref", ["relu4_3"])
     layer = IPSR_model(5 / 16.0, 1, 1, 1, 1, 1)
@@ -397,7 +408,7 @@ def run_ours(args):
                        "parallelism": "batch-sharded x%d, no data-path collective" % world,
                        "mode": args.mode, "cuda_graphs": graphs is not None,
                        "l2": "rotating pool of %d input sets (%d MB) > 126 MB L2" % (pool, pool * bytes_per_set >> 20)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "diagnostics": diag,
             "gpu_launches": launches_per_step * K,
         }
         print(json.dumps(line), flush=True)

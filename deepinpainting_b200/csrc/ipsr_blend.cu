@@ -313,34 +313,62 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
 // ---------------------------------------------------------------------------------------------
 // paste
 // ---------------------------------------------------------------------------------------------
-// A CTA stages CT channel rows of x[b] (N floats each) in shared memory and writes the CT output
-// rows: coalesced reads, coalesced writes, gather inside the SM.
+// A CTA stages CT channel rows of x[b] (N floats each, contiguous in NCHW) in shared memory with one bulk
+// async copy -- its threads fetch rank / ind of their positions meanwhile -- and writes the CT output rows:
+// coalesced reads, coalesced writes, gather inside the SM.
+constexpr int kPastePre = 4;
+
 __device__ __forceinline__ void
 paste_cta(int cx, int b, float* rows, const float* __restrict__ x, const float* __restrict__ y,
           const int* __restrict__ ind, const int* __restrict__ rank, int C, int N, int M, int CT,
           float* __restrict__ out) {
+  __shared__ __align__(8) unsigned long long paste_bar;
   const int c0 = cx * CT;
   const int ct = min(CT, C - c0);
   const float* xb = x + ((size_t)b * C + c0) * N;
   float* ob = out + ((size_t)b * C + c0) * N;
   const int total = ct * N;
-  if ((N & 3) == 0) {
-    const float4* s4 = reinterpret_cast<const float4*>(xb);
-    float4* d4 = reinterpret_cast<float4*>(rows);
-    for (int i = threadIdx.x; i < total / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  const bool bulk = ((total & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(smem_u32(&paste_bar), 1);
+      mbar_fence_init();
+      mbar_expect_tx(smem_u32(&paste_bar), (uint32_t)total * 4u);
+      bulk_g2s(smem_u32(rows), xb, (uint32_t)total * 4u, smem_u32(&paste_bar));
+    }
   } else {
     for (int i = threadIdx.x; i < total; i += blockDim.x) rows[i] = __ldg(xb + i);
   }
   __syncthreads();
+  bool landed = !bulk;
   const int* indb = ind + (size_t)b * N;
-  for (int q = threadIdx.x; q < N; q += blockDim.x) {
-    const int l = rank[q];
-    if (l < 0) {
-      const int p = indb[q];
-      for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = rows[ch * N + p];
-    } else {
-      const float* yr = y + ((size_t)b * padded_steps(M) + l) * C + c0;
-      for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = __ldg(yr + ch);
+  const float* yb = y + (size_t)b * padded_steps(M) * C + c0;
+  for (int base = 0; base < N; base += 256 * kPastePre) {
+    int lq[kPastePre], pq[kPastePre];
+#pragma unroll
+    for (int i = 0; i < kPastePre; ++i) {
+      const int q = base + i * 256 + threadIdx.x;
+      lq[i] = -1;
+      pq[i] = 0;
+      if (q < N) {
+        lq[i] = __ldg(rank + q);
+        pq[i] = __ldg(indb + q);
+      }
+    }
+    if (!landed) {
+      mbar_wait(smem_u32(&paste_bar), 0);
+      landed = true;
+    }
+#pragma unroll
+    for (int i = 0; i < kPastePre; ++i) {
+      const int q = base + i * 256 + threadIdx.x;
+      if (q >= N) continue;
+      if (lq[i] < 0) {
+        for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = rows[ch * N + pq[i]];
+      } else {
+        const float* yr = yb + (size_t)lq[i] * C;
+        for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = __ldg(yr + ch);
+      }
     }
   }
 }
@@ -349,7 +377,7 @@ paste_cta(int cx, int b, float* rows, const float* __restrict__ x, const float* 
 __global__ void __launch_bounds__(256)
 paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ ind,
              const int* __restrict__ rank, int C, int N, int M, int CT, float* __restrict__ out) {
-  extern __shared__ __align__(16) float rows[];          // [CT][N]
+  extern __shared__ __align__(128) float rows[];         // [CT][N]
   paste_cta(blockIdx.x, blockIdx.y, rows, x, y, ind, rank, C, N, M, CT, out);
 }
 
@@ -365,7 +393,7 @@ struct FusedPasteArgs {
 };
 
 __global__ void __launch_bounds__(256) paste_fused_kernel(const FusedPasteArgs a) {
-  extern __shared__ __align__(16) float fsm[];
+  extern __shared__ __align__(128) float fsm[];
   int blk = blockIdx.x;
   if (blk < a.n_routes) {
     build_routes_cta(blk, reinterpret_cast<int*>(fsm), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q);
@@ -382,8 +410,10 @@ __global__ void __launch_bounds__(256) paste_fused_kernel(const FusedPasteArgs a
 }
 
 static int paste_ct(int C, int N) {
-  // channel rows per CTA: ~64 KiB of shared memory, at least 1 row
-  int CT = (int)((64 * 1024) / ((size_t)N * sizeof(float)));
+  // channel rows per CTA: ~32 KiB of shared memory (several CTAs resident per SM, so that the bulk copy of one
+  // overlaps the gather of another), but at least 4 rows while they fit in 64 KiB (rank / ind are re-read per CTA)
+  int CT = (int)((32 * 1024) / ((size_t)N * sizeof(float)));
+  if (CT < 4) CT = (int)((64 * 1024) / ((size_t)N * sizeof(float))) >= 4 ? 4 : (int)((64 * 1024) / ((size_t)N * sizeof(float)));
   if (CT < 1) CT = 1;
   if (CT > 16) CT = 16;
   if (CT > C) CT = C;

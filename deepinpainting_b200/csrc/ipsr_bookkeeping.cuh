@@ -93,10 +93,11 @@ constexpr int kExcThreads = 256;
 // CTAs per image: one per 256 masked steps (every owner thread then walks the whole tail of the recurrence once)
 __host__ __device__ inline int exc_parts(int M) { return M <= kExcThreads ? 1 : (M + kExcThreads - 1) / kExcThreads; }
 
+// out_q receives the POSITION q_l = mask_idx[l] of every surviving entry (the backward gathers g[:, q_l])
 template <bool WRITE>
 __device__ __forceinline__ int replay_owner(int l0, int p, int base, int n, const float* s_wn, const float* s_wo,
-                                            const int* s_p, float& e, int cnt, int* __restrict__ out_l,
-                                            float* __restrict__ out_w) {
+                                            const int* s_p, const int* __restrict__ mask_idx, float& e, int cnt,
+                                            int* __restrict__ out_l, float* __restrict__ out_w) {
   // processes steps l in [max(base, l0), base+n) of this chunk
   int i = l0 - base;
   if (i >= n) return cnt;
@@ -104,7 +105,7 @@ __device__ __forceinline__ int replay_owner(int l0, int p, int base, int n, cons
     e = (l0 == 0) ? 1.f : s_wo[i];
     if (l0 >= 1 && !(fabsf(e) < 1.0f)) {
       if (WRITE) {
-        out_l[cnt] = l0;
+        out_l[cnt] = mask_idx[l0];
         out_w[cnt] = trunc_as_reference(e);
       }
       ++cnt;
@@ -119,7 +120,7 @@ __device__ __forceinline__ int replay_owner(int l0, int p, int base, int n, cons
     if (s_p[i] == p) e = __fadd_rn(e, s_wo[i]);             // row[p_l] += wo                :124
     if (!(fabsf(e) < 1.0f)) {                               // survives the int64 store      :134
       if (WRITE) {
-        out_l[cnt] = base + i;
+        out_l[cnt] = mask_idx[base + i];
         out_w[cnt] = trunc_as_reference(e);
       }
       ++cnt;
@@ -191,7 +192,7 @@ build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restri
     int found = 0;
     for (int base = base0; base < M; base += kExcChunk) {
       stage(base);
-      if (p >= 0) found = replay_owner<false>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, found, nullptr, nullptr);
+      if (p >= 0) found = replay_owner<false>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, found, nullptr, nullptr);
     }
     // reserve a contiguous slot range (placement is arbitrary, order inside is ascending l)
     int start = 0;
@@ -212,7 +213,7 @@ build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restri
       for (int base = base0; base < M; base += kExcChunk) {
         stage(base);
         if (p >= 0)
-          cnt = replay_owner<true>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, e, cnt,
+          cnt = replay_owner<true>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, cnt,
                                    exc_l + (size_t)b * exc_cap + start, exc_w + (size_t)b * exc_cap + start);
       }
     }

@@ -30,13 +30,17 @@ build_exceptions_kernel(const int* __restrict__ ind, const int* __restrict__ mas
 // ---------------------------------------------------------------------------------------------
 // backward proper
 // ---------------------------------------------------------------------------------------------
-// grid = (C / CT, B): the CTA stages CT rows of g[b] (C % CT == 0) and the CSR of the image in shared
-// memory.  Light bank columns (few routes) are summed by their own thread, in a loop of exactly their
-// route count; heavy ones -- a non-negative reference makes a few "hub" patches the best match of
-// hundreds of positions -- are queued and summed by whole warps (lane-strided partial sums in ascending q,
-// then a fixed xor tree: deterministic).  If the exception lists overflowed (exc_total > exc_cap, chaotic
-// inputs only) the column replays the recurrence.
+// grid = (C / CT, B): the CTA stages CT rows of g[b] (C % CT == 0) in shared memory with ONE bulk async copy
+// (the rows are contiguous in NCHW) while its threads already fetch the CSR entries of their columns.
+// Shared memory holds nothing but the rows (+ a small queue), so several CTAs are resident per SM and the
+// copy of one overlaps the gather of another.  Light bank columns (few routes / exceptions) are summed
+// by their own thread in a loop of exactly their entry count; heavy ones -- a non-negative reference makes
+// a few "hub" patches the best match of hundreds of positions -- are queued and summed by whole warps
+// (lane-strided partial sums in ascending q, then a fixed xor tree: deterministic).  If the exception lists
+// overflowed (exc_total > exc_cap, chaotic inputs only) the column replays the recurrence.
 constexpr int kBwdLight = 12;
+constexpr int kBwdQueue = 1024;
+constexpr int kBwdPre = 4;               // columns per thread whose CSR entries are fetched ahead
 
 template <int CT>
 __global__ void __launch_bounds__(256)
@@ -45,32 +49,29 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
                  const int* __restrict__ exc_l, const float* __restrict__ exc_w, const int* __restrict__ exc_total,
                  int exc_cap, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                  const float* __restrict__ wn, const float* __restrict__ wo, float triple_w, float* __restrict__ gin) {
-  extern __shared__ __align__(16) float grow[];           // [CT][N], heavy-column queue [N], CSR copy [2N+1]
+  extern __shared__ __align__(128) float grow[];          // [CT][N]
+  __shared__ int heavy[kBwdQueue];
   __shared__ int nheavy;
-  int* heavy = reinterpret_cast<int*>(grow + (size_t)CT * N);   // [N] (every column can be heavy when exceptions abound)
-  int* ptr = heavy + N;                                          // [N+1]
-  int* rq = ptr + (N + 1);                                       // [N]
+  __shared__ __align__(8) unsigned long long bar;
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * CT;
   const float* gb = g + ((size_t)b * C + c0) * N;
   float* ob = gin + ((size_t)b * C + c0) * N;
   const int total = CT * N;
-  if (threadIdx.x == 0) nheavy = 0;
-  if ((N & 3) == 0) {
-    const float4* s4 = reinterpret_cast<const float4*>(gb);
-    float4* d4 = reinterpret_cast<float4*>(grow);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < total / 4; i += 256) d4[i] = __ldg(s4 + i);
-  } else {
+  const bool bulk = ((total & 3) == 0) && ((reinterpret_cast<uintptr_t>(gb) & 15) == 0);
+  if (threadIdx.x == 0) {
+    nheavy = 0;
+    if (bulk) {
+      mbar_init(smem_u32(&bar), 1);
+      mbar_fence_init();
+      mbar_expect_tx(smem_u32(&bar), (uint32_t)total * 4u);
+      bulk_g2s(smem_u32(grow), gb, (uint32_t)total * 4u, smem_u32(&bar));
+    }
+  }
+  if (!bulk)
     for (int i = threadIdx.x; i < total; i += 256) grow[i] = __ldg(gb + i);
-  }
-  {
-    // the index lists are shared by all channels: one coalesced copy replaces dependent global loads
-    const int* gptr = route_ptr + (size_t)b * (N + 1);
-    const int* grq = route_q + (size_t)b * N;
-    for (int i = threadIdx.x; i <= N; i += 256) ptr[i] = __ldg(gptr + i);
-    for (int i = threadIdx.x; i < N; i += 256) rq[i] = __ldg(grq + i);
-  }
+  const int* gptr = route_ptr + (size_t)b * (N + 1);
+  const int* grq = route_q + (size_t)b * N;
   const bool has_exc = (M > 1) && exc_cnt && exc_total && (exc_total[b] != 0);
   const bool overflow = has_exc && (exc_total[b] > exc_cap);
   const bool lists = has_exc && !overflow;
@@ -78,89 +79,109 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __
   const int* estart = exc_start + (size_t)b * N;
   const int* el = exc_l + (size_t)b * exc_cap;
   const float* ew = exc_w + (size_t)b * exc_cap;
-  __syncthreads();
+  __syncthreads();                                        // barrier initialised / plain copy complete
+  bool landed = !bulk;
 
-  for (int p = threadIdx.x; p < N; p += 256) {
-    const int r0 = ptr[p], r1 = ptr[p + 1];
-    const int ne = lists ? ecnt[p] : 0;
-    if ((r1 - r0) + ne > kBwdLight) {
-      heavy[atomicAdd(&nheavy, 1)] = p;                    // queue order does not affect any sum
-      continue;
-    }
-    float acc[CT];
+  auto replay = [&](int p, float (&acc)[CT]) {            // exception lists overflowed: rare, slow, bit-faithful
+    float e = (ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
+    for (int l = 1; l < M; ++l) {
+      const int ql = mask_idx[l];
+      e = __fmul_rn(e, wn[(size_t)b * M + l]);
+      if (ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, wo[(size_t)b * M + l]);
+      if (!(fabsf(e) < 1.0f)) {
+        const float w = trunc_as_reference(e);
 #pragma unroll
-    for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const int q = rq[r];
-#pragma unroll
-      for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
-    }
-    if (ne > 0) {
-      const int s = estart[p];
-      for (int e = 0; e < ne; ++e) {
-        const int q = mask_idx[el[s + e]];
-        const float w = ew[s + e];
-#pragma unroll
-        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
       }
     }
-    if (overflow) {
-      float e = (ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
-      for (int l = 1; l < M; ++l) {
-        const int ql = mask_idx[l];
-        e = __fmul_rn(e, wn[(size_t)b * M + l]);
-        if (ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, wo[(size_t)b * M + l]);
-        if (!(fabsf(e) < 1.0f)) {
-          const float w = trunc_as_reference(e);
+  };
+
+  for (int base = 0; base < N; base += 256 * kBwdPre) {
+    int r0[kBwdPre], r1[kBwdPre], ne[kBwdPre], es[kBwdPre], q0[kBwdPre];
 #pragma unroll
-          for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
+    for (int i = 0; i < kBwdPre; ++i) {
+      const int p = base + i * 256 + threadIdx.x;
+      r0[i] = r1[i] = ne[i] = es[i] = 0;
+      if (p < N) {
+        r0[i] = __ldg(gptr + p);
+        r1[i] = __ldg(gptr + p + 1);
+        if (lists) {
+          ne[i] = __ldg(ecnt + p);
+          es[i] = __ldg(estart + p);
         }
       }
     }
 #pragma unroll
-    for (int ch = 0; ch < CT; ++ch)                          // g + weighted * triple_w           :173
-      ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
+    for (int i = 0; i < kBwdPre; ++i) q0[i] = (r1[i] > r0[i]) ? __ldg(grq + r0[i]) : 0;
+    if (!landed) {
+      mbar_wait(smem_u32(&bar), 0);
+      landed = true;
+    }
+#pragma unroll
+    for (int i = 0; i < kBwdPre; ++i) {
+      const int p = base + i * 256 + threadIdx.x;
+      if (p >= N) continue;
+      const int n = r1[i] - r0[i];
+      if (n + ne[i] > kBwdLight) {
+        const int slot = atomicAdd(&nheavy, 1);            // queue order does not affect any sum
+        if (slot < kBwdQueue) {
+          heavy[slot] = p;
+          continue;
+        }
+      }
+      float acc[CT];
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
+      if (n > 0) {
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q0[i]];
+        for (int r = r0[i] + 1; r < r1[i]; ++r) {
+          const int q = __ldg(grq + r);
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
+        }
+      }
+      if (ne[i] > 0) {
+        const int s = es[i];
+        for (int e = 0; e < ne[i]; ++e) {
+          const int q = __ldg(el + s + e);
+          const float w = __ldg(ew + s + e);
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+        }
+      }
+      if (overflow) replay(p, acc);
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch)                        // g + weighted * triple_w           :173
+        ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
+    }
   }
   __syncthreads();
 
   // heavy columns: one warp each
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nh = nheavy;
+  const int nh = min(nheavy, kBwdQueue);
   for (int h = warp; h < nh; h += 8) {
     const int p = heavy[h];
-    const int r0 = ptr[p], r1 = ptr[p + 1];
+    const int r0 = __ldg(gptr + p), r1 = __ldg(gptr + p + 1);
     float acc[CT];
 #pragma unroll
     for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
     for (int r = r0 + lane; r < r1; r += 32) {
-      const int q = rq[r];
+      const int q = __ldg(grq + r);
 #pragma unroll
       for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
     }
     if (lists) {
       const int ne = ecnt[p], s = estart[p];
       for (int e = lane; e < ne; e += 32) {
-        const int q = mask_idx[el[s + e]];
-        const float w = ew[s + e];
+        const int q = __ldg(el + s + e);
+        const float w = __ldg(ew + s + e);
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
       }
     }
-    if (overflow) {                                          // lane 0 replays (rare path)
-      if (lane == 0) {
-        float e = (ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
-        for (int l = 1; l < M; ++l) {
-          const int ql = mask_idx[l];
-          e = __fmul_rn(e, wn[(size_t)b * M + l]);
-          if (ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, wo[(size_t)b * M + l]);
-          if (!(fabsf(e) < 1.0f)) {
-            const float w = trunc_as_reference(e);
-#pragma unroll
-            for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
-          }
-        }
-      }
-    }
+    if (overflow && lane == 0) replay(p, acc);             // lane 0 replays (rare path)
 #pragma unroll
     for (int ch = 0; ch < CT; ++ch) acc[ch] = warp_sum(acc[ch]);
     if (lane == 0) {
@@ -221,11 +242,12 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   if (M > 1)
     IPSR_REQUIRE(exc_start && exc_cnt && exc_l && exc_w && exc_total && ind && mask_idx && wn && wo, IPSR_ERR_INVALID_ARG,
                  "ipsr_shift_bwd: exception lists / replay operands missing");
-  // channel rows per CTA: the largest of 8, 4, 2, 1 that divides C and keeps the CTA near 112 KiB of shared memory
+  // channel rows per CTA: the largest of 8, 4, 2, 1 that divides C and keeps the rows within 64 KiB of shared memory
+  // (>= 3 CTAs resident per SM: one CTA's bulk copy overlaps the gathers of the others)
   int CT = 8;
-  while (CT > 1 && (C % CT != 0 || (size_t)(CT + 3) * N * sizeof(float) > 112 * 1024)) CT >>= 1;
-  const size_t smem = (size_t)CT * N * sizeof(float) + (size_t)(3 * N + 2) * sizeof(int);
-  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
+  while (CT > 1 && (C % CT != 0 || (size_t)CT * N * sizeof(float) > 64 * 1024)) CT >>= 1;
+  const size_t smem = (size_t)CT * N * sizeof(float);
+  IPSR_REQUIRE(smem <= 200 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
   void (*kern)(const float*, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
                const int*, int, const int*, const int*, const float*, const float*, float, float*) = nullptr;
   switch (CT) {
@@ -239,7 +261,7 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "shift_bwd smem attribute: %s", cudaGetErrorString(e));
   }
   kern<<<dim3(C / CT, B), 256, smem, as_stream(stream)>>>(g, C, N, M, route_ptr, route_q, exc_start, exc_cnt,
-                                                                     exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn,
-                                                                     wo, triple_w, gin);
+                                                         exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn,
+                                                         wo, triple_w, gin);
   return check_launch("ipsr_shift_bwd");
 }

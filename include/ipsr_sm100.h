@@ -195,14 +195,15 @@ int ipsr_build_routes(const int32_t* ind, const int32_t* flag, const int32_t* ma
 
 /* Replay the attention rows (:123-125: row_l = row_{l-1}*wn_l; row_l[p_l] += wo_l) per bank
  * column and emit every entry of rows l >= 1 that survives the float -> int64 store:
- * exc_start/exc_cnt [B][N], exc_l / exc_w [B][exc_cap], exc_total [B] (zero on entry;
+ * exc_start/exc_cnt [B][N], exc_l / exc_w [B][exc_cap] (exc_l holds the POSITION q_l = mask_idx[l] of the row the
+ * entry belongs to, exc_w its truncated weight), exc_total [B] (zero on entry;
  * > exc_cap afterwards means the lists are incomplete and the backward replays instead). */
 int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
                           int B, int N, int M, int32_t* exc_start, int32_t* exc_cnt,
                           int32_t* exc_l, float* exc_w, int32_t* exc_total, int exc_cap, void* stream);
 
 /* gin[b,:,p] = g[b,:,p] + triple_w * ( sum_{q in routes(p)} g[b,:,q]
- *                                      + sum_{e in exc(p)} exc_w[e] * g[b,:,mask_idx[exc_l[e]]] ) */
+ *                                      + sum_{e in exc(p)} exc_w[e] * g[b,:,exc_l[e]] ) */
 int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
                    const int32_t* route_ptr, const int32_t* route_q,
                    const int32_t* exc_start, const int32_t* exc_cnt, const int32_t* exc_l, const float* exc_w,
