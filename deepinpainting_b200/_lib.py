@@ -32,7 +32,7 @@ class FwdArgs(C.Structure):
         ("out", _p), ("ind", _p), ("wn", _p), ("wo", _p),
         ("route_ptr", _p), ("route_q", _p),
         ("exc_start", _p), ("exc_cnt", _p), ("exc_l", _p), ("exc_w", _p), ("exc_total", _p),
-        ("nrecheck_out", _p), ("ev_corr_begin", _p), ("ev_corr_end", _p),
+        ("nrecheck_out", _p), ("npass2_out", _p), ("ev_corr_begin", _p), ("ev_corr_end", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -44,9 +44,12 @@ SIGNATURES = {
     "ipsr_tensor_path_supported": (_i, [_i, _i]),
     "ipsr_feat_mask": (_i, [_p, _i, _i, _i, _f, _p, _p, _p]),
     "ipsr_build_flags": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
-    "ipsr_extract_normalize": (_i, [_p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "ipsr_correlate_argmax_tc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
-    "ipsr_finalize_argmax": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
+    "ipsr_extract_normalize": (_i, [_p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ipsr_compact_rows": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ipsr_correlate_argmax_tc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ipsr_finalize_argmax": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _i,
+                                  _p, _p, _p, _p, _p, _p]),
+    "ipsr_resolve_rows": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "ipsr_select_all_rows": (_i, [_i, _i, _p, _p, _p, _p]),
     "ipsr_correlate_argmax_fp32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p]),
     "ipsr_apply_recheck": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),

@@ -30,13 +30,17 @@ int check_launch(const char* what) {
 }
 
 constexpr int kMaxPsplit = 8;
-constexpr float kDefaultTolRel = 5e-5f;   // x ||R[q]||: > 2x the worst-case error of the 3 x bf16 split
+// Error allowances of the tcgen05 passes, relative to ||R[q]|| (measured fp32-accumulation error of a C <= 512
+// contraction: 4e-7, scripts/tc_accum_error.py; worst case of truncating adds ~ 6e-6).
+constexpr float kAccumAllowance = 8e-6f;                 // pass 1: added to the exact operand-rounding bound
+constexpr float kDefaultTolRel = 2.0f * (kAccumAllowance + 1.2e-6f);   // pass 2: accumulation + dropped lo*lo + lo rounding
 constexpr float kDefaultTolAbs = 1e-12f;
 
 struct Workspace {
   size_t total = 0;
-  size_t inv_norm, rnorm, counters /* nonfinite[B] + nrecheck[B] */, xt, r_masked, staged, vmask, y, packed, list;
-  size_t x_tiles, r_tiles, part_best, part_idx, part_second;
+  size_t inv_norm, rnorm, counters /* nonfinite[B] + nrecheck[B] + npass2[B] + xerr_max[B] + npair[B] */, xt, r_masked, staged, vmask, y,
+      packed, list;
+  size_t x_tiles, r_tiles, c_tiles, rscale, rerr, list2, part_best, part_idx, part_second, part_idx2, part_third, cand2, pair_list;
   bool tensor = false;
 };
 
@@ -57,7 +61,7 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
   const size_t BN = (size_t)B * N, BM = (size_t)B * (M > 0 ? M : 1);
   w.inv_norm = take(cur, BN * 4);
   w.rnorm = take(cur, BN * 4);
-  w.counters = take(cur, (size_t)2 * B * 4);
+  w.counters = take(cur, (size_t)5 * B * 4);
   w.xt = take(cur, BN * C * 4);
   w.r_masked = take(cur, BM * C * 4);
   w.staged = take(cur, (size_t)B * (size_t)((M + ipsr_scan_block_steps(C) - 1) / ipsr_scan_block_steps(C) + 1) *
@@ -68,13 +72,22 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
   w.list = take(cur, BN * 4);
   w.tensor = (resolve_mode(mode, C, N) == IPSR_MODE_TENSOR);
   if (w.tensor) {
-    w.x_tiles = take(cur, BN * C * 4);
-    w.r_tiles = take(cur, BN * C * 4);
+    w.x_tiles = take(cur, BN * C * 4);                 // fp16 hi + lo of Xn
+    w.r_tiles = take(cur, BN * C * 4);                 // fp16 hi + lo of R
+    w.c_tiles = take(cur, BN * C * 4);                 // fp16 hi + lo of the compacted ambiguous rows of R
+    w.rscale = take(cur, BN * 4);
+    w.rerr = take(cur, BN * 4);
+    w.list2 = take(cur, BN * 4);
     w.part_best = take(cur, (size_t)kMaxPsplit * BN * 4);
     w.part_idx = take(cur, (size_t)kMaxPsplit * BN * 4);
     w.part_second = take(cur, (size_t)kMaxPsplit * BN * 4);
+    w.part_idx2 = take(cur, (size_t)kMaxPsplit * BN * 4);
+    w.part_third = take(cur, (size_t)kMaxPsplit * BN * 4);
+    w.cand2 = take(cur, BN * 4);
+    w.pair_list = take(cur, BN * 4);
   } else {
-    w.x_tiles = w.r_tiles = w.part_best = w.part_idx = w.part_second = 0;
+    w.x_tiles = w.r_tiles = w.c_tiles = w.rscale = w.rerr = w.list2 = w.part_best = w.part_idx = w.part_second = 0;
+    w.part_idx2 = w.part_third = w.cand2 = w.pair_list = 0;
   }
   w.total = cur;
   return w;
@@ -159,10 +172,13 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   cudaStream_t st = as_stream(stream);
   int32_t* nonfinite = at<int32_t>(a, w.counters);
   int32_t* nrecheck = nonfinite + B;
+  int32_t* npass2 = nrecheck + B;
+  float* xerr_max = reinterpret_cast<float*>(npass2 + B);
+  int32_t* npair = npass2 + 2 * B;
   int32_t* list = at<int32_t>(a, w.list);
   int64_t* packed = at<int64_t>(a, w.packed);
 
-  cudaError_t e = cudaMemsetAsync(nonfinite, 0, (size_t)2 * B * sizeof(int32_t), st);
+  cudaError_t e = cudaMemsetAsync(nonfinite, 0, (size_t)5 * B * sizeof(int32_t), st);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memset: %s", cudaGetErrorString(e));
   if (a->need_grad && M > 1) {
     e = cudaMemsetAsync(a->exc_total, 0, (size_t)B * sizeof(int32_t), st);
@@ -179,29 +195,45 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   IPSR_FORWARD(ipsr_extract_normalize(a->x, a->ref, B, C, N, a->rank, M, at<float>(a, w.inv_norm), at<float>(a, w.rnorm),
                                       at<float>(a, w.xt), at<float>(a, w.r_masked),
                                       tensor ? at<void>(a, w.x_tiles) : nullptr, tensor ? at<void>(a, w.r_tiles) : nullptr,
-                                      nonfinite, stream));
+                                      nonfinite, tensor ? at<float>(a, w.rscale) : nullptr,
+                                      tensor ? at<float>(a, w.rerr) : nullptr, nullptr, tensor ? xerr_max : nullptr, stream));
   if (tensor) {
-    int psplit = a->psplit;
-    if (psplit <= 0) {
+    const int RB = N / kTileRows;
+    auto auto_split = [&](long long tiles) {
       // one CTA per SM is resident (the ring + row tile fill shared memory): split the bank columns only
       // while that still adds whole CTAs to a single wave
-      const long long tiles = (long long)B * (N / kTileRows);
-      psplit = (int)(148 / tiles);
-    }
-    if (psplit > kMaxPsplit) psplit = kMaxPsplit;
-    const int max_split = (ce - cb) / 128;
-    if (psplit > max_split) psplit = max_split;
-    if (psplit < 1) psplit = 1;
-    IPSR_FORWARD(record(a->ev_corr_begin));
-    IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, psplit,
-                                          at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
-                                          at<float>(a, w.part_second), nullptr, stream));
-    IPSR_FORWARD(record(a->ev_corr_end));
-    const float tol_rel = a->tol_rel >= 0.f ? a->tol_rel : kDefaultTolRel;
+      int ps = a->psplit > 0 ? a->psplit : (int)(148 / (tiles > 0 ? tiles : 1));
+      if (ps > kMaxPsplit) ps = kMaxPsplit;
+      const int max_split = (ce - cb) / 128;
+      if (ps > max_split) ps = max_split;
+      return ps < 1 ? 1 : ps;
+    };
     const float tol_abs = a->tol_abs >= 0.f ? a->tol_abs : kDefaultTolAbs;
+    int32_t* list2 = at<int32_t>(a, w.list2);
+    // pass 1: hi * hi over every row
+    const int ps1 = auto_split((long long)B * RB);
+    IPSR_FORWARD(record(a->ev_corr_begin));
+    IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps1, 1, 2, nullptr,
+                                          at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
+                                          at<float>(a, w.part_second), nullptr, nullptr, nullptr, stream));
+    IPSR_FORWARD(record(a->ev_corr_end));
     IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
-                                      psplit, at<float>(a, w.rnorm), nonfinite, B, N, tol_rel, tol_abs, a->ind, list,
-                                      nrecheck, packed, stream));
+                                      ps1, at<float>(a, w.rnorm), at<float>(a, w.rscale), at<float>(a, w.rerr), xerr_max,
+                                      nonfinite, nullptr, nullptr, B, N, kAccumAllowance, tol_abs, a->ind, list2, npass2,
+                                      packed, at<void>(a, w.r_tiles), at<void>(a, w.c_tiles), C, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, stream));
+    // pass 2: the three-pass split over the ambiguous rows finalize just compacted (typically a few % of the rows)
+    const int ps2 = auto_split((long long)B * (RB >= 8 ? RB / 8 : 1));
+    IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.c_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps2, 3, 2, npass2,
+                                          at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
+                                          at<float>(a, w.part_second), at<int32_t>(a, w.part_idx2),
+                                          at<float>(a, w.part_third), nullptr, stream));
+    const float tol_rel = a->tol_rel >= 0.f ? a->tol_rel : kDefaultTolRel;
+    IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
+                                      ps2, at<float>(a, w.rnorm), at<float>(a, w.rscale), nullptr, nullptr, nonfinite, list2,
+                                      npass2, B, N, tol_rel, tol_abs, a->ind, list, nrecheck, nullptr, nullptr, nullptr, C,
+                                      at<int32_t>(a, w.part_idx2), at<float>(a, w.part_third), at<int32_t>(a, w.cand2),
+                                      at<int32_t>(a, w.pair_list), npair, stream));
   } else {
     IPSR_FORWARD(ipsr_select_all_rows(B, N, list, nrecheck, packed, stream));
   }
@@ -213,13 +245,20 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
     e = cudaMemcpyAsync(a->nrecheck_out, nrecheck, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memcpy: %s", cudaGetErrorString(e));
   }
+  if (a->npass2_out) {
+    e = cudaMemcpyAsync(a->npass2_out, npass2, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memcpy: %s", cudaGetErrorString(e));
+  }
+  // rows recomputed in exact fp32 take their key; rows with exactly two candidates are settled by two exact dot products
+  IPSR_FORWARD(ipsr_resolve_rows(packed, list, nrecheck, tensor ? at<int32_t>(a, w.pair_list) : nullptr, npair,
+                                 tensor ? at<int32_t>(a, w.cand2) : nullptr, at<float>(a, w.xt), a->ref,
+                                 at<float>(a, w.inv_norm), B, C, N, a->ind, nullptr, stream));
   if (a->stop_after_corr) {
     // bank-sharded mode: every row leaves with an exact (score, idx) key of its LOCAL winner
     if (tensor)
       IPSR_FORWARD(ipsr_pack_winner_scores(at<float>(a, w.xt), a->ref, at<float>(a, w.inv_norm), a->ind, B, C, N, packed, stream));
     return IPSR_OK;
   }
-  IPSR_FORWARD(ipsr_apply_recheck(packed, list, nrecheck, B, N, a->ind, nullptr, stream));
   return run_blend_and_paste(a, w, stream);
 }
 

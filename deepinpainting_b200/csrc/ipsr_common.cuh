@@ -2,7 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -34,18 +34,23 @@ int check_launch(const char* what);
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------------------------------------
-// tile-image geometry of the bf16 hi/lo operands (written by prep, read by the tcgen05 GEMM)
+// tile-image geometry of the fp16 hi/lo operands (written by prep, read by the tcgen05 GEMM)
 //   [B][KB = C/64][2 (hi, lo)][RB = N/128][128 rows x 128 bytes, 128B swizzle]
 // ---------------------------------------------------------------------------------------------
 constexpr int kTileRows = 128;
-constexpr int kTileK = 64;                       // bf16 elements per row of a tile = 128 bytes
+constexpr int kTileK = 64;                       // fp16 elements per row of a tile = 128 bytes
 constexpr int kTileBytes = kTileRows * kTileK * 2;  // 16 KiB
 
 __host__ __device__ inline size_t tile_offset_bytes(int b, int kb, int hl, int rb, int KB, int RB) {
   return ((((size_t)b * KB + kb) * 2 + hl) * RB + rb) * (size_t)kTileBytes;
 }
 
-// byte offset of the 16-byte chunk `chunk` (0..7, 8 bf16 each) of row `r` (0..127) inside a tile
+// same with `nhalf` operand parts per 64-channel block (1: hi only, 2: hi, lo)
+__host__ __device__ inline size_t tile_offset_bytes_n(int b, int kb, int hl, int rb, int KB, int RB, int nhalf) {
+  return ((((size_t)b * KB + kb) * nhalf + hl) * RB + rb) * (size_t)kTileBytes;
+}
+
+// byte offset of the 16-byte chunk `chunk` (0..7, 8 fp16 each) of row `r` (0..127) inside a tile
 // image: canonical UMMA K-major SWIZZLE_128B layout = Swizzle<3,4,3> on (row*128 + chunk*16).
 __host__ __device__ inline uint32_t tile_chunk_offset(int r, int chunk) {
   return (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
@@ -152,8 +157,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 x fp16 -> fp32 (operand types come from idesc), issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -193,9 +198,10 @@ __host__ __device__ inline uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// tcgen05 instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M x N tile.
-__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// tcgen05 instruction descriptor, kind::f16: D = fp32 (bits 4-5 = 1), A = B = fp16 (format fields bits 7-9 and
+// 10-12 = 0; 1 would be bf16), both K-major, M x N tile.
+__host__ __device__ inline uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ipsr

@@ -213,6 +213,53 @@ __global__ void apply_recheck_kernel(const long long* __restrict__ packed, const
   if (vmax) vmax[(size_t)b * N + q] = v;
 }
 
+// Settles what the tensor passes left open, in one launch:
+//   (1) rows of `list` (recomputed in exact fp32 by ipsr_correlate_argmax_fp32): ind[b,q] <- packed[b,q];
+//   (2) rows of `pair_list` (exactly two candidates, ind[b,q] and cand2[b,q], inside the error band of the
+//       three-pass split): one warp computes both exact fp32 scores <R[q], fl(X[p] inv_norm[p])> and keeps the
+//       larger one (the lower column on a tie, torch.max).
+// grid = (G, B), 256 threads.
+__global__ void __launch_bounds__(256)
+resolve_kernel(const long long* __restrict__ packed, const int* __restrict__ list, const int* __restrict__ nlist,
+               const int* __restrict__ pair_list, const int* __restrict__ npair, const int* __restrict__ cand2,
+               const float* __restrict__ xt, const float* __restrict__ ref, const float* __restrict__ inv_norm,
+               int C, int N, int* __restrict__ ind, float* __restrict__ vmax) {
+  const int b = blockIdx.y;
+  const int nl = min(nlist[b], N);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) {
+    const int q = list[(size_t)b * N + i];
+    float v;
+    int idx;
+    unpack_maxidx(packed[(size_t)b * N + q], &v, &idx);
+    ind[(size_t)b * N + q] = idx;
+    if (vmax) vmax[(size_t)b * N + q] = v;
+  }
+  if (!pair_list) return;
+  const int np = min(npair[b], N);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = blockIdx.x * 8 + warp; j < np; j += gridDim.x * 8) {
+    const int q = pair_list[(size_t)b * N + j];
+    const int p1 = ind[(size_t)b * N + q], p2 = cand2[(size_t)b * N + q];
+    const float i1 = inv_norm[(size_t)b * N + p1], i2 = inv_norm[(size_t)b * N + p2];
+    const float* x1 = xt + ((size_t)b * N + p1) * C;
+    const float* x2 = xt + ((size_t)b * N + p2) * C;
+    const float* rr = ref + (size_t)b * C * N + q;
+    float a1 = 0.f, a2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float r = __ldg(rr + (size_t)c * N);
+      a1 = fmaf(r, __fmul_rn(__ldg(x1 + c), i1), a1);      // Xn = fl(X * inv_norm)   (NPS:40)
+      a2 = fmaf(r, __fmul_rn(__ldg(x2 + c), i2), a2);
+    }
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (lane == 0) {
+      const bool second_wins = (a2 > a1) || (a2 == a1 && p2 < p1);
+      ind[(size_t)b * N + q] = second_wins ? p2 : p1;
+      if (vmax) vmax[(size_t)b * N + q] = second_wins ? a2 : a1;
+    }
+  }
+}
+
 // one warp per (b, q): exact score of the already chosen winner, as an exchange key.
 __global__ void __launch_bounds__(256)
 pack_winner_kernel(const float* __restrict__ xt, const float* __restrict__ ref, const float* __restrict__ inv_norm,
@@ -314,6 +361,22 @@ extern "C" int ipsr_apply_recheck(const int64_t* packed, const int32_t* recheck_
   apply_recheck_kernel<<<dim3((N + 255) / 256, B), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const long long*>(packed), recheck_list, nrecheck, N, ind, vmax);
   return check_launch("ipsr_apply_recheck");
+}
+
+extern "C" int ipsr_resolve_rows(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck,
+                                 const int32_t* pair_list, const int32_t* npair, const int32_t* cand2,
+                                 const float* xt, const float* ref, const float* inv_norm,
+                                 int B, int C, int N, int32_t* ind, float* vmax, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(packed && recheck_list && nrecheck && ind && B > 0 && N > 0 && C > 0 && B <= 65535, IPSR_ERR_INVALID_ARG,
+               "ipsr_resolve_rows: bad arguments");
+  IPSR_REQUIRE(!pair_list || (npair && cand2 && xt && ref && inv_norm), IPSR_ERR_INVALID_ARG,
+               "ipsr_resolve_rows: the pair list needs npair, cand2, xt, ref and inv_norm");
+  int G = (N + 255) / 256;
+  if (G > 8) G = 8;
+  resolve_kernel<<<dim3(G, B), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(packed), recheck_list, nrecheck,
+                                                            pair_list, npair, cand2, xt, ref, inv_norm, C, N, ind, vmax);
+  return check_launch("ipsr_resolve_rows");
 }
 
 extern "C" int ipsr_pack_winner_scores(const float* xt, const float* ref, const float* inv_norm, const int32_t* ind,

@@ -2,50 +2,65 @@
 // epilogue.  Replaces models/IPSRFunction.py:59 (conv_enc(ref) -> S[1,N,H,W] materialised) and
 // util/MaxCoord.py:21-22 (zeros_like(S) + torch.max(S, 1)); S never leaves the SM.
 //
-// Arithmetic: S = R * Xn^T with both operands split into bf16 hi + lo parts; three tcgen05.mma passes
-// (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) give |error| <~ 1e-5 * ||R[q]||, and rows whose
-// top-2 gap is inside that band are recomputed in exact fp32 (ipsr_correlate_argmax_fp32).
+// Arithmetic: S = R * Xn^T on power-of-two pre-scaled fp16 operands (ipsr_prep.cu), fp32 accumulation in TMEM,
+// as a precision CASCADE:
+//   pass 1 (PASSES = 1)  hi(R) * hi(X) over EVERY row: one tcgen05.mma pass at the full fp16 rate.  Its error is
+//                        rigorously bounded per row by rerr[q] + ||R~[q]|| * max_p xerr[p] (+ accumulation),
+//                        so a row whose top-2 gap exceeds twice that bound already has its fp32 arg-max;
+//   pass 2 (PASSES = 3)  hi*lo + lo*hi + hi*hi (~fp32 accurate) over the compacted ambiguous rows only
+//                        (ipsr_compact_rows; a few % of the rows), against the whole bank;
+//   pass 3               rows still inside the error band of pass 2 are recomputed in exact fp32
+//                        (ipsr_correlate_argmax_fp32).
 //
-// One CTA = 128 query rows (one TMEM lane each) x a range of bank columns, walked in blocks of
-// BLOCK_N columns.  Warp roles (192 threads):
-//   warp 0      producer: bulk async copies (UBLKCP) of pre-swizzled 16 KiB tile images -> smem ring
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue, commits free the ring slots
-//   warps 2..5  epilogue: tcgen05.ld of the finished accumulator (double-buffered in TMEM) and the
-//               running (best, idx, second) per row in registers -- thread == row, no shuffles.
-// A_RESIDENT: the R row tile (C <= 256: 128 KiB hi+lo) stays in shared memory for the whole CTA and
-// only bank tiles stream; otherwise both operands stream per 64-channel block.
+// One CTA = ROWT x 128 query rows (one TMEM lane each) x a range of bank columns, walked in blocks of 128
+// columns.  Warp roles (64 + 128*ROWT threads):
+//   warp 0       producer: bulk async copies (UBLKCP) of pre-swizzled 16 KiB tile images -> smem ring
+//   warp 1       TMEM allocation + single-thread tcgen05.mma issue, commits free the ring slots
+//   warps 2..    epilogue, 4 warps per row tile: tcgen05.ld of the finished accumulator (double-buffered in
+//                TMEM) and the running (best, idx, second) per row in registers -- thread == row, no shuffles.
+// A_RESIDENT: the R row tiles stay in shared memory for the whole CTA and only bank tiles stream (with
+// ROWT = 2 every streamed bank tile feeds 2 x 128 rows: half the L2 -> SM traffic per FLOP); otherwise both
+// operands stream per 64-channel block.
 #include "ipsr_common.cuh"
 
 namespace ipsr {
 
-constexpr int kTcThreads = 192;
+constexpr int kBlockN = 128;
 
 struct TcParams {
-  const uint8_t* r_tiles;
-  const uint8_t* x_tiles;
+  const uint8_t* r_tiles;   // [B][KB][a_parts][RB] tile images; PASSES 1 reads part 0 (hi), PASSES 3 parts 0, 1 (hi, lo)
+  int a_parts;
+  const uint8_t* x_tiles;   // [B][KB][2][RB] tile images (hi, lo)
+  const int* row_limit;     // optional [B]: only the first row_limit[b] rows of r_tiles are populated
   int B, KB, RB, N;
-  int col_begin;        // first bank column (multiple of 128)
-  int blocks_total;     // number of BLOCK_N column blocks in [col_begin, col_end)
+  int col_begin;            // first bank column (multiple of 128)
+  int blocks_total;         // number of 128-column blocks in [col_begin, col_end)
   int psplit;
   int stages;
   float* part_best;
   int* part_idx;
   float* part_second;
+  int* part_idx2;           // PASSES 3 only (optional): column of the runner-up and the third-best score, so that rows
+  float* part_third;        // with exactly two candidates inside the error band need two exact dot products, not N
   float* s_dump;
 };
 
-template <int BLOCK_N, bool A_RESIDENT>
-__global__ void __launch_bounds__(kTcThreads, 1) corr_tc_kernel(const TcParams prm) {
+template <int ROWT, int PASSES, bool A_RESIDENT>
+__global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcParams prm) {
+  static_assert(PASSES == 1 || PASSES == 3, "one hi*hi pass or the three-pass split");
+  static_assert(ROWT == 1 || (A_RESIDENT && ROWT == 2), "two row tiles need the resident A operand");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // manual 1024-byte alignment (SWIZZLE_128B atoms repeat every 1024 bytes)
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
 
-  constexpr int kBTiles = BLOCK_N / 128;                       // 16 KiB tiles per bank operand half
-  constexpr uint32_t kStageBytes = (A_RESIDENT ? 0u : 2u * kTileBytes) + 2u * kBTiles * kTileBytes;
+  constexpr int AH = (PASSES == 3) ? 2 : 1;                    // operand parts per 64-channel block (hi[, lo])
+  constexpr uint32_t kStageBytes = (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes) + (uint32_t)AH * kTileBytes;
+  constexpr int kEpiWarps = 4 * ROWT;
+  constexpr uint32_t kTmemCols = (uint32_t)ROWT * 2u * kBlockN;
   const int KB = prm.KB, RB = prm.RB;
-  const uint32_t a_bytes = A_RESIDENT ? (uint32_t)KB * 2u * kTileBytes : 0u;
+  const uint32_t a_bytes = A_RESIDENT ? (uint32_t)ROWT * KB * AH * kTileBytes : 0u;
   const uint32_t a_base = base;
   const uint32_t ring_base = base + a_bytes;
   const uint32_t bar_base = ring_base + (uint32_t)prm.stages * kStageBytes;
@@ -60,11 +75,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) corr_tc_kernel(const TcParams p
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // work decomposition: blockIdx.x -> (b, rb, split)
+  // work decomposition: blockIdx.x -> (b, row-tile group, split)
+  const int RBG = RB / ROWT;
   int t = blockIdx.x;
   const int split = t % prm.psplit; t /= prm.psplit;
-  const int rb = t % RB;
-  const int b = t / RB;
+  const int rbg = t % RBG;
+  const int b = t / RBG;
+  if (prm.row_limit && rbg * ROWT * kTileRows >= prm.row_limit[b]) return;     // compacted operand: nothing here
   const int per = (prm.blocks_total + prm.psplit - 1) / prm.psplit;
   const int blk0 = split * per;
   const int blk1 = min(prm.blocks_total, blk0 + per);
@@ -78,11 +95,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) corr_tc_kernel(const TcParams p
     mbar_init(a_full_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);     // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), kEpiWarps);     // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -93,14 +110,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) corr_tc_kernel(const TcParams p
     if (lane == 0 && nblk > 0) {
       if (A_RESIDENT) {
         mbar_expect_tx(a_full_bar, a_bytes);
-        for (int kb = 0; kb < KB; ++kb)
-          for (int hl = 0; hl < 2; ++hl)
-            bulk_g2s(a_base + (uint32_t)(kb * 2 + hl) * kTileBytes,
-                     prm.r_tiles + tile_offset_bytes(b, kb, hl, rb, KB, RB), kTileBytes, a_full_bar);
+        for (int rt = 0; rt < ROWT; ++rt)
+          for (int kb = 0; kb < KB; ++kb)
+            for (int hl = 0; hl < AH; ++hl)
+              bulk_g2s(a_base + (uint32_t)((rt * KB + kb) * AH + hl) * kTileBytes,
+                       prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg * ROWT + rt, KB, RB, prm.a_parts), kTileBytes, a_full_bar);
       }
       int it = 0;
       for (int blk = blk0; blk < blk1; ++blk) {
-        const int cb = (prm.col_begin >> 7) + blk * kBTiles;     // first 128-row bank tile of the block
+        const int cb = (prm.col_begin >> 7) + blk;                // 128-row bank tile of the block
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % prm.stages;
           const uint32_t ph = (uint32_t)(it / prm.stages) & 1u;
@@ -108,19 +126,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) corr_tc_kernel(const TcParams p
           mbar_expect_tx(full_bar(s), kStageBytes);
           uint32_t dst = ring_base + (uint32_t)s * kStageBytes;
           if (!A_RESIDENT) {
-            for (int hl = 0; hl < 2; ++hl, dst += kTileBytes)
-              bulk_g2s(dst, prm.r_tiles + tile_offset_bytes(b, kb, hl, rb, KB, RB), kTileBytes, full_bar(s));
+            for (int hl = 0; hl < AH; ++hl, dst += kTileBytes)
+              bulk_g2s(dst, prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg, KB, RB, prm.a_parts), kTileBytes, full_bar(s));
           }
-          for (int hl = 0; hl < 2; ++hl)
-            for (int tl = 0; tl < kBTiles; ++tl, dst += kTileBytes)
-              bulk_g2s(dst, prm.x_tiles + tile_offset_bytes(b, kb, hl, cb + tl, KB, RB), kTileBytes, full_bar(s));
+          for (int hl = 0; hl < AH; ++hl, dst += kTileBytes)
+            bulk_g2s(dst, prm.x_tiles + tile_offset_bytes(b, kb, hl, cb, KB, RB), kTileBytes, full_bar(s));
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && nblk > 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
+      const uint32_t idesc = umma_idesc_f16(128, kBlockN);
       if (A_RESIDENT) {
         mbar_wait(a_full_bar, 0);
         tc_fence_after();
@@ -131,62 +148,87 @@ __global__ void __launch_bounds__(kTcThreads, 1) corr_tc_kernel(const TcParams p
         const uint32_t aph = (uint32_t)(j >> 1) & 1u;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % prm.stages;
           const uint32_t ph = (uint32_t)(it / prm.stages) & 1u;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t stage = ring_base + (uint32_t)s * kStageBytes;
-          const uint32_t a_hi = A_RESIDENT ? a_base + (uint32_t)(kb * 2) * kTileBytes : stage;
-          const uint32_t a_lo = a_hi + kTileBytes;
-          const uint32_t b_hi = stage + (A_RESIDENT ? 0u : 2u * kTileBytes);
-          const uint32_t b_lo = b_hi + kBTiles * kTileBytes;
-          const uint64_t da[3] = {umma_desc_k_sw128(a_hi), umma_desc_k_sw128(a_hi), umma_desc_k_sw128(a_lo)};
-          const uint64_t db[3] = {umma_desc_k_sw128(b_lo), umma_desc_k_sw128(b_hi), umma_desc_k_sw128(b_hi)};
-          // small cross terms first, hi*hi last
+          const uint32_t b_hi = stage + (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes);
+          const uint32_t b_lo = b_hi + kTileBytes;
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const int pp = (pass == 0) ? 0 : (pass == 1 ? 2 : 1);   // hi*lo, lo*hi, hi*hi
+          for (int rt = 0; rt < ROWT; ++rt) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((rt * 2 + as) * kBlockN);
+            const uint32_t a_hi = A_RESIDENT ? a_base + (uint32_t)((rt * KB + kb) * AH) * kTileBytes : stage;
+            const uint32_t a_lo = a_hi + kTileBytes;
+            if (PASSES == 3) {
+              const uint64_t da[3] = {umma_desc_k_sw128(a_hi), umma_desc_k_sw128(a_lo), umma_desc_k_sw128(a_hi)};
+              const uint64_t db[3] = {umma_desc_k_sw128(b_lo), umma_desc_k_sw128(b_hi), umma_desc_k_sw128(b_hi)};
+              // small cross terms first, hi*hi last
 #pragma unroll
-            for (int k = 0; k < kTileK / 16; ++k) {
-              // +32 bytes per 16-element K step inside the 128-byte swizzle row (descriptor units of 16 B)
-              umma_bf16(d_tmem, da[pp] + (uint64_t)(2 * k), db[pp] + (uint64_t)(2 * k), idesc,
-                        (kb > 0 || pass > 0 || k > 0) ? 1u : 0u);
+              for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k) {
+                  // +32 bytes per 16-element K step inside the 128-byte swizzle row (descriptor units of 16 B)
+                  umma_f16(d_tmem, da[pass] + (uint64_t)(2 * k), db[pass] + (uint64_t)(2 * k), idesc,
+                           (kb > 0 || pass > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+            } else {
+              const uint64_t da = umma_desc_k_sw128(a_hi), db = umma_desc_k_sw128(b_hi);
+#pragma unroll
+              for (int k = 0; k < kTileK / 16; ++k)
+                umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(s));          // ring slot reusable once these MMAs retire
         }
-        umma_commit(tfull_bar(as));           // accumulator complete -> epilogue
+        umma_commit(tfull_bar(as));           // accumulators complete -> epilogue
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (thread == row)
+    const int rt = (warp - 2) >> 2;
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
-    const int q = rb * 128 + row;
-    float best = -INFINITY, second = -INFINITY;
-    int bidx = prm.col_begin + blk0 * BLOCK_N;
+    const int q = (rbg * ROWT + rt) * kTileRows + row;   // (compact) row index
+    float best = -INFINITY, second = -INFINITY, third = -INFINITY;
+    int bidx = prm.col_begin + blk0 * kBlockN, sidx = bidx;
+    const bool top3 = (PASSES == 3) && prm.part_idx2 != nullptr;
     float* dump = prm.s_dump ? prm.s_dump + ((size_t)b * prm.N + q) * prm.N : nullptr;
     for (int j = 0; j < nblk; ++j) {
       const int as = j & 1;
       const uint32_t aph = (uint32_t)(j >> 1) & 1u;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      const int colb = prm.col_begin + (blk0 + j) * BLOCK_N;
+      const int colb = prm.col_begin + (blk0 + j) * kBlockN;
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      for (int ch = 0; ch < kBlockN / 32; ++ch) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + ch * 32), r);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((rt * 2 + as) * kBlockN + ch * 32), r);
         tmem_ld_wait();
         const int c0 = colb + ch * 32;
+        if (top3) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float v = __uint_as_float(r[e]);
-          const bool gt = v > best;                       // strict: the lowest column wins ties
-          second = gt ? best : fmaxf(second, v);
-          bidx = gt ? (c0 + e) : bidx;
-          best = gt ? v : best;
+          for (int e = 0; e < 32; ++e) {
+            const float v = __uint_as_float(r[e]);
+            const bool g1 = v > best;                     // strict: the lowest column wins ties
+            const bool g2 = v > second;
+            third = g2 ? second : fmaxf(third, v);
+            sidx = g1 ? bidx : (g2 ? (c0 + e) : sidx);
+            second = g1 ? best : (g2 ? v : second);
+            bidx = g1 ? (c0 + e) : bidx;
+            best = g1 ? v : best;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float v = __uint_as_float(r[e]);
+            const bool gt = v > best;                     // strict: the lowest column wins ties
+            second = gt ? best : fmaxf(second, v);
+            bidx = gt ? (c0 + e) : bidx;
+            best = gt ? v : best;
+          }
         }
         if (dump) {
 #pragma unroll
@@ -204,60 +246,144 @@ __global__ void __launch_bounds__(kTcThreads, 1) corr_tc_kernel(const TcParams p
     prm.part_best[o] = best;
     prm.part_idx[o] = bidx;
     prm.part_second[o] = second;
+    if (top3) {
+      prm.part_idx2[o] = sidx;
+      prm.part_third[o] = third;
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-// Merge the per-split triples and decide which rows the tensor result can be trusted for.
+// Merge the per-split triples (scores in scaled units; true score = scaled * rscale[q] > 0 scaling) and decide
+// which rows can be trusted.
+//   pass 1 (list_in == NULL): row index = q;  tol[q] = 2 (rerr[q] + rnorm[q] (1.001 xerr_max[b] + acc)) + tol_abs
+//   pass 2 (list_in != NULL): row index r < nlist_in[b] is position q = list_in[b][r];  tol[q] = tol_rel rnorm[q] + tol_abs
+// Trusted rows get ind[b,q]; the others are appended to list_out[b] (order arbitrary).  Pass 1 with c_tiles != NULL
+// also COMPACTS: the hi and lo tile rows of every appended position are copied to row `pos` of the compact tile
+// images the three-pass split reads (one warp per row, 16-byte chunks, coalesced 128-byte tile rows).
 __global__ void finalize_kernel(const float* __restrict__ part_best, const int* __restrict__ part_idx,
                                 const float* __restrict__ part_second, int psplit, const float* __restrict__ rnorm,
-                                const int* __restrict__ nonfinite, int B, int N, float tol_rel, float tol_abs,
-                                int* __restrict__ ind, int* __restrict__ list, int* __restrict__ nlist,
-                                long long* __restrict__ packed) {
+                                const float* __restrict__ rscale, const float* __restrict__ rerr,
+                                const float* __restrict__ xerr_max, const int* __restrict__ nonfinite,
+                                const int* __restrict__ list_in, const int* __restrict__ nlist_in, int B, int N,
+                                float tol_rel, float tol_abs, int* __restrict__ ind, int* __restrict__ list_out,
+                                int* __restrict__ nlist_out, long long* __restrict__ packed,
+                                const uint8_t* __restrict__ r_tiles, uint8_t* __restrict__ c_tiles, int KB,
+                                const int* __restrict__ part_idx2, const float* __restrict__ part_third,
+                                int* __restrict__ cand2, int* __restrict__ pair_list, int* __restrict__ npair) {
   const int b = blockIdx.y;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= N) return;
-  float best = -INFINITY, second = -INFINITY;
-  int idx = 0;
-  for (int s = 0; s < psplit; ++s) {                     // splits are in ascending column order
-    const size_t o = ((size_t)s * B + b) * N + q;
-    const float vb = part_best[o], vs = part_second[o];
-    if (vb > best) {
-      second = fmaxf(best, vs);
-      best = vb;
-      idx = part_idx[o];
-    } else {
-      second = fmaxf(second, vb);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = r < N;
+  int q = r;
+  if (list_in) {
+    live = live && r < min(nlist_in[b], N);
+    if (live) q = list_in[(size_t)b * N + r];
+  }
+  bool amb = false;
+  int pos = 0;
+  if (live) {
+    float best = -INFINITY, second = -INFINITY, third = -INFINITY;
+    int idx = 0, idx2 = 0;
+    const bool top3 = part_idx2 != nullptr;
+    auto insert = [&](float v, int i) {
+      if (v > best) {
+        third = second;
+        second = best;
+        idx2 = idx;
+        best = v;
+        idx = i;
+      } else if (v > second) {
+        third = second;
+        second = v;
+        idx2 = i;
+      } else {
+        third = fmaxf(third, v);
+      }
+    };
+    for (int s = 0; s < psplit; ++s) {                     // splits are in ascending column order
+      const size_t o = ((size_t)s * B + b) * N + r;
+      const float vb = part_best[o], vs = part_second[o];
+      const float vt = top3 ? part_third[o] : -INFINITY;
+      const int ib = part_idx[o], is = top3 ? part_idx2[o] : 0;
+      // insert (vb, ib), (vs, is), vt into the running top three; strict comparisons keep the lowest column on ties
+      // (vt <= vs <= the running second once vs is in, so it only competes for third place)
+      insert(vb, ib);
+      insert(vs, is);
+      third = fmaxf(third, vt);
+    }
+    const size_t bq = (size_t)b * N + q;
+    const float rn = rnorm[bq];
+    float tol;
+    if (list_in) tol = fmaf(tol_rel, rn, tol_abs);
+    else tol = fmaf(2.0f, fmaf(rn, fmaf(1.001f, xerr_max[b], tol_rel), rerr[bq]), tol_abs);
+    const float rs = rscale[bq];
+    const float gap = __fmul_rn(best - second, rs);
+    const bool bad = (nonfinite && nonfinite[b] != 0);
+    ind[bq] = idx;                                         // provisional for untrusted rows
+    // !(gap >= tol) also catches NaN and the all -inf row
+    amb = bad || !(gap >= tol);
+    if (amb && top3 && !bad && (__fmul_rn(best - third, rs) >= tol)) {
+      // exactly two candidates inside the error band: two exact dot products settle the row (ipsr_resolve_rows)
+      amb = false;
+      cand2[bq] = idx2;
+      pair_list[(size_t)b * N + atomicAdd(npair + b, 1)] = q;
+    }
+    if (amb) {
+      pos = atomicAdd(nlist_out + b, 1);
+      list_out[(size_t)b * N + pos] = q;
+    }
+    if (!list_in) packed[bq] = kPackedIdentity;
+  }
+  if (c_tiles == nullptr) return;
+  // compaction (pass 1 only; N % 32 == 0 on the tensor path, so whole warps arrive here)
+  const int lane = threadIdx.x & 31;
+  const int RB = N / kTileRows;
+  unsigned todo = __ballot_sync(0xffffffffu, amb);
+  while (todo) {
+    const int src_lane = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int qs = __shfl_sync(0xffffffffu, q, src_lane);
+    const int ps = __shfl_sync(0xffffffffu, pos, src_lane);
+    const int srb = qs / kTileRows, sr = qs % kTileRows, drb = ps / kTileRows, dr = ps % kTileRows;
+    for (int i = lane; i < KB * 16; i += 32) {             // (kb, part, chunk)
+      const int kb = i >> 4, part = (i >> 3) & 1, chunk = i & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(r_tiles + tile_offset_bytes(b, kb, part, srb, KB, RB) + tile_chunk_offset(sr, chunk));
+      *reinterpret_cast<uint4*>(c_tiles + tile_offset_bytes(b, kb, part, drb, KB, RB) + tile_chunk_offset(dr, chunk)) = v;
     }
   }
-  const float tol = fmaf(tol_rel, rnorm[(size_t)b * N + q], tol_abs);
-  const bool bad = (nonfinite && nonfinite[b] != 0);
-  // !(gap >= tol) also catches NaN and the all -inf row
-  if (!bad && (best - second) >= tol) {
-    ind[(size_t)b * N + q] = idx;
-  } else {
-    ind[(size_t)b * N + q] = idx;                        // overwritten by ipsr_apply_recheck
-    const int pos = atomicAdd(nlist + b, 1);
-    list[(size_t)b * N + pos] = q;
-  }
-  packed[(size_t)b * N + q] = kPackedIdentity;
 }
 
-static int tc_stage_count(int C, bool a_resident, int block_n, size_t* smem_out) {
-  const size_t stage = (a_resident ? 0 : 2 * (size_t)kTileBytes) + 2 * (size_t)(block_n / 128) * kTileBytes;
-  const size_t a_bytes = a_resident ? (size_t)(C / kTileK) * 2 * kTileBytes : 0;
+static int tc_stage_count(size_t a_bytes, size_t stage, size_t* smem_out) {
   const size_t fixed = a_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   const size_t budget = 227 * 1024;
+  if (fixed + 2 * stage > budget) {
+    *smem_out = 0;
+    return 0;
+  }
   int stages = (int)((budget - fixed) / stage);
-  if (stages > 6) stages = 6;
+  if (stages > 8) stages = 8;
   *smem_out = fixed + (size_t)stages * stage;
   return stages;
+}
+
+template <int ROWT, int PASSES, bool A_RES>
+static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
+  constexpr int AH = (PASSES == 3) ? 2 : 1;
+  const size_t a_bytes = A_RES ? (size_t)ROWT * (C / kTileK) * AH * kTileBytes : 0;
+  const size_t stage = (A_RES ? 0 : (size_t)AH * kTileBytes) + (size_t)AH * kTileBytes;
+  size_t smem = 0;
+  prm.stages = tc_stage_count(a_bytes, stage, &smem);
+  IPSR_REQUIRE(prm.stages >= 2, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: C=%d leaves %d pipeline stages", C, prm.stages);
+  cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<ROWT, PASSES, A_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
+  corr_tc_kernel<ROWT, PASSES, A_RES><<<(unsigned)ctas, 64 + 128 * ROWT, smem, st>>>(prm);
+  return check_launch("ipsr_correlate_argmax_tc");
 }
 
 }  // namespace ipsr
@@ -267,9 +393,9 @@ extern "C" int ipsr_tensor_path_supported(int C, int N) {
 }
 
 extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles, int B, int C, int N,
-                                        int col_begin, int col_end, int psplit,
-                                        float* part_best, int32_t* part_idx, float* part_second,
-                                        float* s_dump, void* stream) {
+                                        int col_begin, int col_end, int psplit, int passes, int r_parts,
+                                        const int32_t* row_limit, float* part_best, int32_t* part_idx, float* part_second,
+                                        int32_t* part_idx2, float* part_third, float* s_dump, void* stream) {
   using namespace ipsr;
   IPSR_REQUIRE(r_tiles && x_tiles && part_best && part_idx && part_second, IPSR_ERR_INVALID_ARG,
                "ipsr_correlate_argmax_tc: null pointer");
@@ -278,48 +404,65 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   IPSR_REQUIRE(B > 0 && col_begin >= 0 && col_end <= N && col_begin < col_end && col_begin % 128 == 0 &&
                    col_end % 128 == 0 && psplit >= 1,
                IPSR_ERR_INVALID_ARG, "ipsr_correlate_argmax_tc: bad column range [%d,%d) psplit=%d", col_begin, col_end, psplit);
-  const bool a_res = (C <= 256);
-  const int ncols = col_end - col_begin;
-  // A resident: BLOCK_N = 128 keeps 3+ ring stages next to the 128 KiB row tile; streaming: 256.
-  int block_n = a_res ? 128 : 256;
-  if (ncols % block_n != 0) block_n = 128;
+  IPSR_REQUIRE(passes == 1 || passes == 3, IPSR_ERR_INVALID_ARG, "ipsr_correlate_argmax_tc: passes must be 1 or 3");
+  IPSR_REQUIRE(r_parts == 2 || (r_parts == 1 && passes == 1), IPSR_ERR_INVALID_ARG,
+               "ipsr_correlate_argmax_tc: r_tiles must hold 2 parts (or 1 for a single pass)");
   TcParams prm;
   prm.r_tiles = reinterpret_cast<const uint8_t*>(r_tiles);
   prm.x_tiles = reinterpret_cast<const uint8_t*>(x_tiles);
+  prm.row_limit = row_limit;
+  prm.a_parts = r_parts;
   prm.B = B; prm.KB = C / kTileK; prm.RB = N / kTileRows; prm.N = N;
   prm.col_begin = col_begin;
-  prm.blocks_total = ncols / block_n;
+  prm.blocks_total = (col_end - col_begin) / kBlockN;
   // psplit > blocks_total is allowed: the surplus splits own no column block and report -inf
   prm.psplit = psplit;
+  prm.stages = 0;
   prm.part_best = part_best; prm.part_idx = part_idx; prm.part_second = part_second; prm.s_dump = s_dump;
-  size_t smem = 0;
-  prm.stages = tc_stage_count(C, a_res, block_n, &smem);
-  IPSR_REQUIRE(prm.stages >= 2, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: C=%d leaves %d pipeline stages", C, prm.stages);
-  const long long ctas = (long long)B * prm.RB * psplit;
+  prm.part_idx2 = (passes == 3 && part_third) ? part_idx2 : nullptr;
+  prm.part_third = part_third;
+  cudaStream_t st = as_stream(stream);
+  const int AH = passes == 3 ? 2 : 1;
+  const size_t a_one = (size_t)(C / kTileK) * AH * kTileBytes;           // resident bytes per 128-row tile
+  const bool a_res = a_one + 3 * (size_t)AH * kTileBytes + 2048 <= 227 * 1024;    // resident rows + >= 3 ring stages
+  if (passes == 3) {
+    const long long ctas = (long long)B * prm.RB * psplit;
+    IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
+    return a_res ? launch_tc<1, 3, true>(prm, C, ctas, st) : launch_tc<1, 3, false>(prm, C, ctas, st);
+  }
+  // two row tiles per CTA when the grid still fills the machine and both fit next to >= 4 ring stages
+  const bool two = a_res && (prm.RB % 2 == 0) && (2 * a_one + 4 * (size_t)kTileBytes + 2048 <= 227 * 1024) &&
+                   ((long long)B * (prm.RB / 2) * psplit >= 148) && s_dump == nullptr;
+  const long long ctas = (long long)B * (two ? prm.RB / 2 : prm.RB) * psplit;
   IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
-
-  void (*kern)(const TcParams) = nullptr;
-  if (a_res && block_n == 128) kern = corr_tc_kernel<128, true>;
-  else if (!a_res && block_n == 256) kern = corr_tc_kernel<256, false>;
-  else if (!a_res && block_n == 128) kern = corr_tc_kernel<128, false>;
-  IPSR_REQUIRE(kern != nullptr, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: no kernel variant");
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
-  kern<<<(unsigned)ctas, kTcThreads, smem, as_stream(stream)>>>(prm);
-  return check_launch("ipsr_correlate_argmax_tc");
+  if (two) return launch_tc<2, 1, true>(prm, C, ctas, st);
+  return a_res ? launch_tc<1, 1, true>(prm, C, ctas, st) : launch_tc<1, 1, false>(prm, C, ctas, st);
 }
 
 extern "C" int ipsr_finalize_argmax(const float* part_best, const int32_t* part_idx, const float* part_second,
-                                    int psplit, const float* rnorm, const int32_t* nonfinite,
+                                    int psplit, const float* rnorm, const float* rscale, const float* rerr,
+                                    const float* xerr_max, const int32_t* nonfinite,
+                                    const int32_t* list_in, const int32_t* nlist_in,
                                     int B, int N, float tol_rel, float tol_abs,
-                                    int32_t* ind, int32_t* recheck_list, int32_t* nrecheck, int64_t* packed,
-                                    void* stream) {
+                                    int32_t* ind, int32_t* list_out, int32_t* nlist_out, int64_t* packed,
+                                    const void* r_tiles, void* c_tiles, int C,
+                                    const int32_t* part_idx2, const float* part_third,
+                                    int32_t* cand2, int32_t* pair_list, int32_t* npair, void* stream) {
   using namespace ipsr;
-  IPSR_REQUIRE(part_best && part_idx && part_second && rnorm && ind && recheck_list && nrecheck && packed,
+  IPSR_REQUIRE(part_best && part_idx && part_second && rnorm && rscale && ind && list_out && nlist_out,
                IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: null pointer");
-  IPSR_REQUIRE(B > 0 && N > 0 && psplit >= 1, IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: bad dims");
+  IPSR_REQUIRE(list_in ? (nlist_in != nullptr) : (rerr && xerr_max && packed), IPSR_ERR_INVALID_ARG,
+               "ipsr_finalize_argmax: pass 1 needs rerr / xerr_max / packed, pass 2 needs nlist_in");
+  IPSR_REQUIRE(B > 0 && N > 0 && psplit >= 1 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: bad dims");
+  if (c_tiles)
+    IPSR_REQUIRE(r_tiles && !list_in && ipsr_tensor_path_supported(C, N), IPSR_ERR_INVALID_ARG,
+                 "ipsr_finalize_argmax: compaction needs pass 1, r_tiles and a tensor-path shape");
+  if (part_idx2)
+    IPSR_REQUIRE(part_third && cand2 && pair_list && npair, IPSR_ERR_INVALID_ARG,
+                 "ipsr_finalize_argmax: the pair list needs part_third, cand2, pair_list and npair");
   finalize_kernel<<<dim3((N + 255) / 256, B), 256, 0, as_stream(stream)>>>(
-      part_best, part_idx, part_second, psplit, rnorm, nonfinite, B, N, tol_rel, tol_abs, ind, recheck_list, nrecheck,
-      reinterpret_cast<long long*>(packed));
+      part_best, part_idx, part_second, psplit, rnorm, rscale, rerr, xerr_max, nonfinite, list_in, nlist_in, B, N, tol_rel,
+      tol_abs, ind, list_out, nlist_out, reinterpret_cast<long long*>(packed), reinterpret_cast<const uint8_t*>(r_tiles),
+      reinterpret_cast<uint8_t*>(c_tiles), c_tiles ? C / kTileK : 0, part_idx2, part_third, cand2, pair_list, npair);
   return check_launch("ipsr_finalize_argmax");
 }

@@ -141,6 +141,7 @@ class ShiftSaved:
     exc_total: Optional[torch.Tensor] = None
     exc_cap: int = 0
     nrecheck: Optional[torch.Tensor] = None
+    npass2: Optional[torch.Tensor] = None
 
 
 class _Call:
@@ -173,6 +174,7 @@ class _Call:
                 s.exc_total = torch.empty((B,), dtype=torch.int32, device=dev)
         if diagnostics:
             s.nrecheck = torch.empty((B,), dtype=torch.int32, device=dev)
+            s.npass2 = torch.zeros((B,), dtype=torch.int32, device=dev)
         lib = _lib.load()
         mode_id = _lib.MODES[mode]
         nbytes = lib.ipsr_workspace_bytes(B, Cc, H, W, M, mode_id)
@@ -190,6 +192,7 @@ class _Call:
         a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total = (_ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l),
                                                                _ptr(s.exc_w), _ptr(s.exc_total))
         a.nrecheck_out = _ptr(s.nrecheck)
+        a.npass2_out = _ptr(s.npass2)
         if events is not None:                       # (begin, end) torch.cuda.Event pair, already materialised
             a.ev_corr_begin, a.ev_corr_end = events[0].cuda_event, events[1].cuda_event
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), nbytes
@@ -226,7 +229,7 @@ def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Opti
     mode = mode or config["correlation_mode"]
     tensor = mode == "tensor" or (mode == "auto" and _lib.load().ipsr_tensor_path_supported(C, N) == 1)
     n = 1                                   # extract_normalize
-    n += 2 if tensor else 1                 # correlate_tc + finalize | select_all_rows
+    n += 4 if tensor else 1                 # correlate_tc + finalize (+ compaction), correlate_tc + finalize | select_all_rows
     n += 2                                  # correlate_fp32 + apply_recheck
     if M > 0:
         n += 2                              # blend_stage + blend_scan
@@ -314,7 +317,7 @@ def extract_normalize(x: torch.Tensor):
     xt = torch.empty((B, N, Cc), dtype=torch.float32, device=x.device)
     inv = torch.empty((B, N), dtype=torch.float32, device=x.device)
     _lib.call("ipsr_extract_normalize", x.data_ptr(), x.data_ptr(), B, Cc, N, None, 0, inv.data_ptr(), None,
-              xt.data_ptr(), None, None, None, None, _stream_ptr(x.device))
+              xt.data_ptr(), None, None, None, None, None, None, None, None, _stream_ptr(x.device))
     return xt, inv
 
 

@@ -33,7 +33,7 @@ extern "C" {
 
 /* correlation precision modes (north_star (b)) */
 #define IPSR_MODE_AUTO    0   /* tensor path when the shape allows it, else exact */
-#define IPSR_MODE_TENSOR  1   /* tcgen05 3xBF16 split GEMM + fp32 recheck of ambiguous rows */
+#define IPSR_MODE_TENSOR  1   /* tcgen05 fp16 precision cascade (1 pass, 3-pass split on ambiguous rows) + fp32 recheck */
 #define IPSR_MODE_EXACT   2   /* fp32 FFMA correlation for every row */
 
 const char* ipsr_last_error_string(void);
@@ -64,44 +64,72 @@ int ipsr_build_flags(const uint8_t* feat_u8, int H, int W, int patch, int stride
  *
  * For X = x[b] viewed [N,C]:  inv_norm[b,p] = 1/(||X[p]||_2 + 1e-8);
  *   xt        fp32 [B,N,C]   position-major copy of x (raw patches = decoder weights, NPS:54);
- *   x_tiles   bf16 hi/lo split of Xn = X*inv_norm in the UMMA tile image layout (may be NULL);
+ *   x_tiles   fp16 hi/lo split of Xn * 2^11, Xn = X*inv_norm, in the UMMA tile image layout (may be NULL);
  * For R = ref[b] viewed [N,C]:  rnorm[b,q] = ||R[q]||_2;
  *   r_masked  fp32 [B,M,C]   rows of R at masked positions (rank_i32 from ipsr_build_flags);
- *   r_tiles   bf16 hi/lo split of R, same layout (may be NULL).
+ *   r_tiles   fp16 hi/lo split of R[q] * 2^s_q (max |.| in [2^13, 2^14)), same layout (may be NULL);
+ *   rscale    [B,N]  2^-(s_q + 11): true score = tensor score * rscale[b,q];
+ *   rerr      [B,N]  ||R[q] - hi part||_2 (true units);  xerr [B,N] (may be NULL) the same for Xn[p];
+ *   xerr_max  [B]    max_p xerr[b,p] (must be zero on entry).
+ *   => |single-pass score - exact score| <= rerr[q] + ||R~[q]|| * xerr_max[b] (+ fp32 accumulation).
  * nonfinite [B] (may be NULL): set to 1 when x[b] or ref[b] holds a NaN/inf (the tensor path
  * then defers every row of that image to the exact path).  Must be zero on entry.
- * Tile image layout: [B][C/64][2 (hi,lo)][N/128][128 rows x 64 bf16, 128B-swizzled K-major].
+ * Tile image layout: [B][C/64][2 (hi, lo)][N/128][128 rows x 64 fp16, 128B-swizzled K-major].
  * ------------------------------------------------------------------------------------------- */
 int ipsr_extract_normalize(const float* x, const float* ref, int B, int C, int N,
                            const int32_t* rank_i32, int M,
                            float* inv_norm, float* rnorm, float* xt, float* r_masked,
-                           void* x_tiles, void* r_tiles, int32_t* nonfinite, void* stream);
+                           void* x_tiles, void* r_tiles, int32_t* nonfinite,
+                           float* rscale, float* rerr, float* xerr, float* xerr_max, void* stream);
+
+/* Rows list[b][0 .. nlist[b]) of ref[b] -> compact fp16 hi AND lo tile images (2 parts) for the three-pass
+ * correlation of the ambiguous rows: compact row r = position list[b][r], scaled by the same 2^s_q
+ * (rscale from ipsr_extract_normalize); rows up to the next multiple of 128 are zero-filled. */
+int ipsr_compact_rows(const float* ref, int B, int C, int N, const int32_t* list, const int32_t* nlist,
+                      const float* rscale, void* c_tiles, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (b)+(c) correlation + fused row arg-max   (models/IPSRFunction.py:59, util/MaxCoord.py:22)
  *
- * S[q,p] = <R[q], Xn[p]> is never written to memory.
+ * S[q,p] = <R[q], Xn[p]> is never written to memory.  Precision cascade: one tcgen05 pass (hi*hi, fp16)
+ * over every row; rows whose top-2 gap is inside twice its rigorous error bound are compacted and redone
+ * with the three-pass split (hi*lo + lo*hi + hi*hi, ~fp32 accurate); rows still ambiguous after that are
+ * recomputed in exact fp32.
  * ------------------------------------------------------------------------------------------- */
 
-/* tcgen05/TMEM GEMM (3 x BF16 split) over bank columns [col_begin, col_end) (multiples of 128),
- * split into `psplit` column ranges per 128-row tile.  Writes per row and per split the best
- * score, its (global) column index and the runner-up score: part_* are [psplit][B][N].
- * s_dump (optional, tests only): fp32 [B][N][N] receives the full score matrix. */
+/* tcgen05/TMEM GEMM over bank columns [col_begin, col_end) (multiples of 128), split into `psplit` column
+ * ranges per row tile.  passes = 1: hi * hi only; passes = 3: hi*lo + lo*hi + hi*hi.  r_parts: parts per
+ * 64-channel block in the r_tiles image (2; 1 is accepted for a hi-only image with passes = 1).
+ * row_limit (optional, [B]): only the first row_limit[b] rows of r_tiles are populated (compacted operand).
+ * Writes per row and per split the best SCALED score, its (global) column index and the runner-up score:
+ * part_* are [psplit][B][N].  part_idx2 / part_third (optional, passes = 3 only): column of the runner-up and the
+ * third-best score.  s_dump (optional, tests only): fp32 [B][N][N] receives the full scaled score
+ * matrix. */
 int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles, int B, int C, int N,
-                             int col_begin, int col_end, int psplit,
-                             float* part_best, int32_t* part_idx, float* part_second,
-                             float* s_dump, void* stream);
+                             int col_begin, int col_end, int psplit, int passes, int r_parts,
+                             const int32_t* row_limit, float* part_best, int32_t* part_idx, float* part_second,
+                             int32_t* part_idx2, float* part_third, float* s_dump, void* stream);
 
 /* Merge the `psplit` partial (best, idx, second) triples per row, then decide per row:
- *   gap = best - second >= tol_rel * rnorm[b,q] + tol_abs  -> ind[b,q] = idx (trusted);
- *   otherwise (or when nonfinite[b] != 0) the row is appended to recheck_list[b] and
- *   packed[b,q] is reset, so that ipsr_correlate_argmax_fp32 recomputes it exactly.
- * nrecheck[b] must be zero on entry. */
+ *   gap = (best - second) * rscale[b,q] >= tol[q]  -> ind[b,q] = idx (trusted);
+ *   otherwise (or when nonfinite[b] != 0) the row is appended to list_out[b] (ind[b,q] = idx provisionally).
+ * Pass 1 (list_in == NULL): rows are positions; tol[q] = 2 (rerr[q] + rnorm[q] (1.001 xerr_max[b] + tol_rel)) + tol_abs;
+ *   packed[b,q] is reset for every row.  With c_tiles != NULL it also COMPACTS: the hi and lo tile rows of every
+ *   appended position are copied from r_tiles to row `pos` of the compact image c_tiles (same layout) that the
+ *   three-pass split then reads with row_limit = nlist_out.
+ * Pass 2 (list_in != NULL): row r < nlist_in[b] is position list_in[b][r]; tol[q] = tol_rel rnorm[q] + tol_abs.
+ *   With part_idx2 / part_third: an untrusted row whose THIRD-best score is outside the band has exactly two
+ *   candidates; it goes to pair_list[b] (cand2[b,q] = the runner-up's column) instead of list_out[b].
+ * nlist_out[b] (and npair[b]) must be zero on entry. */
 int ipsr_finalize_argmax(const float* part_best, const int32_t* part_idx, const float* part_second,
-                         int psplit, const float* rnorm, const int32_t* nonfinite,
+                         int psplit, const float* rnorm, const float* rscale, const float* rerr,
+                         const float* xerr_max, const int32_t* nonfinite,
+                         const int32_t* list_in, const int32_t* nlist_in,
                          int B, int N, float tol_rel, float tol_abs,
-                         int32_t* ind, int32_t* recheck_list, int32_t* nrecheck, int64_t* packed,
-                         void* stream);
+                         int32_t* ind, int32_t* list_out, int32_t* nlist_out, int64_t* packed,
+                         const void* r_tiles, void* c_tiles, int C,
+                         const int32_t* part_idx2, const float* part_third,
+                         int32_t* cand2, int32_t* pair_list, int32_t* npair, void* stream);
 
 /* Select every row for the exact path (IPSR_MODE_EXACT): recheck_list[b] = 0..N-1,
  * nrecheck[b] = N, packed = identity. */
@@ -119,6 +147,14 @@ int ipsr_correlate_argmax_fp32(const float* x, const float* ref, const float* in
                                const int32_t* recheck_list, const int32_t* nrecheck, int row_ctas,
                                int64_t* packed, void* stream);
 
+/* Settle what the tensor passes left open, in one launch: (1) packed[b,q] -> ind[b,q] (and optionally vmax[b,q])
+ * for the rows in recheck_list; (2) for the rows in pair_list (may be NULL) -- exactly two candidates, ind[b,q]
+ * and cand2[b,q], inside the error band of the three-pass split -- one warp computes both exact fp32 scores
+ * and keeps the larger (the lower column on a tie). */
+int ipsr_resolve_rows(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck,
+                      const int32_t* pair_list, const int32_t* npair, const int32_t* cand2,
+                      const float* xt, const float* ref, const float* inv_norm,
+                      int B, int C, int N, int32_t* ind, float* vmax, void* stream);
 /* packed[b,q] -> ind[b,q] (and optionally vmax[b,q]) for the rows in recheck_list. */
 int ipsr_apply_recheck(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck,
                        int B, int N, int32_t* ind, float* vmax, void* stream);
@@ -253,7 +289,7 @@ typedef struct ipsr_fwd_args {
   int32_t stop_after_corr; /* bank-sharded mode: stop after (b,c) with packed keys ready */
   int32_t psplit;          /* column splits per row tile on the tensor path (<=0: auto)  */
   int32_t exc_cap;
-  float tol_rel, tol_abs;  /* recheck threshold (<0: library default)                    */
+  float tol_rel, tol_abs;  /* recheck threshold after the three-pass split (<0: default) */
   float* out;              /* [B,C,H,W]                                                  */
   /* saved for backward (caller-owned) */
   int32_t* ind;            /* [B,N]                                                      */
@@ -264,6 +300,7 @@ typedef struct ipsr_fwd_args {
   int32_t* exc_l; float* exc_w;           /* [B,exc_cap]                                 */
   int32_t* exc_total;      /* [B]                                                        */
   int32_t* nrecheck_out;   /* [B] optional: rows that took the exact path (diagnostics)  */
+  int32_t* npass2_out;     /* [B] optional: rows redone by the three-pass split          */
   void* ev_corr_begin;     /* optional cudaEvent_t pair recorded on `stream` around the      */
   void* ev_corr_end;       /*   correlation kernel ((b,c)), for live roofline measurement    */
   void* workspace; size_t workspace_bytes;

@@ -71,7 +71,7 @@ def test_argument_validation_without_gpu():
     assert "null" in _lib.last_error()
     args = _lib.FwdArgs()
     assert lib.ipsr_shift_forward(ctypes.byref(args), None) == -1
-    assert lib.ipsr_correlate_argmax_tc(1, 1, 1, 48, 100, 0, 100, 1, 1, 1, 1, None, None) == -2
+    assert lib.ipsr_correlate_argmax_tc(1, 1, 1, 48, 100, 0, 100, 1, 1, 2, None, 1, 1, 1, None, None, None, None) == -2
     with pytest.raises(_lib.IpsrError):
         _lib.call("ipsr_maxcoord", None, 0, 0, None, None, None)
 
