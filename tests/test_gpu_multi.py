@@ -1,0 +1,71 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box, skipped otherwise): one process per GPU, NCCL.
+
+* batch sharding: every rank runs the layer on its slice of the batch, no collective in the data path;
+  the concatenation equals the single-GPU result bit for bit;
+* bank sharding: every rank correlates against its slice of the bank columns, ONE all-reduce MAX of the packed
+  int64 (score, ~index) keys over NCCL, then the blend / paste run replicated; equals the unsharded result.
+"""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port):
+    import torch.distributed as dist
+    from deepinpainting_b200 import shift_ops
+    from deepinpainting_b200.sharding import allreduce_max_keys, shard_bank, shard_batch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        gen = torch.Generator().manual_seed(11)                    # same data on every rank
+        B, C, H = 4, 256, 32
+        N = H * H
+        x = torch.randn(B, C, H, H, generator=gen).to(dev)
+        ref = (torch.relu(torch.randn(B, C, H, H, generator=gen)) * 3).to(dev)
+        g = torch.randn(B, C, H, H, generator=gen).to(dev)
+        flag = torch.zeros(H, H, dtype=torch.int64)
+        flag[8:24, 6:20] = 1
+        mi = shift_ops.mask_index_from_flag(flag.view(-1), dev)
+        for mode in ("tensor", "exact"):
+            full_out, full_saved = shift_ops.shift_forward(x, ref, mi, need_grad=True, mode=mode)
+            full_gin = shift_ops.shift_backward(g, full_saved, 1.0)
+            # ---- batch sharding: no collective; gather only to compare ----
+            b0, b1 = shard_batch(B, world, rank)
+            out_s, saved_s = shift_ops.shift_forward(x[b0:b1].contiguous(), ref[b0:b1].contiguous(), mi, need_grad=True, mode=mode)
+            gin_s = shift_ops.shift_backward(g[b0:b1].contiguous(), saved_s, 1.0)
+            assert torch.equal(out_s, full_out[b0:b1]) and torch.equal(gin_s, full_gin[b0:b1])
+            assert torch.equal(saved_s.ind, full_saved.ind[b0:b1])
+            # ---- bank sharding: one NCCL all-reduce MAX of int64 keys ----
+            cb, ce = shard_bank(N, world, rank)
+            out_k, saved_k = shift_ops.shift_forward_sharded(x, ref, mi, cb, ce, allreduce_max_keys, need_grad=True, mode=mode)
+            gin_k = shift_ops.shift_backward(g, saved_k, 1.0)
+            torch.cuda.synchronize()
+            assert torch.equal(saved_k.ind, full_saved.ind), mode
+            assert torch.equal(out_k, full_out) and torch.equal(gin_k, full_gin), mode
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_batch_and_bank_sharding_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)
