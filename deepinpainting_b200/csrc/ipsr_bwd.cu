@@ -30,164 +30,182 @@ build_exceptions_kernel(const int* __restrict__ ind, const int* __restrict__ mas
 // ---------------------------------------------------------------------------------------------
 // backward proper
 // ---------------------------------------------------------------------------------------------
-// grid = (C / CT, B): the CTA stages CT rows of g[b] (C % CT == 0) in shared memory with ONE bulk async copy
-// (the rows are contiguous in NCHW) while its threads already fetch the CSR entries of their columns.
-// Shared memory holds nothing but the rows (+ a small queue), so several CTAs are resident per SM and the
-// copy of one overlaps the gather of another.  Light bank columns (few routes / exceptions) are summed
-// by their own thread in a loop of exactly their entry count; heavy ones -- a non-negative reference makes
-// a few "hub" patches the best match of hundreds of positions -- are queued and summed by whole warps
-// (lane-strided partial sums in ascending q, then a fixed xor tree: deterministic).  If the exception lists
-// overflowed (exc_total > exc_cap, chaotic inputs only) the column replays the recurrence.
-constexpr int kBwdLight = 12;
-constexpr int kBwdQueue = 1024;
-constexpr int kBwdPre = 4;               // columns per thread whose CSR entries are fetched ahead
+// grid = (parts, B): a CTA owns a contiguous range of channel tiles (CT rows each, C % CT == 0) of ONE image and
+// streams them through a two-stage ring of bulk async copies (the CT rows of a tile are contiguous in NCHW), so
+// the copy of tile t+1 overlaps the work on tile t.  Most bank columns receive nothing (a non-negative reference
+// concentrates the matches on a few hundred patches), hence per tile:
+//   (1) copy-out   gin tile = g tile, 16-byte vector stores straight from shared memory;
+//   (2) correct    the columns that do receive something -- a compact list built ONCE per CTA from the CSR and
+//                  the exception directory, so every lane has work -- are recomputed as
+//                  g[:,p] + triple_w (sum of routed rows + weighted exception rows) by one thread each, hub
+//                  columns (hundreds of routes) by whole warps (lane-strided partial sums in ascending q, then a
+//                  fixed xor tree): deterministic.
+// If the exception lists overflowed (exc_total > exc_cap, chaotic inputs only) every column replays the recurrence.
+constexpr int kBwdLight = 24;            // entries a single thread sums; heavier columns go to a warp
+constexpr int kBwdQueue = 512;
 
 template <int CT>
-__global__ void __launch_bounds__(256)
-shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, const int* __restrict__ route_ptr,
+__global__ void __launch_bounds__(1024)
+shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per_cta, const int* __restrict__ route_ptr,
                  const int* __restrict__ route_q, const int* __restrict__ exc_start, const int* __restrict__ exc_cnt,
                  const int* __restrict__ exc_l, const float* __restrict__ exc_w, const int* __restrict__ exc_total,
                  int exc_cap, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                  const float* __restrict__ wn, const float* __restrict__ wo, float triple_w, float* __restrict__ gin) {
-  extern __shared__ __align__(128) float grow[];          // [CT][N]
+  extern __shared__ __align__(128) float bwd_smem[];      // rows[2][CT*N] | spec[N]
   __shared__ int heavy[kBwdQueue];
-  __shared__ int nheavy;
-  __shared__ __align__(8) unsigned long long bar;
+  __shared__ int nheavy, nspec_s;
+  __shared__ __align__(8) unsigned long long bars[2];
   const int b = blockIdx.y;
-  const int c0 = blockIdx.x * CT;
-  const float* gb = g + ((size_t)b * C + c0) * N;
-  float* ob = gin + ((size_t)b * C + c0) * N;
-  const int total = CT * N;
-  const bool bulk = ((total & 3) == 0) && ((reinterpret_cast<uintptr_t>(gb) & 15) == 0);
+  const int ntiles = C / CT;
+  const int t0 = blockIdx.x * tiles_per_cta;
+  const int t1 = min(ntiles, t0 + tiles_per_cta);
+  if (t0 >= t1) return;
+  const int tile_elems = CT * N;
+  const uint32_t tile_bytes = (uint32_t)tile_elems * 4u;
+  float* rows0 = bwd_smem;
+  int* spec = reinterpret_cast<int*>(bwd_smem + 2 * (size_t)tile_elems);
+  const int nthreads = blockDim.x;
+  const float* gimg = g + (size_t)b * C * N;
+  float* oimg = gin + (size_t)b * C * N;
+  const bool vec = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(gimg) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(oimg) & 15) == 0);
+
+  auto load_tile = [&](int t, int buf) {                  // executed by thread 0 (bulk) or by everybody (fallback)
+    const float* src = gimg + (size_t)t * tile_elems;
+    float* dst = rows0 + (size_t)buf * tile_elems;
+    if (vec) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(smem_u32(&bars[buf]), tile_bytes);
+        bulk_g2s(smem_u32(dst), src, tile_bytes, smem_u32(&bars[buf]));
+      }
+    } else {
+      for (int i = threadIdx.x; i < tile_elems; i += nthreads) dst[i] = __ldg(src + i);
+    }
+  };
+
   if (threadIdx.x == 0) {
     nheavy = 0;
-    if (bulk) {
-      mbar_init(smem_u32(&bar), 1);
-      mbar_fence_init();
-      mbar_expect_tx(smem_u32(&bar), (uint32_t)total * 4u);
-      bulk_g2s(smem_u32(grow), gb, (uint32_t)total * 4u, smem_u32(&bar));
-    }
+    nspec_s = 0;
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_fence_init();
   }
-  if (!bulk)
-    for (int i = threadIdx.x; i < total; i += 256) grow[i] = __ldg(gb + i);
-  const int* gptr = route_ptr + (size_t)b * (N + 1);
-  const int* grq = route_q + (size_t)b * N;
+  __syncthreads();
+  load_tile(t0, 0);
+  if (t0 + 1 < t1) load_tile(t0 + 1, 1);
+
   const bool has_exc = (M > 1) && exc_cnt && exc_total && (exc_total[b] != 0);
   const bool overflow = has_exc && (exc_total[b] > exc_cap);
   const bool lists = has_exc && !overflow;
+  const int* gptr = route_ptr + (size_t)b * (N + 1);
+  const int* grq = route_q + (size_t)b * N;
   const int* ecnt = exc_cnt + (size_t)b * N;
   const int* estart = exc_start + (size_t)b * N;
   const int* el = exc_l + (size_t)b * exc_cap;
   const float* ew = exc_w + (size_t)b * exc_cap;
-  __syncthreads();                                        // barrier initialised / plain copy complete
-  bool landed = !bulk;
-
-  auto replay = [&](int p, float (&acc)[CT]) {            // exception lists overflowed: rare, slow, bit-faithful
-    float e = (ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
-    for (int l = 1; l < M; ++l) {
-      const int ql = mask_idx[l];
-      e = __fmul_rn(e, wn[(size_t)b * M + l]);
-      if (ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, wo[(size_t)b * M + l]);
-      if (!(fabsf(e) < 1.0f)) {
-        const float w = trunc_as_reference(e);
-#pragma unroll
-        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
-      }
-    }
-  };
-
-  for (int base = 0; base < N; base += 256 * kBwdPre) {
-    int r0[kBwdPre], r1[kBwdPre], ne[kBwdPre], es[kBwdPre], q0[kBwdPre];
-#pragma unroll
-    for (int i = 0; i < kBwdPre; ++i) {
-      const int p = base + i * 256 + threadIdx.x;
-      r0[i] = r1[i] = ne[i] = es[i] = 0;
-      if (p < N) {
-        r0[i] = __ldg(gptr + p);
-        r1[i] = __ldg(gptr + p + 1);
-        if (lists) {
-          ne[i] = __ldg(ecnt + p);
-          es[i] = __ldg(estart + p);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kBwdPre; ++i) q0[i] = (r1[i] > r0[i]) ? __ldg(grq + r0[i]) : 0;
-    if (!landed) {
-      mbar_wait(smem_u32(&bar), 0);
-      landed = true;
-    }
-#pragma unroll
-    for (int i = 0; i < kBwdPre; ++i) {
-      const int p = base + i * 256 + threadIdx.x;
-      if (p >= N) continue;
-      const int n = r1[i] - r0[i];
-      if (n + ne[i] > kBwdLight) {
-        const int slot = atomicAdd(&nheavy, 1);            // queue order does not affect any sum
+  // the columns that receive something, once per CTA (list order does not affect any sum)
+  for (int p = threadIdx.x; p < N; p += nthreads) {
+    const int work = __ldg(gptr + p + 1) - __ldg(gptr + p) + (lists ? __ldg(ecnt + p) : 0);
+    if (overflow || work > 0) {
+      bool queued = false;
+      if (work > kBwdLight && !overflow) {
+        const int slot = atomicAdd(&nheavy, 1);
         if (slot < kBwdQueue) {
           heavy[slot] = p;
-          continue;
+          queued = true;
         }
       }
+      if (!queued) spec[atomicAdd(&nspec_s, 1)] = p;
+    }
+  }
+  __syncthreads();
+  const int nspec = nspec_s;
+  const int nh = min(nheavy, kBwdQueue);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+
+  for (int t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    const float* grow = rows0 + (size_t)buf * tile_elems;
+    float* ob = oimg + (size_t)t * tile_elems;
+    if (vec) mbar_wait(smem_u32(&bars[buf]), (uint32_t)((t - t0) >> 1) & 1u);
+    else __syncthreads();
+
+    // (1) copy-out: g + triple_w * 0
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(grow);
+      float4* d4 = reinterpret_cast<float4*>(ob);
+      for (int i = threadIdx.x; i < tile_elems / 4; i += nthreads) d4[i] = s4[i];
+    } else {
+      for (int i = threadIdx.x; i < tile_elems; i += nthreads) ob[i] = grow[i];
+    }
+    __syncthreads();                                         // the corrections below overwrite some of these stores
+
+    // (2) corrections
+    for (int k = threadIdx.x; k < nspec; k += nthreads) {
+      const int p = spec[k];
+      const int r0 = __ldg(gptr + p), r1 = __ldg(gptr + p + 1);
+      const int ne = lists ? __ldg(ecnt + p) : 0;
+      const int es = lists ? __ldg(estart + p) : 0;
       float acc[CT];
 #pragma unroll
       for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
-      if (n > 0) {
+      for (int r = r0; r < r1; ++r) {
+        const int q = __ldg(grq + r);
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q0[i]];
-        for (int r = r0[i] + 1; r < r1[i]; ++r) {
-          const int q = __ldg(grq + r);
+        for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
+      }
+      for (int e = 0; e < ne; ++e) {
+        const int q = __ldg(el + es + e);
+        const float w = __ldg(ew + es + e);
 #pragma unroll
-          for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
+        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+      }
+      if (overflow) {                                        // rare, slow, bit-faithful replay of the recurrence
+        float e = (ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
+        for (int l = 1; l < M; ++l) {
+          const int ql = mask_idx[l];
+          e = __fmul_rn(e, wn[(size_t)b * M + l]);
+          if (ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, wo[(size_t)b * M + l]);
+          if (!(fabsf(e) < 1.0f)) {
+            const float w = trunc_as_reference(e);
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
+          }
         }
       }
-      if (ne[i] > 0) {
-        const int s = es[i];
-        for (int e = 0; e < ne[i]; ++e) {
-          const int q = __ldg(el + s + e);
-          const float w = __ldg(ew + s + e);
-#pragma unroll
-          for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
-        }
-      }
-      if (overflow) replay(p, acc);
 #pragma unroll
       for (int ch = 0; ch < CT; ++ch)                        // g + weighted * triple_w           :173
         ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
     }
-  }
-  __syncthreads();
-
-  // heavy columns: one warp each
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nh = min(nheavy, kBwdQueue);
-  for (int h = warp; h < nh; h += 8) {
-    const int p = heavy[h];
-    const int r0 = __ldg(gptr + p), r1 = __ldg(gptr + p + 1);
-    float acc[CT];
+    for (int h = warp; h < nh; h += nwarps) {                // hub columns: one warp each
+      const int p = heavy[h];
+      const int r0 = __ldg(gptr + p), r1 = __ldg(gptr + p + 1);
+      float acc[CT];
 #pragma unroll
-    for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
-    for (int r = r0 + lane; r < r1; r += 32) {
-      const int q = __ldg(grq + r);
+      for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
+      for (int r = r0 + lane; r < r1; r += 32) {
+        const int q = __ldg(grq + r);
 #pragma unroll
-      for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
-    }
-    if (lists) {
-      const int ne = ecnt[p], s = estart[p];
-      for (int e = lane; e < ne; e += 32) {
-        const int q = __ldg(el + s + e);
-        const float w = __ldg(ew + s + e);
+        for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
+      }
+      if (lists) {
+        const int ne = __ldg(ecnt + p), es = __ldg(estart + p);
+        for (int e = lane; e < ne; e += 32) {
+          const int q = __ldg(el + es + e);
+          const float w = __ldg(ew + es + e);
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+          for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) acc[ch] = warp_sum(acc[ch]);
+      if (lane == 0) {
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
       }
     }
-    if (overflow && lane == 0) replay(p, acc);             // lane 0 replays (rare path)
-#pragma unroll
-    for (int ch = 0; ch < CT; ++ch) acc[ch] = warp_sum(acc[ch]);
-    if (lane == 0) {
-#pragma unroll
-      for (int ch = 0; ch < CT; ++ch) ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
-    }
+    __syncthreads();                                         // everybody is done reading this buffer
+    if (t + 2 < t1) load_tile(t + 2, buf);
   }
 }
 
@@ -242,13 +260,35 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   if (M > 1)
     IPSR_REQUIRE(exc_start && exc_cnt && exc_l && exc_w && exc_total && ind && mask_idx && wn && wo, IPSR_ERR_INVALID_ARG,
                  "ipsr_shift_bwd: exception lists / replay operands missing");
-  // channel rows per CTA: the largest of 8, 4, 2, 1 that divides C and keeps the rows within 64 KiB of shared memory
-  // (>= 3 CTAs resident per SM: one CTA's bulk copy overlaps the gathers of the others)
+  // channel rows per tile: the largest of 8, 4, 2, 1 that divides C and keeps a tile within 32 KiB (N > 2048: 64 KiB)
   int CT = 8;
-  while (CT > 1 && (C % CT != 0 || (size_t)CT * N * sizeof(float) > 64 * 1024)) CT >>= 1;
-  const size_t smem = (size_t)CT * N * sizeof(float);
-  IPSR_REQUIRE(smem <= 200 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
-  void (*kern)(const float*, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
+  const size_t tile_cap = (N <= 2048 ? 32 : 64) * 1024;
+  while (CT > 1 && (C % CT != 0 || (size_t)CT * N * sizeof(float) > tile_cap)) CT >>= 1;
+  const size_t smem = 2 * (size_t)CT * N * sizeof(float) + (size_t)N * sizeof(int);
+  IPSR_REQUIRE(smem <= 227 * 1024 - 4 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
+  const int threads = N > 2048 ? 1024 : 512;
+  // split every image's tiles over `parts` CTAs so that the grid fills whole waves of resident CTAs
+  const int ntiles = C / CT;
+  int resident = (int)((227 * 1024) / (smem + 4 * 1024));
+  if (resident < 1) resident = 1;
+  if (resident > 2048 / threads) resident = 2048 / threads;
+  const int slots = 148 * resident;
+  int parts = 1;
+  double best_cost = 1e300;
+  for (int pcand = 1; pcand <= ntiles; ++pcand) {
+    const int tpc = (ntiles + pcand - 1) / pcand;
+    const int np = (ntiles + tpc - 1) / tpc;
+    const long long ctas = (long long)B * np;
+    const long long waves = (ctas + slots - 1) / slots;
+    // time ~ waves * (tiles per CTA + the fixed cost of building the column list, about one tile)
+    const double cost = (double)waves * (tpc + 1.0);
+    if (cost < best_cost * 0.9999) {
+      best_cost = cost;
+      parts = np;
+    }
+  }
+  const int tiles_per_cta = (ntiles + parts - 1) / parts;
+  void (*kern)(const float*, int, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
                const int*, int, const int*, const int*, const float*, const float*, float, float*) = nullptr;
   switch (CT) {
     case 8: kern = shift_bwd_kernel<8>; break;
@@ -260,8 +300,8 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "shift_bwd smem attribute: %s", cudaGetErrorString(e));
   }
-  kern<<<dim3(C / CT, B), 256, smem, as_stream(stream)>>>(g, C, N, M, route_ptr, route_q, exc_start, exc_cnt,
-                                                         exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn,
-                                                         wo, triple_w, gin);
+  kern<<<dim3(parts, B), threads, smem, as_stream(stream)>>>(g, C, N, M, tiles_per_cta, route_ptr, route_q, exc_start, exc_cnt,
+                                                            exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn, wo, triple_w,
+                                                            gin);
   return check_launch("ipsr_shift_bwd");
 }
