@@ -7,6 +7,8 @@
 // allocation, so the whole layer is CUDA-graph capturable.
 #include <stdarg.h>
 
+#include <mutex>
+
 #include "ipsr_common.cuh"
 
 namespace ipsr {
@@ -93,6 +95,31 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
   return w;
 }
 
+// A side stream per device for the latency-bound bookkeeping of the backward (exception lists): it forks from
+// the caller's stream after the scan, runs next to the bandwidth-bound paste and joins before the forward
+// returns -- legal under CUDA-graph stream capture (the fork / join events pull the side stream into the capture).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+  static SideStream table[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& s = table[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      s.stream = nullptr;
+      return nullptr;
+    }
+  }
+  return &s;
+}
+
 template <typename T>
 static T* at(const ipsr_fwd_args* a, size_t off) {
   return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(a->workspace) + off);
@@ -139,10 +166,25 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
                                             a->mask_idx, a->flag, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask),
                                             grad ? a->route_ptr : nullptr, grad ? a->route_q : nullptr, stream));
   if (M > 0) IPSR_FORWARD(ipsr_blend_scan(at<float>(a, w.staged), B, C, M, at<float>(a, w.y), a->wn, a->wo, stream));
-  if (grad && M > 1)
+  if (grad && M > 1) {
+    // the exception lists depend on wn / wo only: build them on the side stream while the paste streams x -> out
+    SideStream* ss = side_stream();
+    cudaStream_t st = as_stream(stream);
+    if (ss && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
+      int rc = ipsr_build_exceptions(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l, a->exc_w,
+                                     a->exc_total, a->exc_cap, ss->stream);
+      const int rc2 = ipsr_paste(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream);
+      // always join, even after an error, so that a capture in progress is not left forked
+      const bool joined = cudaEventRecord(ss->join, ss->stream) == cudaSuccess && cudaStreamWaitEvent(st, ss->join, 0) == cudaSuccess;
+      if (rc == IPSR_OK) rc = rc2;
+      IPSR_REQUIRE(joined, IPSR_ERR_CUDA, "ipsr_shift_forward: side stream join failed");
+      return rc;
+    }
+    (void)cudaGetLastError();
     return ipsr_paste_with_bookkeeping(a->x, at<float>(a, w.y), a->ind, a->rank, a->flag, a->mask_idx, a->wn, a->wo, B, C,
                                        N, M, a->out, nullptr, nullptr, a->exc_start, a->exc_cnt, a->exc_l,
                                        a->exc_w, a->exc_total, a->exc_cap, stream);
+  }
   return ipsr_paste(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream);
 }
 

@@ -202,11 +202,13 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
   const uint32_t blk_bytes = (uint32_t)blk_floats * sizeof(float);
   const uint32_t stage_bytes = (blk_bytes + 127u) & ~127u;
   float* ysm = reinterpret_cast<float*>(scan_smem + 2 * (size_t)stage_bytes);     // [C] y at the end of the previous block
+  float* ytile = ysm + C;                                                        // [T][C+1] the block's y rows, transposed on the way out
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblocks = (M + T - 1) / T;
   const float* src = staged + (size_t)b * nblocks * blk_floats;
-  float* yb = y + (size_t)b * padded_steps(M) * C;
+  const int Mp = padded_steps(M);
+  float* yb = y + (size_t)b * C * Mp;                    // [C][Mp]: channel-major, so that the paste reads rows
   float* wnb = wn_out + (size_t)b * M;
   float* wob = wo_out + (size_t)b * M;
 
@@ -230,6 +232,17 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
   float yreg[kScanMaxCpt];
 #pragma unroll
   for (int m = 0; m < kScanMaxCpt; ++m) yreg[m] = 0.f;
+
+  // y[c][l0 .. l0+nvalid) of block kb from ytile: one warp per channel row, lanes along the steps (coalesced
+  // segments).  Runs OFF the critical path: warps 1.. store block k-1 while warp 0 walks the scalar steps of block k.
+  auto store_ytile = [&](int kb, int w0, int nw) {
+    const int lb = kb * T;
+    const int nv = min(T, M - lb);
+    if (lane < nv) {
+#pragma unroll 4
+      for (int c = warp - w0; c < C; c += nw) yb[(size_t)c * Mp + lb + lane] = ytile[lane * (C + 1) + c];
+    }
+  };
 
   for (int k = 0; k < nblocks; ++k) {
     const int s = k & 1;
@@ -285,6 +298,8 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
           wob[l0 + lane] = my_wo;
         }
       }
+    } else if (k > 0) {
+      store_ytile(k - 1, 1, kScanThreads / 32 - 1);
     }
     __syncthreads();
 
@@ -295,90 +310,123 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
       const int c = tid + m * kScanThreads;
       if (c < C) {
         float yy = yreg[m];
-        float* yrow = yb + (size_t)l0 * C + c;
 #pragma unroll 8
         for (int j = 0; j < nvalid; ++j) {
           yy = __fadd_rn(__fmul_rn(wn_s[j], yy), __fmul_rn(wo_s[j], K[(size_t)j * C + c]));     // :122
-          yrow[(size_t)j * C] = yy;
+          ytile[j * (C + 1) + c] = yy;
         }
         yreg[m] = yy;
         ysm[c] = yy;
       }
     }
-    __syncthreads();                                       // ysm complete; stage s no longer read
+    __syncthreads();                                       // ysm / ytile complete; stage s no longer read
     if (tid == 0 && k + 2 < nblocks) issue(k + 2);
   }
+  store_ytile(nblocks - 1, 0, kScanThreads / 32);          // the last block: every warp helps
 }
 
 // ---------------------------------------------------------------------------------------------
 // paste
 // ---------------------------------------------------------------------------------------------
-// A CTA stages CT channel rows of x[b] (N floats each, contiguous in NCHW) in shared memory with one bulk
-// async copy -- its threads fetch rank / ind of their positions meanwhile -- and writes the CT output rows:
-// coalesced reads, coalesced writes, gather inside the SM.
-constexpr int kPastePre = 4;
-
+// A CTA owns a contiguous range of channel tiles (CT rows each) of ONE image.  It stages rank[] and ind[b][]
+// in shared memory once, then streams the tiles of x[b] (CT * N contiguous floats in NCHW) through a two-stage
+// ring of bulk async copies: the copy of tile t+1 overlaps the gather of tile t, every index lookup is a
+// shared-memory access, reads and writes of HBM are coalesced and the gather happens inside the SM.
 __device__ __forceinline__ void
-paste_cta(int cx, int b, float* rows, const float* __restrict__ x, const float* __restrict__ y,
+paste_cta(int part, int b, int tiles_per_cta, float* psm, const float* __restrict__ x, const float* __restrict__ y,
           const int* __restrict__ ind, const int* __restrict__ rank, int C, int N, int M, int CT,
           float* __restrict__ out) {
-  __shared__ __align__(8) unsigned long long paste_bar;
-  const int c0 = cx * CT;
-  const int ct = min(CT, C - c0);
-  const float* xb = x + ((size_t)b * C + c0) * N;
-  float* ob = out + ((size_t)b * C + c0) * N;
-  const int total = ct * N;
-  const bool bulk = ((total & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0);
-  if (bulk) {
-    if (threadIdx.x == 0) {
-      mbar_init(smem_u32(&paste_bar), 1);
-      mbar_fence_init();
-      mbar_expect_tx(smem_u32(&paste_bar), (uint32_t)total * 4u);
-      bulk_g2s(smem_u32(rows), xb, (uint32_t)total * 4u, smem_u32(&paste_bar));
+  __shared__ __align__(8) unsigned long long paste_bars[2];
+  const int ntiles = (C + CT - 1) / CT;
+  const int t0 = part * tiles_per_cta;
+  const int t1 = min(ntiles, t0 + tiles_per_cta);
+  if (t0 >= t1) return;
+  const int nthreads = blockDim.x;
+  const int Mp = padded_steps(M);
+  const int tile_x = CT * N, tile_y = CT * Mp, tile_elems = tile_x + tile_y;
+  float* rows0 = psm;                                          // [2][CT*N + CT*Mp]: rows of x, then rows of y
+  int* ind_s = reinterpret_cast<int*>(psm + 2 * (size_t)tile_elems);   // [N]
+  int* rank_s = ind_s + N;                                     // [N]
+  const float* ximg = x + (size_t)b * C * N;
+  const float* yimg = y + (size_t)b * C * Mp;                  // [C][Mp] (ipsr_blend_scan)
+  float* oimg = out + (size_t)b * C * N;
+  const bool bulk = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(ximg) & 15) == 0) &&
+                    (M == 0 || (reinterpret_cast<uintptr_t>(yimg) & 15) == 0);
+
+  auto load_tile = [&](int t, int buf) {                       // thread 0 (bulk) or everybody (fallback)
+    const int ct = min(CT, C - t * CT);
+    const float* src = ximg + (size_t)t * tile_x;
+    const float* srcy = yimg + (size_t)t * tile_y;
+    float* dst = rows0 + (size_t)buf * tile_elems;
+    if (bulk) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(smem_u32(&paste_bars[buf]), (uint32_t)(ct * (N + (M > 0 ? Mp : 0))) * 4u);
+        bulk_g2s(smem_u32(dst), src, (uint32_t)(ct * N) * 4u, smem_u32(&paste_bars[buf]));
+        if (M > 0) bulk_g2s(smem_u32(dst + tile_x), srcy, (uint32_t)(ct * Mp) * 4u, smem_u32(&paste_bars[buf]));
+      }
+    } else {
+      for (int i = threadIdx.x; i < ct * N; i += nthreads) dst[i] = __ldg(src + i);
+      if (M > 0)
+        for (int i = threadIdx.x; i < ct * Mp; i += nthreads) dst[tile_x + i] = __ldg(srcy + i);
     }
-  } else {
-    for (int i = threadIdx.x; i < total; i += blockDim.x) rows[i] = __ldg(xb + i);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&paste_bars[0]), 1);
+    mbar_init(smem_u32(&paste_bars[1]), 1);
+    mbar_fence_init();
   }
   __syncthreads();
-  bool landed = !bulk;
+  load_tile(t0, 0);
+  if (t0 + 1 < t1) load_tile(t0 + 1, 1);
   const int* indb = ind + (size_t)b * N;
-  const float* yb = y + (size_t)b * padded_steps(M) * C + c0;
-  for (int base = 0; base < N; base += 256 * kPastePre) {
-    int lq[kPastePre], pq[kPastePre];
-#pragma unroll
-    for (int i = 0; i < kPastePre; ++i) {
-      const int q = base + i * 256 + threadIdx.x;
-      lq[i] = -1;
-      pq[i] = 0;
-      if (q < N) {
-        lq[i] = __ldg(rank + q);
-        pq[i] = __ldg(indb + q);
-      }
+  for (int q = threadIdx.x; q < N; q += nthreads) {
+    ind_s[q] = __ldg(indb + q);
+    rank_s[q] = __ldg(rank + q);
+  }
+  __syncthreads();
+  for (int t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    const int ct = min(CT, C - t * CT);
+    const float* rows = rows0 + (size_t)buf * tile_elems;
+    const float* yrows = rows + tile_x;
+    float* ob = oimg + (size_t)t * tile_x;
+    if (bulk) mbar_wait(smem_u32(&paste_bars[buf]), (uint32_t)((t - t0) >> 1) & 1u);
+    else __syncthreads();
+    for (int q = threadIdx.x; q < N; q += nthreads) {
+      const int l = rank_s[q];
+      const float* srow = (l < 0) ? rows + ind_s[q] : yrows + l;
+      const int stride = (l < 0) ? N : Mp;
+      for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = srow[ch * stride];
     }
-    if (!landed) {
-      mbar_wait(smem_u32(&paste_bar), 0);
-      landed = true;
-    }
-#pragma unroll
-    for (int i = 0; i < kPastePre; ++i) {
-      const int q = base + i * 256 + threadIdx.x;
-      if (q >= N) continue;
-      if (lq[i] < 0) {
-        for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = rows[ch * N + pq[i]];
-      } else {
-        const float* yr = yb + (size_t)lq[i] * C;
-        for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = __ldg(yr + ch);
-      }
-    }
+    __syncthreads();                                           // everybody is done reading this buffer
+    if (t + 2 < t1) load_tile(t + 2, buf);
   }
 }
 
-// grid = (C / CT, B)
-__global__ void __launch_bounds__(256)
+// Tiles per CTA for a persistent tile loop: split every image's `ntiles` tiles over as many CTAs as fill whole
+// waves of `slots` resident CTAs, charging the per-CTA setup (index staging) about one tile.
+static int tiles_per_cta_for(int B, int ntiles, int slots) {
+  int best_tpc = ntiles;
+  double best_cost = 1e300;
+  for (int pcand = 1; pcand <= ntiles; ++pcand) {
+    const int tpc = (ntiles + pcand - 1) / pcand;
+    const int np = (ntiles + tpc - 1) / tpc;
+    const long long waves = ((long long)B * np + slots - 1) / slots;
+    const double cost = (double)waves * (tpc + 1.0);
+    if (cost < best_cost * 0.9999) {
+      best_cost = cost;
+      best_tpc = tpc;
+    }
+  }
+  return best_tpc;
+}
+
+// grid = (parts, B)
+__global__ void __launch_bounds__(512)
 paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ ind,
-             const int* __restrict__ rank, int C, int N, int M, int CT, float* __restrict__ out) {
-  extern __shared__ __align__(128) float rows[];         // [CT][N]
-  paste_cta(blockIdx.x, blockIdx.y, rows, x, y, ind, rank, C, N, M, CT, out);
+             const int* __restrict__ rank, int C, int N, int M, int CT, int tiles_per_cta, float* __restrict__ out) {
+  extern __shared__ __align__(128) float rows[];         // [2][CT][N] + ind[N] + rank[N]
+  paste_cta(blockIdx.x, blockIdx.y, tiles_per_cta, rows, x, y, ind, rank, C, N, M, CT, out);
 }
 
 // The paste and the two bookkeeping builders of the backward are independent once the scan is done:
@@ -386,13 +434,13 @@ paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int
 // The latency-bound bookkeeping CTAs are scheduled first and overlap the bandwidth-bound paste.
 struct FusedPasteArgs {
   const float* x; const float* y; const int* ind; const int* rank; float* out;
-  int B, C, N, M, CT, ctiles;
+  int B, C, N, M, CT, parts, tiles_per_cta;
   const int* flag; const int* mask_idx; int* route_ptr; int* route_q;
   const float* wn; const float* wo; int* exc_start; int* exc_cnt; int* exc_l; float* exc_w; int* exc_total; int exc_cap;
   int n_routes, n_exc, exc_per_img;
 };
 
-__global__ void __launch_bounds__(256) paste_fused_kernel(const FusedPasteArgs a) {
+__global__ void __launch_bounds__(512) paste_fused_kernel(const FusedPasteArgs a) {
   extern __shared__ __align__(128) float fsm[];
   int blk = blockIdx.x;
   if (blk < a.n_routes) {
@@ -406,18 +454,26 @@ __global__ void __launch_bounds__(256) paste_fused_kernel(const FusedPasteArgs a
     return;
   }
   blk -= a.n_exc;
-  paste_cta(blk % a.ctiles, blk / a.ctiles, fsm, a.x, a.y, a.ind, a.rank, a.C, a.N, a.M, a.CT, a.out);
+  paste_cta(blk % a.parts, blk / a.parts, a.tiles_per_cta, fsm, a.x, a.y, a.ind, a.rank, a.C, a.N, a.M, a.CT, a.out);
 }
 
 static int paste_ct(int C, int N) {
-  // channel rows per CTA: ~32 KiB of shared memory (several CTAs resident per SM, so that the bulk copy of one
-  // overlaps the gather of another), but at least 4 rows while they fit in 64 KiB (rank / ind are re-read per CTA)
-  int CT = (int)((32 * 1024) / ((size_t)N * sizeof(float)));
-  if (CT < 4) CT = (int)((64 * 1024) / ((size_t)N * sizeof(float))) >= 4 ? 4 : (int)((64 * 1024) / ((size_t)N * sizeof(float)));
+  // channel rows per tile: ~32 KiB of x rows (N > 2048: 64 KiB), at least 1 row
+  int CT = (int)(((N <= 2048 ? 32 : 64) * 1024) / ((size_t)N * sizeof(float)));
   if (CT < 1) CT = 1;
   if (CT > 16) CT = 16;
   if (CT > C) CT = C;
   return CT;
+}
+static size_t paste_smem(int CT, int N, int M) {
+  return 2 * (size_t)CT * (N + padded_steps(M)) * sizeof(float) + 2 * (size_t)N * sizeof(int);
+}
+static int paste_threads(int N) { return N > 2048 ? 512 : 256; }
+static int paste_slots(size_t smem, int threads) {
+  int resident = (int)((227 * 1024) / (smem + 2 * 1024));
+  if (resident < 1) resident = 1;
+  if (resident > 2048 / threads) resident = 2048 / threads;
+  return 148 * resident;
 }
 
 }  // namespace ipsr
@@ -460,7 +516,7 @@ static int dispatch_stage(const StageArgs& a, cudaStream_t st) {
 template <int T>
 static int launch_scan(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, cudaStream_t st) {
   const size_t blk_bytes = (size_t)staged_block_floats(C) * sizeof(float);
-  const size_t smem = 2 * ((blk_bytes + 127) & ~(size_t)127) + (size_t)C * sizeof(float);
+  const size_t smem = 2 * ((blk_bytes + 127) & ~(size_t)127) + ((size_t)C + (size_t)T * (C + 1)) * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -525,7 +581,7 @@ extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, co
   IPSR_REQUIRE(x && ind && rank && out && (M == 0 || y), IPSR_ERR_INVALID_ARG, "ipsr_paste: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_paste: bad dims");
   const int CT = paste_ct(C, N);
-  const size_t smem = (size_t)CT * N * sizeof(float);
+  const size_t smem = paste_smem(CT, N, M);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste: N=%d too large", N);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -533,7 +589,10 @@ extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, co
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  paste_kernel<<<dim3((C + CT - 1) / CT, B), 256, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, out);
+  const int threads = paste_threads(N);
+  const int ntiles = (C + CT - 1) / CT;
+  const int tpc = tiles_per_cta_for(B, ntiles, paste_slots(smem, threads));
+  paste_kernel<<<dim3((ntiles + tpc - 1) / tpc, B), threads, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, tpc, out);
   return check_launch("ipsr_paste");
 }
 
@@ -555,15 +614,21 @@ extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const
                  "ipsr_paste_with_bookkeeping: exception buffers missing");
   FusedPasteArgs a;
   a.x = x; a.y = y; a.ind = ind; a.rank = rank; a.out = out;
-  a.B = B; a.C = C; a.N = N; a.M = M; a.CT = paste_ct(C, N); a.ctiles = (C + a.CT - 1) / a.CT;
+  a.B = B; a.C = C; a.N = N; a.M = M; a.CT = paste_ct(C, N);
+  const int threads = paste_threads(N);
+  {
+    const int ntiles = (C + a.CT - 1) / a.CT;
+    a.tiles_per_cta = tiles_per_cta_for(B, ntiles, paste_slots(paste_smem(a.CT, N, M), threads));
+    a.parts = (ntiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  }
   a.flag = flag; a.mask_idx = mask_idx; a.route_ptr = route_ptr; a.route_q = route_q;
   a.wn = wn; a.wo = wo; a.exc_start = exc_start; a.exc_cnt = exc_cnt; a.exc_l = exc_l; a.exc_w = exc_w;
   a.exc_total = exc_total; a.exc_cap = exc_cap;
   a.n_routes = routes ? B : 0;
   a.exc_per_img = exc ? exc_parts(M) : 0;
   a.n_exc = B * a.exc_per_img;
-  size_t smem = (size_t)a.CT * N * sizeof(float);
-  const size_t smem_routes = (size_t)(2 * N + 1) * sizeof(int), smem_exc = ((size_t)N + 3 * kExcChunk) * sizeof(int);
+  size_t smem = paste_smem(a.CT, N, M);
+  const size_t smem_routes = (size_t)(2 * N + 1) * sizeof(int), smem_exc = ((size_t)((N + 3) & ~3) + ((M + 3) & ~3) + 3 * kExcChunk) * sizeof(int);
   if (routes && smem_routes > smem) smem = smem_routes;
   if (exc && smem_exc > smem) smem = smem_exc;
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: N=%d too large", N);
@@ -573,8 +638,8 @@ extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste_fused smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  const long long ctas = (long long)a.n_routes + a.n_exc + (long long)B * a.ctiles;
+  const long long ctas = (long long)a.n_routes + a.n_exc + (long long)B * a.parts;
   IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: grid too large");
-  paste_fused_kernel<<<(unsigned)ctas, 256, smem, as_stream(stream)>>>(a);
+  paste_fused_kernel<<<(unsigned)ctas, threads, smem, as_stream(stream)>>>(a);
   return check_launch("ipsr_paste_with_bookkeeping");
 }

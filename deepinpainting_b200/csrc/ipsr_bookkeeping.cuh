@@ -10,13 +10,13 @@ namespace ipsr {
 // ---------------------------------------------------------------------------------------------
 // unit routes: stable counting sort of {q : unmasked or q == q_0} by p = ind[q]
 // ---------------------------------------------------------------------------------------------
-// one CTA of 256 threads per image; rsm: (2N+1) ints of shared memory
+// one CTA (any multiple of 32 threads up to 1024) per image; rsm: (2N+1) ints of shared memory
 __device__ __forceinline__ void
 build_routes_cta(int b, int* rsm, const int* __restrict__ ind, const int* __restrict__ flag, const int* __restrict__ mask_idx,
                  int N, int M, int* __restrict__ route_ptr, int* __restrict__ route_q) {
   int* cursor = rsm;            // [N+1] counts -> exclusive offsets -> running cursors
   int* key = rsm + (N + 1);     // [N]   p = ind[q] for routed q, -1 otherwise
-  __shared__ int warp_tot[8];
+  __shared__ int warp_tot[32];
   __shared__ int carry;
   const int* indb = ind + (size_t)b * N;
   const int q_first = (M > 0) ? mask_idx[0] : -1;
@@ -32,7 +32,8 @@ build_routes_cta(int b, int* rsm, const int* __restrict__ ind, const int* __rest
     if (routed) atomicAdd(&cursor[p], 1);
   }
   __syncthreads();
-  // exclusive scan of cursor[0..N) in chunks of 256, cursor[N] = total
+  // exclusive scan of cursor[0..N) in chunks of blockDim.x, cursor[N] = total
+  const int nwarps = blockDim.x >> 5;
   for (int base = 0; base < N; base += blockDim.x) {
     const int i = base + threadIdx.x;
     const int v = (i < N) ? cursor[i] : 0;
@@ -50,7 +51,7 @@ build_routes_cta(int b, int* rsm, const int* __restrict__ ind, const int* __rest
     __syncthreads();
     if (threadIdx.x == 0) {
       int t = 0;
-      for (int w = 0; w < 8; ++w) t += warp_tot[w];
+      for (int w = 0; w < nwarps; ++w) t += warp_tot[w];
       carry += t;
     }
     __syncthreads();
@@ -93,19 +94,34 @@ constexpr int kExcThreads = 256;
 // CTAs per image: one per 256 masked steps (every owner thread then walks the whole tail of the recurrence once)
 __host__ __device__ inline int exc_parts(int M) { return M <= kExcThreads ? 1 : (M + kExcThreads - 1) / kExcThreads; }
 
-// out_q receives the POSITION q_l = mask_idx[l] of every surviving entry (the backward gathers g[:, q_l])
+// One owner = one bank column p, identified by the first masked step l0 whose match is p.  Walks
+// row_l[p] = row_{l-1}[p] * wn_l (+ wo_l if p_l == p) for l = l0 .. M-1 in the reference's operation order and
+// counts (WRITE: stores) every entry that survives the float -> int64 store (l >= 1, |e| >= 1): the position
+// q_l = mask_idx[l] of the row and its truncated weight.  The walk is a chain of M dependent steps executed by a
+// lone warp, so the step is kept to a handful of instructions: operands come as 16-byte shared-memory vectors, the
+// addend is selected off the dependent chain (adding +0 when p_l != p leaves every non-zero value untouched).
 template <bool WRITE>
 __device__ __forceinline__ int replay_owner(int l0, int p, int base, int n, const float* s_wn, const float* s_wo,
                                             const int* s_p, const int* __restrict__ mask_idx, float& e, int cnt,
-                                            int* __restrict__ out_l, float* __restrict__ out_w) {
+                                            int* __restrict__ out_q, float* __restrict__ out_w) {
   // processes steps l in [max(base, l0), base+n) of this chunk
+  auto step = [&](int i, float wn_i, float wo_i, int p_i) {
+    e = __fadd_rn(__fmul_rn(e, wn_i), (p_i == p) ? wo_i : 0.f);     // row * wn; row[p_l] += wo        :123-124
+    if (!(fabsf(e) < 1.0f)) {                                        // survives the int64 store        :134
+      if (WRITE) {
+        out_q[cnt] = mask_idx[base + i];
+        out_w[cnt] = trunc_as_reference(e);
+      }
+      ++cnt;
+    }
+  };
   int i = l0 - base;
   if (i >= n) return cnt;
   if (i >= 0) {                                             // first appearance: row[p] = 0*wn + wo (or 1 at l = 0)
     e = (l0 == 0) ? 1.f : s_wo[i];
     if (l0 >= 1 && !(fabsf(e) < 1.0f)) {
       if (WRITE) {
-        out_l[cnt] = mask_idx[l0];
+        out_q[cnt] = mask_idx[l0];
         out_w[cnt] = trunc_as_reference(e);
       }
       ++cnt;
@@ -114,36 +130,41 @@ __device__ __forceinline__ int replay_owner(int l0, int p, int base, int n, cons
   } else {
     i = 0;
   }
-#pragma unroll 4
-  for (; i < n; ++i) {
-    e = __fmul_rn(e, s_wn[i]);                              // row * wn                      :123
-    if (s_p[i] == p) e = __fadd_rn(e, s_wo[i]);             // row[p_l] += wo                :124
-    if (!(fabsf(e) < 1.0f)) {                               // survives the int64 store      :134
-      if (WRITE) {
-        out_l[cnt] = mask_idx[base + i];
-        out_w[cnt] = trunc_as_reference(e);
-      }
-      ++cnt;
-    }
+  for (; (i & 3) != 0 && i < n; ++i) step(i, s_wn[i], s_wo[i], s_p[i]);
+  for (; i + 4 <= n; i += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(s_wn + i);
+    const float4 c = *reinterpret_cast<const float4*>(s_wo + i);
+    const int4 pp = *reinterpret_cast<const int4*>(s_p + i);
+    step(i, a.x, c.x, pp.x);
+    step(i + 1, a.y, c.y, pp.y);
+    step(i + 2, a.z, c.z, pp.z);
+    step(i + 3, a.w, c.w, pp.w);
   }
+  for (; i < n; ++i) step(i, s_wn[i], s_wo[i], s_p[i]);
   return cnt;
 }
 
-// CTA `part` of `nparts` of image b owns the masked steps l0 = part + nparts * k.
-// fsm: first-occurrence table [N] ints, then 3*kExcChunk staging words
+// CTA `part` of `nparts` of image b owns the masked steps l0 with l0 % nparts == part.
+// fsm: first-occurrence table [N] ints, owner list [M] ints (padded to 4), then 3*kExcChunk staging words (16-byte aligned)
 __device__ __forceinline__ void
 build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                      const float* __restrict__ wn, const float* __restrict__ wo, int N, int M,
                      int* __restrict__ exc_start, int* __restrict__ exc_cnt, int* __restrict__ exc_l,
                      float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap) {
   int* first = reinterpret_cast<int*>(fsm);                 // [N] first masked step whose match is p, or INT_MAX
-  float* s_wn = reinterpret_cast<float*>(first + N);
+  int* owners = first + ((N + 3) & ~3);                     // [M] compact list of this part's owner steps
+  float* s_wn = reinterpret_cast<float*>(owners + ((M + 3) & ~3));
   float* s_wo = s_wn + kExcChunk;
   int* s_p = reinterpret_cast<int*>(s_wo + kExcChunk);
+  __shared__ int nonfinite_w, nown_s;
   const int* ind_b = ind + (size_t)b * N;
   const float* wnb = wn + (size_t)b * M;
   const float* wob = wo + (size_t)b * M;
   for (int p = threadIdx.x; p < N; p += blockDim.x) first[p] = 0x7FFFFFFF;
+  if (threadIdx.x == 0) {
+    nonfinite_w = 0;
+    nown_s = 0;
+  }
   __syncthreads();
   for (int l = threadIdx.x; l < M; l += blockDim.x) atomicMin(&first[ind_b[mask_idx[l]]], l);
   __syncthreads();
@@ -157,11 +178,13 @@ build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restri
       exc_cnt[(size_t)b * N + p] = 0;
     }
   }
+  // compact owner list: only the first occurrence of a column walks it, and only a fraction of the masked steps
+  // are first occurrences -- compaction keeps every lane of the walking warps busy
+  for (int l0 = part + nparts * (int)threadIdx.x; l0 < M; l0 += nparts * (int)blockDim.x)
+    if (first[ind_b[mask_idx[l0]]] == l0) owners[atomicAdd(&nown_s, 1)] = l0;
   // A non-finite weight turns EVERY column of the later rows into NaN (0 * inf), which the sparse
   // "first occurrence" walk below cannot represent: flag the image as overflowed so that the backward
   // replays the full recurrence per column (bit-faithful, slow, chaotic inputs only).
-  __shared__ int nonfinite_w;
-  if (threadIdx.x == 0) nonfinite_w = 0;
   int cur_base = -1;                                        // chunk currently staged (uniform)
   auto stage = [&](int base) {
     if (base == cur_base) return;
@@ -177,22 +200,19 @@ build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restri
     __syncthreads();
     cur_base = base;
   };
-  // owners are processed in rounds of blockDim.x masked positions of this part
-  const int span = (int)blockDim.x * nparts;
-  for (int round = 0; round < M; round += span) {
-    const int l0 = round + (int)threadIdx.x * nparts + part;
-    int p = -1;
-    if (l0 < M) {
-      p = ind_b[mask_idx[l0]];
-      if (first[p] != l0) p = -1;                           // not the first occurrence: another thread owns p
-    }
-    const int base0 = (round / kExcChunk) * kExcChunk;
-    // pass 0: count the surviving entries of this column
+  stage(0);                                                 // also publishes the owner list
+  const int nown = nown_s;
+  for (int round = 0; round < nown; round += blockDim.x) {
+    const int k = round + threadIdx.x;
+    const int l0 = (k < nown) ? owners[k] : M;
+    const int p = (k < nown) ? ind_b[mask_idx[l0]] : -1;
+    // walk 1: count the surviving entries of this column
     float e = 0.f;
     int found = 0;
-    for (int base = base0; base < M; base += kExcChunk) {
+    for (int base = 0; base < M; base += kExcChunk) {
       stage(base);
-      if (p >= 0) found = replay_owner<false>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, found, nullptr, nullptr);
+      if (p >= 0) found = replay_owner<false>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, found, nullptr,
+                                              nullptr);
     }
     // reserve a contiguous slot range (placement is arbitrary, order inside is ascending l)
     int start = 0;
@@ -205,14 +225,13 @@ build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restri
         exc_cnt[(size_t)b * N + p] = found;
       }
     }
-    // pass 1 (only when somebody in the CTA has something to write -- uniform decision)
+    // walk 2: only the owners that have something to write (uniform decision)
     if (__syncthreads_or(fits ? 1 : 0)) {
-      if (!fits) p = -1;
       e = 0.f;
       int cnt = 0;
-      for (int base = base0; base < M; base += kExcChunk) {
+      for (int base = 0; base < M; base += kExcChunk) {
         stage(base);
-        if (p >= 0)
+        if (fits)
           cnt = replay_owner<true>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, cnt,
                                    exc_l + (size_t)b * exc_cap + start, exc_w + (size_t)b * exc_cap + start);
       }

@@ -22,7 +22,7 @@ build_exceptions_kernel(const int* __restrict__ ind, const int* __restrict__ mas
                         const float* __restrict__ wo, int N, int M, int* __restrict__ exc_start, int* __restrict__ exc_cnt,
                         int* __restrict__ exc_l, float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap,
                         int nparts) {
-  extern __shared__ int esm[];                             // [N] + 3*kExcChunk words
+  extern __shared__ __align__(16) int esm[];               // [N] + [M] + 3*kExcChunk words
   build_exceptions_cta(blockIdx.x / nparts, blockIdx.x % nparts, nparts, esm, ind, mask_idx, wn, wo, N, M, exc_start,
                        exc_cnt, exc_l, exc_w, exc_total, exc_cap);
 }
@@ -236,7 +236,7 @@ extern "C" int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx
   IPSR_REQUIRE(ind && mask_idx && wn && wo && exc_start && exc_cnt && exc_l && exc_w && exc_total, IPSR_ERR_INVALID_ARG,
                "ipsr_build_exceptions: null pointer");
   IPSR_REQUIRE(B > 0 && N > 0 && exc_cap > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_build_exceptions: bad dims");
-  const size_t smem = ((size_t)N + 3 * kExcChunk) * sizeof(int);
+  const size_t smem = ((size_t)((N + 3) & ~3) + ((M + 3) & ~3) + 3 * kExcChunk) * sizeof(int);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_build_exceptions: N=%d too large", N);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(build_exceptions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -230,10 +230,14 @@ def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Opti
     tensor = mode == "tensor" or (mode == "auto" and _lib.load().ipsr_tensor_path_supported(C, N) == 1)
     n = 1                                   # extract_normalize
     n += 4 if tensor else 1                 # correlate_tc + finalize (+ compaction), correlate_tc + finalize | select_all_rows
-    n += 2                                  # correlate_fp32 + apply_recheck
+    n += 2                                  # correlate_fp32 + resolve_rows
     if M > 0:
-        n += 2                              # blend_stage + blend_scan
-    n += 1                                  # paste (+ routes / exceptions builders in the same launch)
+        n += 2                              # blend_stage (+ routes builders in the same launch) + blend_scan
+    elif need_grad:
+        n += 1                              # build_routes
+    n += 1                                  # paste
+    if need_grad and M > 1:
+        n += 1                              # build_exceptions (side stream, next to the paste)
     if backward:
         n += 1                              # shift_bwd
     return n

@@ -205,11 +205,12 @@ int ipsr_padded_steps(int M);
  * wn = a/(a+v); wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).  Inside a block the
  * scalars a_l are tracked by linearity (a_i <- wn_l a_i + wo_l Gt[l][i]) so that the dependent chain
  * is one scalar step per masked position; y is re-anchored at every block boundary.
- * Writes y [B][ipsr_padded_steps(M)][C], wn/wo [B,M] (wn[b,0] = 0, wo[b,0] = 1). */
+ * Writes y [B][C][ipsr_padded_steps(M)] (channel-major: the paste reads rows), wn/wo [B,M] (wn[b,0] = 0,
+ * wo[b,0] = 1). */
 int ipsr_blend_scan(const float* staged, int B, int C, int M,
                     float* y, float* wn, float* wo, void* stream);
 
-/* out[b,:,q] = y[b,rank[q],:] (y laid out [B][ipsr_padded_steps(M)][C]) for masked q,
+/* out[b,:,q] = y[b,:,rank[q]] (y laid out [B][C][ipsr_padded_steps(M)]) for masked q,
  * x[b,:,ind[b,q]] otherwise (replaces the dense
  * conv_transpose of IPSRFunction.py:131). */
 int ipsr_paste(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
