@@ -253,16 +253,34 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
     const float* V = Gt + T * T;
     const int l0 = k * T;
 
-    // ---- B: z_i = <u_i, y_prev> ----
-    for (int i = warp; i < T; i += kScanThreads / 32) {
-      const float* u = U + (size_t)i * C;
-      float p0 = 0.f, p1 = 0.f;
-      for (int c = lane; c < C; c += 64) {
-        p0 = fmaf(u[c], ysm[c], p0);
-        if (c + 32 < C) p1 = fmaf(u[c + 32], ysm[c + 32], p1);
+    // ---- B: z_i = <u_i, y_prev>: every warp takes T/8 rows at once (y is read once per lane, the row
+    //         reductions overlap) ----
+    {
+      constexpr int R = (T + 7) / 8;                         // rows per warp
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 4
+      for (int c = lane; c < C; c += 32) {
+        const float yv = ysm[c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = warp + r * (kScanThreads / 32);
+          if (i < T) acc[r] = fmaf(U[(size_t)i * C + c], yv, acc[r]);
+        }
       }
-      const float zz = warp_sum(p0 + p1);
-      if (lane == 0) zs[i] = zz;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = warp + r * (kScanThreads / 32);
+          if (i < T) zs[i] = acc[r];
+        }
+      }
     }
     __syncthreads();
 
@@ -272,19 +290,24 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
       float z = zs[li];
       const float v = V[li];
       float my_wn = 0.f, my_wo = 1.f;
+      // operands that do not depend on the chain first: Gram column of this lane, v of every step
+      float g[T], vj[T];
 #pragma unroll
       for (int j = 0; j < T; ++j) {
-        const float g = Gt[j * T + li];
+        g[j] = Gt[j * T + li];
+        vj[j] = __shfl_sync(0xffffffffu, v, j);
+      }
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
         const float zj = __shfl_sync(0xffffffffu, z, j);
-        const float vj = __shfl_sync(0xffffffffu, v, j);
-        const float r = rcp_approx(__fadd_rn(zj, vj));          // no clamp: inf / nan propagate      :120
+        const float r = rcp_approx(__fadd_rn(zj, vj[j]));       // no clamp: inf / nan propagate      :120
         float wn = __fmul_rn(zj, r);
-        float wo = __fmul_rn(vj, r);                            //                                     :121
+        float wo = __fmul_rn(vj[j], r);                         //                                     :121
         if (k == 0 && j == 0) {                                 // first masked patch: plain copy      :98-101
           wn = 0.f;
           wo = 1.f;
         }
-        z = fmaf(wn, z, __fmul_rn(wo, g));
+        z = fmaf(wn, z, __fmul_rn(wo, g[j]));
         if (lane == j) {
           my_wn = wn;
           my_wo = wo;
@@ -310,10 +333,20 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
       const int c = tid + m * kScanThreads;
       if (c < C) {
         float yy = yreg[m];
-#pragma unroll 8
-        for (int j = 0; j < nvalid; ++j) {
-          yy = __fadd_rn(__fmul_rn(wn_s[j], yy), __fmul_rn(wo_s[j], K[(size_t)j * C + c]));     // :122
-          ytile[j * (C + 1) + c] = yy;
+        if (nvalid == T) {                                   // full block: operands first, then the 2-op chain
+          float kv[T];
+#pragma unroll
+          for (int j = 0; j < T; ++j) kv[j] = K[(size_t)j * C + c];
+#pragma unroll
+          for (int j = 0; j < T; ++j) {
+            yy = __fadd_rn(__fmul_rn(wn_s[j], yy), __fmul_rn(wo_s[j], kv[j]));                  // :122
+            ytile[j * (C + 1) + c] = yy;
+          }
+        } else {
+          for (int j = 0; j < nvalid; ++j) {
+            yy = __fadd_rn(__fmul_rn(wn_s[j], yy), __fmul_rn(wo_s[j], K[(size_t)j * C + c]));   // :122
+            ytile[j * (C + 1) + c] = yy;
+          }
         }
         yreg[m] = yy;
         ysm[c] = yy;
