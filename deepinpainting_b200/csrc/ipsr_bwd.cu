@@ -45,14 +45,16 @@ constexpr int kBwdLight = 24;            // entries a single thread sums; heavie
 constexpr int kBwdQueue = 512;
 
 template <int CT>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(CT >= 8 ? 512 : 1024)
 shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per_cta, const int* __restrict__ route_ptr,
                  const int* __restrict__ route_q, const int* __restrict__ exc_start, const int* __restrict__ exc_cnt,
                  const int* __restrict__ exc_l, const float* __restrict__ exc_w, const int* __restrict__ exc_total,
                  int exc_cap, const int* __restrict__ ind, const int* __restrict__ mask_idx,
-                 const float* __restrict__ wn, const float* __restrict__ wo, float triple_w, float* __restrict__ gin) {
-  extern __shared__ __align__(128) float bwd_smem[];      // rows[2][CT*N] | spec[N]
+                 const float* __restrict__ wn, const float* __restrict__ wo, float triple_w, float* __restrict__ gin,
+                 int ninfo, int nexc_s) {
+  extern __shared__ __align__(128) float bwd_smem[];      // rows[2][CT*N] | spec[N] | info[N] int4 | rq[N] | el[E] | ew[E]
   __shared__ int heavy[kBwdQueue];
+  __shared__ int4 heavy_info[kBwdQueue];
   __shared__ int nheavy, nspec_s;
   __shared__ __align__(8) unsigned long long bars[2];
   const int b = blockIdx.y;
@@ -64,6 +66,10 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
   const uint32_t tile_bytes = (uint32_t)tile_elems * 4u;
   float* rows0 = bwd_smem;
   int* spec = reinterpret_cast<int*>(bwd_smem + 2 * (size_t)tile_elems);
+  int4* info = reinterpret_cast<int4*>(spec + ((N + 3) & ~3));      // per listed column: first route, routes, first exception, exceptions
+  int* rq_s = reinterpret_cast<int*>(info + ninfo);                 // the CSR's row list
+  int* el_s = rq_s + N;                                             // exception entries (when they fit)
+  float* ew_s = reinterpret_cast<float*>(el_s + nexc_s);
   const int nthreads = blockDim.x;
   const float* gimg = g + (size_t)b * C * N;
   float* oimg = gin + (size_t)b * C * N;
@@ -103,22 +109,42 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
   const int* estart = exc_start + (size_t)b * N;
   const int* el = exc_l + (size_t)b * exc_cap;
   const float* ew = exc_w + (size_t)b * exc_cap;
-  // the columns that receive something, once per CTA (list order does not affect any sum)
+  // the columns that receive something, once per CTA (list order does not affect any sum); their CSR entries and
+  // the image's route / exception lists are staged in shared memory, so that the per-tile work below never waits
+  // on global memory for an index
+  const int etotal = lists ? min(exc_total[b], exc_cap) : 0;
+  const bool exc_in_smem = etotal <= nexc_s;
   for (int p = threadIdx.x; p < N; p += nthreads) {
-    const int work = __ldg(gptr + p + 1) - __ldg(gptr + p) + (lists ? __ldg(ecnt + p) : 0);
+    const int r0 = __ldg(gptr + p), n = __ldg(gptr + p + 1) - r0;
+    const int ne = lists ? __ldg(ecnt + p) : 0;
+    const int work = n + ne;
     if (overflow || work > 0) {
+      const int4 rec = make_int4(r0, n, lists ? __ldg(estart + p) : 0, ne);
       bool queued = false;
       if (work > kBwdLight && !overflow) {
         const int slot = atomicAdd(&nheavy, 1);
         if (slot < kBwdQueue) {
           heavy[slot] = p;
+          heavy_info[slot] = rec;
           queued = true;
         }
       }
-      if (!queued) spec[atomicAdd(&nspec_s, 1)] = p;
+      if (!queued) {
+        const int k = atomicAdd(&nspec_s, 1);
+        spec[k] = p;
+        if (k < ninfo) info[k] = rec;
+      }
     }
   }
+  for (int i = threadIdx.x; i < N; i += nthreads) rq_s[i] = __ldg(grq + i);
+  if (exc_in_smem)
+    for (int i = threadIdx.x; i < etotal; i += nthreads) {
+      el_s[i] = __ldg(el + i);
+      ew_s[i] = __ldg(ew + i);
+    }
   __syncthreads();
+  const int* elx = exc_in_smem ? el_s : el;
+  const float* ewx = exc_in_smem ? ew_s : ew;
   const int nspec = nspec_s;
   const int nh = min(nheavy, kBwdQueue);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
@@ -143,20 +169,22 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
     // (2) corrections
     for (int k = threadIdx.x; k < nspec; k += nthreads) {
       const int p = spec[k];
-      const int r0 = __ldg(gptr + p), r1 = __ldg(gptr + p + 1);
-      const int ne = lists ? __ldg(ecnt + p) : 0;
-      const int es = lists ? __ldg(estart + p) : 0;
+      int4 rec;
+      if (k < ninfo) rec = info[k];
+      else rec = make_int4(__ldg(gptr + p), __ldg(gptr + p + 1) - __ldg(gptr + p), lists ? __ldg(estart + p) : 0,
+                           lists ? __ldg(ecnt + p) : 0);
+      const int r0 = rec.x, r1 = rec.x + rec.y, es = rec.z, ne = rec.w;
       float acc[CT];
 #pragma unroll
       for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
       for (int r = r0; r < r1; ++r) {
-        const int q = __ldg(grq + r);
+        const int q = rq_s[r];
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
       }
       for (int e = 0; e < ne; ++e) {
-        const int q = __ldg(el + es + e);
-        const float w = __ldg(ew + es + e);
+        const int q = elx[es + e];
+        const float w = ewx[es + e];
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
       }
@@ -179,20 +207,21 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
     }
     for (int h = warp; h < nh; h += nwarps) {                // hub columns: one warp each
       const int p = heavy[h];
-      const int r0 = __ldg(gptr + p), r1 = __ldg(gptr + p + 1);
+      const int4 rec = heavy_info[h];
+      const int r0 = rec.x, r1 = rec.x + rec.y;
       float acc[CT];
 #pragma unroll
       for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
       for (int r = r0 + lane; r < r1; r += 32) {
-        const int q = __ldg(grq + r);
+        const int q = rq_s[r];
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
       }
       if (lists) {
-        const int ne = __ldg(ecnt + p), es = __ldg(estart + p);
+        const int ne = rec.w, es = rec.z;
         for (int e = lane; e < ne; e += 32) {
-          const int q = __ldg(el + es + e);
-          const float w = __ldg(ew + es + e);
+          const int q = elx[es + e];
+          const float w = ewx[es + e];
 #pragma unroll
           for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
         }
@@ -264,12 +293,21 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   int CT = 8;
   const size_t tile_cap = (N <= 2048 ? 32 : 64) * 1024;
   while (CT > 1 && (C % CT != 0 || (size_t)CT * N * sizeof(float) > tile_cap)) CT >>= 1;
-  const size_t smem = 2 * (size_t)CT * N * sizeof(float) + (size_t)N * sizeof(int);
-  IPSR_REQUIRE(smem <= 227 * 1024 - 4 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
+  // shared memory: two tiles + the column list [N] + the CSR row list [N], then as much of the per-column records
+  // (16 B each) and of the exception entries (8 B each) as fits: what does not fit is read from global memory
+  const size_t base_smem = 2 * (size_t)CT * N * sizeof(float) + 2 * (size_t)((N + 3) & ~3) * sizeof(int);
+  IPSR_REQUIRE(base_smem <= 227 * 1024 - 12 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
+  const size_t room = (N <= 2048 ? 96 : 215) * 1024 - 12 * 1024 > base_smem ? (N <= 2048 ? 96 : 215) * 1024 - 12 * 1024 - base_smem : 0;
+  int ninfo = (int)((room / 2) / 16);
+  if (ninfo > N) ninfo = N;
+  int nexc_s = (int)((room - (size_t)ninfo * 16) / 8) & ~3;
+  if (nexc_s > exc_cap) nexc_s = (exc_cap + 3) & ~3;
+  if (M <= 1) nexc_s = 0;
+  const size_t smem = base_smem + (size_t)ninfo * 16 + (size_t)nexc_s * 8;
   const int threads = N > 2048 ? 1024 : 512;
   // split every image's tiles over `parts` CTAs so that the grid fills whole waves of resident CTAs
   const int ntiles = C / CT;
-  int resident = (int)((227 * 1024) / (smem + 4 * 1024));
+  int resident = (int)((227 * 1024) / (smem + 12 * 1024));
   if (resident < 1) resident = 1;
   if (resident > 2048 / threads) resident = 2048 / threads;
   const int slots = 148 * resident;
@@ -289,19 +327,19 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   }
   const int tiles_per_cta = (ntiles + parts - 1) / parts;
   void (*kern)(const float*, int, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
-               const int*, int, const int*, const int*, const float*, const float*, float, float*) = nullptr;
+               const int*, int, const int*, const int*, const float*, const float*, float, float*, int, int) = nullptr;
   switch (CT) {
     case 8: kern = shift_bwd_kernel<8>; break;
     case 4: kern = shift_bwd_kernel<4>; break;
     case 2: kern = shift_bwd_kernel<2>; break;
     default: kern = shift_bwd_kernel<1>; break;
   }
-  if (smem > 48 * 1024) {
+  if (smem + 12 * 1024 > 48 * 1024) {                       // static (queues) + dynamic shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "shift_bwd smem attribute: %s", cudaGetErrorString(e));
   }
   kern<<<dim3(parts, B), threads, smem, as_stream(stream)>>>(g, C, N, M, tiles_per_cta, route_ptr, route_q, exc_start, exc_cnt,
                                                             exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn, wo, triple_w,
-                                                            gin);
+                                                            gin, ninfo, nexc_s);
   return check_launch("ipsr_shift_bwd");
 }
