@@ -253,7 +253,13 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
     const float tol_abs = a->tol_abs >= 0.f ? a->tol_abs : kDefaultTolAbs;
     int32_t* list2 = at<int32_t>(a, w.list2);
     // pass 1: hi * hi over every row
-    const int ps1 = auto_split((long long)B * RB);
+    // two row tiles per CTA halve the L2 -> SM traffic of the streamed bank tiles: prefer them (with a column split
+    // that brings the CTA count back up) whenever that still occupies most SMs
+    int ps1 = auto_split((long long)B * RB);
+    if (RB % 2 == 0 && a->psplit <= 0) {
+      const int ps_two = auto_split((long long)B * (RB / 2));
+      if ((long long)B * (RB / 2) * ps_two >= 100) ps1 = ps_two;
+    }
     IPSR_FORWARD(record(a->ev_corr_begin));
     IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps1, 1, 2, nullptr,
                                           at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),

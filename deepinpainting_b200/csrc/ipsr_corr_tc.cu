@@ -432,9 +432,9 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
     IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
     return a_res ? launch_tc<1, 3, true>(prm, C, ctas, st) : launch_tc<1, 3, false>(prm, C, ctas, st);
   }
-  // two row tiles per CTA when the grid still fills the machine and both fit next to >= 4 ring stages
+  // two row tiles per CTA when the grid still fills most of the machine and both fit next to >= 4 ring stages
   const bool two = a_res && (prm.RB % 2 == 0) && (2 * a_one + 4 * (size_t)kTileBytes + 2048 <= 227 * 1024) &&
-                   ((long long)B * (prm.RB / 2) * psplit >= 148) && s_dump == nullptr;
+                   ((long long)B * (prm.RB / 2) * psplit >= 100) && s_dump == nullptr;
   const long long ctas = (long long)B * (two ? prm.RB / 2 : prm.RB) * psplit;
   IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
   if (two) return launch_tc<2, 1, true>(prm, C, ctas, st);
