@@ -62,7 +62,10 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
   float* gG = gK + (size_t)T * C;
   float* gV = gG + T * T;
 
-  for (int r = warp; r < T; r += 8) {
+#pragma unroll
+  for (int rr_ = 0; rr_ < (T + 7) / 8; ++rr_) {           // unrolled: the index chains of the warp's rows overlap
+    const int r = warp + 8 * rr_;
+    if (r >= T) break;
     const int l = l0 + r;
     float* su = Us + (size_t)r * ld;
     float* sk = Ks + (size_t)r * ld;
@@ -109,15 +112,17 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
   }
   __syncthreads();
 
-  // Gram: tile (ti, tj) -> rows i = 2ti, 2ti+1 of U against rows j = 2tj, 2tj+1 of K
+  // Gram: tile (ti, tj) -> rows i = ti, ti + T/2 of U against rows j = tj, tj + T/2 of K
   const int tile = threadIdx.x % kTiles, ks = threadIdx.x / kTiles;
   const int ti = tile / (T / 2), tj = tile % (T / 2);
   const int cper = ((C / 4 + kSplit - 1) / kSplit) * 4;
   const int cbeg = ks * cper, cend = min(C, cbeg + cper);
-  const float* u0 = Us + (size_t)(2 * ti) * ld;
-  const float* u1 = u0 + ld;
-  const float* k0 = Ks + (size_t)(2 * tj) * ld;
-  const float* k1 = k0 + ld;
+  // rows (ti, ti + T/2) x (tj, tj + T/2): the 8 lanes of a quarter warp read 8 CONSECUTIVE rows of K, whose padded
+  // stride of C + 4 floats puts their 16-byte vectors on 8 different bank groups (conflict-free)
+  const float* u0 = Us + (size_t)ti * ld;
+  const float* u1 = u0 + (size_t)(T / 2) * ld;
+  const float* k0 = Ks + (size_t)tj * ld;
+  const float* k1 = k0 + (size_t)(T / 2) * ld;
   float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
 #pragma unroll 4
   for (int c = cbeg; c < cend; c += 4) {
@@ -130,18 +135,18 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
     g10 = fmaf(a1.x, b0.x, g10); g10 = fmaf(a1.y, b0.y, g10); g10 = fmaf(a1.z, b0.z, g10); g10 = fmaf(a1.w, b0.w, g10);
     g11 = fmaf(a1.x, b1.x, g11); g11 = fmaf(a1.y, b1.y, g11); g11 = fmaf(a1.z, b1.z, g11); g11 = fmaf(a1.w, b1.w, g11);
   }
-  const int i0 = 2 * ti, j0 = 2 * tj;
+  const int i0 = ti, i1 = ti + T / 2, j0 = tj, j1 = tj + T / 2;
   if (kSplit == 1) {
-    gG[(j0) * T + i0] = g00;
-    gG[(j0 + 1) * T + i0] = g01;
-    gG[(j0) * T + i0 + 1] = g10;
-    gG[(j0 + 1) * T + i0 + 1] = g11;
+    gG[j0 * T + i0] = g00;
+    gG[j1 * T + i0] = g01;
+    gG[j0 * T + i1] = g10;
+    gG[j1 * T + i1] = g11;
   } else {
     float* mine = red + (size_t)ks * T * T;
-    mine[(j0) * T + i0] = g00;
-    mine[(j0 + 1) * T + i0] = g01;
-    mine[(j0) * T + i0 + 1] = g10;
-    mine[(j0 + 1) * T + i0 + 1] = g11;
+    mine[j0 * T + i0] = g00;
+    mine[j1 * T + i0] = g01;
+    mine[j0 * T + i1] = g10;
+    mine[j1 * T + i1] = g11;
     __syncthreads();
     for (int e = threadIdx.x; e < T * T; e += 256) {
       float s = red[e];
