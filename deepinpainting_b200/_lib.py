@@ -42,6 +42,7 @@ SIGNATURES = {
     "ipsr_last_error_string": (C.c_char_p, []),
     "ipsr_version": (_i, []),
     "ipsr_tensor_path_supported": (_i, [_i, _i]),
+    "ipsr_tensor_cascade": (_i, [_i, _i, _i]),
     "ipsr_feat_mask": (_i, [_p, _i, _i, _i, _f, _p, _p, _p]),
     "ipsr_build_flags": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ipsr_extract_normalize": (_i, [_p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -193,6 +193,12 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
 extern "C" const char* ipsr_last_error_string(void) { return ipsr::g_err; }
 extern "C" int ipsr_version(void) { return 100; }
 
+extern "C" int ipsr_tensor_cascade(int B, int C, int N) {
+  if (!ipsr_tensor_path_supported(C, N)) return 0;
+  const long long rb = N / ipsr::kTileRows;
+  return ((long long)B * rb * rb * (C / ipsr::kTileK) >= 12000) ? 1 : 0;
+}
+
 extern "C" size_t ipsr_workspace_bytes(int B, int C, int H, int W, int M, int mode) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || M < 0) return 0;
   return ipsr::carve(B, C, H * W, M, mode).total;
@@ -251,37 +257,54 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
       return ps < 1 ? 1 : ps;
     };
     const float tol_abs = a->tol_abs >= 0.f ? a->tol_abs : kDefaultTolAbs;
-    int32_t* list2 = at<int32_t>(a, w.list2);
-    // pass 1: hi * hi over every row
-    // two row tiles per CTA halve the L2 -> SM traffic of the streamed bank tiles: prefer them (with a column split
-    // that brings the CTA count back up) whenever that still occupies most SMs
-    int ps1 = auto_split((long long)B * RB);
-    if (RB % 2 == 0 && a->psplit <= 0) {
-      const int ps_two = auto_split((long long)B * (RB / 2));
-      if ((long long)B * (RB / 2) * ps_two >= 100) ps1 = ps_two;
-    }
-    IPSR_FORWARD(record(a->ev_corr_begin));
-    IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps1, 1, 2, nullptr,
-                                          at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
-                                          at<float>(a, w.part_second), nullptr, nullptr, nullptr, stream));
-    IPSR_FORWARD(record(a->ev_corr_end));
-    IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
-                                      ps1, at<float>(a, w.rnorm), at<float>(a, w.rscale), at<float>(a, w.rerr), xerr_max,
-                                      nonfinite, nullptr, nullptr, B, N, kAccumAllowance, tol_abs, a->ind, list2, npass2,
-                                      packed, at<void>(a, w.r_tiles), at<void>(a, w.c_tiles), C, nullptr, nullptr, nullptr,
-                                      nullptr, nullptr, stream));
-    // pass 2: the three-pass split over the ambiguous rows finalize just compacted (typically a few % of the rows)
-    const int ps2 = auto_split((long long)B * (RB >= 8 ? RB / 8 : 1));
-    IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.c_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps2, 3, 2, npass2,
-                                          at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
-                                          at<float>(a, w.part_second), at<int32_t>(a, w.part_idx2),
-                                          at<float>(a, w.part_third), nullptr, stream));
     const float tol_rel = a->tol_rel >= 0.f ? a->tol_rel : kDefaultTolRel;
-    IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
-                                      ps2, at<float>(a, w.rnorm), at<float>(a, w.rscale), nullptr, nullptr, nonfinite, list2,
-                                      npass2, B, N, tol_rel, tol_abs, a->ind, list, nrecheck, nullptr, nullptr, nullptr, C,
-                                      at<int32_t>(a, w.part_idx2), at<float>(a, w.part_third), at<int32_t>(a, w.cand2),
-                                      at<int32_t>(a, w.pair_list), npair, stream));
+    int32_t* list2 = at<int32_t>(a, w.list2);
+    // The cascade pays ~25 us of extra launches; below ~12 us of single-pass tensor time (tile MMAs per SM) the
+    // three-pass split over every row is the shorter path.
+    const bool direct = ipsr_tensor_cascade(B, C, N) == 0;
+    if (direct) {
+      const int ps = auto_split((long long)B * RB);
+      IPSR_FORWARD(record(a->ev_corr_begin));
+      IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps, 3, 2, nullptr,
+                                            at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
+                                            at<float>(a, w.part_second), at<int32_t>(a, w.part_idx2),
+                                            at<float>(a, w.part_third), nullptr, stream));
+      IPSR_FORWARD(record(a->ev_corr_end));
+      IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
+                                        ps, at<float>(a, w.rnorm), at<float>(a, w.rscale), nullptr, nullptr, nonfinite,
+                                        nullptr, nullptr, B, N, tol_rel, tol_abs, a->ind, list, nrecheck, packed, nullptr,
+                                        nullptr, C, at<int32_t>(a, w.part_idx2), at<float>(a, w.part_third),
+                                        at<int32_t>(a, w.cand2), at<int32_t>(a, w.pair_list), npair, stream));
+    } else {
+      // pass 1: hi * hi over every row.  Two row tiles per CTA halve the L2 -> SM traffic of the streamed bank tiles:
+      // prefer them (with a column split that brings the CTA count back up) whenever that still occupies most SMs
+      int ps1 = auto_split((long long)B * RB);
+      if (RB % 2 == 0 && a->psplit <= 0) {
+        const int ps_two = auto_split((long long)B * (RB / 2));
+        if ((long long)B * (RB / 2) * ps_two >= 100) ps1 = ps_two;
+      }
+      IPSR_FORWARD(record(a->ev_corr_begin));
+      IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps1, 1, 2, nullptr,
+                                            at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
+                                            at<float>(a, w.part_second), nullptr, nullptr, nullptr, stream));
+      IPSR_FORWARD(record(a->ev_corr_end));
+      IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
+                                        ps1, at<float>(a, w.rnorm), at<float>(a, w.rscale), at<float>(a, w.rerr), xerr_max,
+                                        nonfinite, nullptr, nullptr, B, N, kAccumAllowance, tol_abs, a->ind, list2, npass2,
+                                        packed, at<void>(a, w.r_tiles), at<void>(a, w.c_tiles), C, nullptr, nullptr, nullptr,
+                                        nullptr, nullptr, stream));
+      // pass 2: the three-pass split over the ambiguous rows finalize just compacted (typically a few % of the rows)
+      const int ps2 = auto_split((long long)B * (RB >= 8 ? RB / 8 : 1));
+      IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.c_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps2, 3, 2, npass2,
+                                            at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
+                                            at<float>(a, w.part_second), at<int32_t>(a, w.part_idx2),
+                                            at<float>(a, w.part_third), nullptr, stream));
+      IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
+                                        ps2, at<float>(a, w.rnorm), at<float>(a, w.rscale), nullptr, nullptr, nonfinite, list2,
+                                        npass2, B, N, tol_rel, tol_abs, a->ind, list, nrecheck, nullptr, nullptr, nullptr, C,
+                                        at<int32_t>(a, w.part_idx2), at<float>(a, w.part_third), at<int32_t>(a, w.cand2),
+                                        at<int32_t>(a, w.pair_list), npair, stream));
+    }
   } else {
     IPSR_FORWARD(ipsr_select_all_rows(B, N, list, nrecheck, packed, stream));
   }

@@ -264,8 +264,9 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
 
 // Merge the per-split triples (scores in scaled units; true score = scaled * rscale[q] > 0 scaling) and decide
 // which rows can be trusted.
-//   pass 1 (list_in == NULL): row index = q;  tol[q] = 2 (rerr[q] + rnorm[q] (1.001 xerr_max[b] + acc)) + tol_abs
-//   pass 2 (list_in != NULL): row index r < nlist_in[b] is position q = list_in[b][r];  tol[q] = tol_rel rnorm[q] + tol_abs
+//   rows: list_in == NULL: row index = q; else row index r < nlist_in[b] is position q = list_in[b][r]
+//   after the single pass (rerr != NULL):  tol[q] = 2 (rerr[q] + rnorm[q] (1.001 xerr_max[b] + tol_rel)) + tol_abs
+//   after the three-pass split (rerr == NULL):  tol[q] = tol_rel rnorm[q] + tol_abs
 // Trusted rows get ind[b,q]; the others are appended to list_out[b] (order arbitrary).  Pass 1 with c_tiles != NULL
 // also COMPACTS: the hi and lo tile rows of every appended position are copied to row `pos` of the compact tile
 // images the three-pass split reads (one warp per row, 16-byte chunks, coalesced 128-byte tile rows).
@@ -322,8 +323,8 @@ __global__ void finalize_kernel(const float* __restrict__ part_best, const int* 
     const size_t bq = (size_t)b * N + q;
     const float rn = rnorm[bq];
     float tol;
-    if (list_in) tol = fmaf(tol_rel, rn, tol_abs);
-    else tol = fmaf(2.0f, fmaf(rn, fmaf(1.001f, xerr_max[b], tol_rel), rerr[bq]), tol_abs);
+    if (rerr == nullptr) tol = fmaf(tol_rel, rn, tol_abs);                 // after the three-pass split
+    else tol = fmaf(2.0f, fmaf(rn, fmaf(1.001f, xerr_max[b], tol_rel), rerr[bq]), tol_abs);   // after the single pass
     const float rs = rscale[bq];
     const float gap = __fmul_rn(best - second, rs);
     const bool bad = (nonfinite && nonfinite[b] != 0);
@@ -340,7 +341,7 @@ __global__ void finalize_kernel(const float* __restrict__ part_best, const int* 
       pos = atomicAdd(nlist_out + b, 1);
       list_out[(size_t)b * N + pos] = q;
     }
-    if (!list_in) packed[bq] = kPackedIdentity;
+    if (packed) packed[bq] = kPackedIdentity;
   }
   if (c_tiles == nullptr) return;
   // compaction (pass 1 only; N % 32 == 0 on the tensor path, so whole warps arrive here)
@@ -453,8 +454,8 @@ extern "C" int ipsr_finalize_argmax(const float* part_best, const int32_t* part_
   using namespace ipsr;
   IPSR_REQUIRE(part_best && part_idx && part_second && rnorm && rscale && ind && list_out && nlist_out,
                IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: null pointer");
-  IPSR_REQUIRE(list_in ? (nlist_in != nullptr) : (rerr && xerr_max && packed), IPSR_ERR_INVALID_ARG,
-               "ipsr_finalize_argmax: pass 1 needs rerr / xerr_max / packed, pass 2 needs nlist_in");
+  IPSR_REQUIRE(!list_in || nlist_in, IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: list_in needs nlist_in");
+  IPSR_REQUIRE(!rerr || xerr_max, IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: the single-pass bound needs rerr and xerr_max");
   IPSR_REQUIRE(B > 0 && N > 0 && psplit >= 1 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: bad dims");
   if (c_tiles)
     IPSR_REQUIRE(r_tiles && !list_in && ipsr_tensor_path_supported(C, N), IPSR_ERR_INVALID_ARG,

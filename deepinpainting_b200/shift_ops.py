@@ -223,13 +223,15 @@ def shift_forward(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, need_grad: 
     return call.out, call.saved
 
 
-def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Optional[str] = None, backward: bool = True) -> int:
+def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Optional[str] = None, backward: bool = True,
+                      B: int = 1) -> int:
     """Number of libipsr_sm100 KERNEL launches of one forward (+ backward) -- what bench.py reports as
     gpu_launches (memsets / event records are not kernels)."""
     mode = mode or config["correlation_mode"]
     tensor = mode == "tensor" or (mode == "auto" and _lib.load().ipsr_tensor_path_supported(C, N) == 1)
     n = 1                                   # extract_normalize
-    n += 4 if tensor else 1                 # correlate_tc + finalize (+ compaction), correlate_tc + finalize | select_all_rows
+    cascade = tensor and _lib.load().ipsr_tensor_cascade(B, C, N) == 1
+    n += (4 if cascade else 2) if tensor else 1   # correlate_tc + finalize [x2 with the cascade] | select_all_rows
     n += 2                                  # correlate_fp32 + resolve_rows
     if M > 0:
         n += 2                              # blend_stage (+ routes builders in the same launch) + blend_scan

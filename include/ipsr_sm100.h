@@ -40,6 +40,10 @@ const char* ipsr_last_error_string(void);
 int ipsr_version(void);
 /* 1 when (C, N) can run on the tcgen05 path (C % 64 == 0, N % 128 == 0, N <= 65536). */
 int ipsr_tensor_path_supported(int C, int N);
+/* 1 when the tensor path of ipsr_shift_forward runs the precision cascade (single pass + three-pass split on the
+ * ambiguous rows) for this problem size, 0 when it runs the three-pass split over every row (small problems, where
+ * the cascade's extra launches cost more than the tensor time they save). */
+int ipsr_tensor_cascade(int B, int C, int N);
 
 /* ---------------------------------------------------------------------------------------------
  * Mask helpers
@@ -113,12 +117,13 @@ int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles, int B, in
 /* Merge the `psplit` partial (best, idx, second) triples per row, then decide per row:
  *   gap = (best - second) * rscale[b,q] >= tol[q]  -> ind[b,q] = idx (trusted);
  *   otherwise (or when nonfinite[b] != 0) the row is appended to list_out[b] (ind[b,q] = idx provisionally).
- * Pass 1 (list_in == NULL): rows are positions; tol[q] = 2 (rerr[q] + rnorm[q] (1.001 xerr_max[b] + tol_rel)) + tol_abs;
- *   packed[b,q] is reset for every row.  With c_tiles != NULL it also COMPACTS: the hi and lo tile rows of every
- *   appended position are copied from r_tiles to row `pos` of the compact image c_tiles (same layout) that the
- *   three-pass split then reads with row_limit = nlist_out.
- * Pass 2 (list_in != NULL): row r < nlist_in[b] is position list_in[b][r]; tol[q] = tol_rel rnorm[q] + tol_abs.
- *   With part_idx2 / part_third: an untrusted row whose THIRD-best score is outside the band has exactly two
+ * Rows: list_in == NULL: row r is position q = r; otherwise row r < nlist_in[b] is position list_in[b][r].
+ * Tolerance: rerr != NULL (after the single pass): tol[q] = 2 (rerr[q] + rnorm[q] (1.001 xerr_max[b] + tol_rel)) + tol_abs;
+ *   rerr == NULL (after the three-pass split): tol[q] = tol_rel rnorm[q] + tol_abs.
+ * packed (optional): packed[b,q] is reset for every row seen.  c_tiles (optional, list_in == NULL only): COMPACTS --
+ *   the hi and lo tile rows of every appended position are copied from r_tiles to row `pos` of the compact image
+ *   c_tiles (same layout) that the three-pass split then reads with row_limit = nlist_out.
+ * part_idx2 / part_third (optional): an untrusted row whose THIRD-best score is outside the band has exactly two
  *   candidates; it goes to pair_list[b] (cand2[b,q] = the runner-up's column) instead of list_out[b].
  * nlist_out[b] (and npair[b]) must be zero on entry. */
 int ipsr_finalize_argmax(const float* part_best, const int32_t* part_idx, const float* part_second,
