@@ -531,7 +531,7 @@ static int launch_stage(StageArgs a, cudaStream_t st) {
   }
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d / N=%d too large", a.C, a.N);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(blend_stage_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_stage smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
@@ -557,7 +557,7 @@ static int launch_scan(const float* staged, int B, int C, int M, float* y, float
   const size_t smem = 2 * ((blk_bytes + 127) & ~(size_t)127) + ((size_t)C + (size_t)T * (C + 1)) * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
@@ -622,7 +622,7 @@ extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, co
   const size_t smem = paste_smem(CT, N, M);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste: N=%d too large", N);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
@@ -671,7 +671,7 @@ extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const
   if (exc && smem_exc > smem) smem = smem_exc;
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: N=%d too large", N);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(paste_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste_fused smem attribute: %s", cudaGetErrorString(e));
     configured = smem;

@@ -248,7 +248,7 @@ extern "C" int ipsr_build_routes(const int32_t* ind, const int32_t* flag, const 
   IPSR_REQUIRE(N <= 16384, IPSR_ERR_UNSUPPORTED, "ipsr_build_routes: N=%d > 16384", N);
   const size_t smem = (size_t)(2 * N + 1) * sizeof(int);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(build_routes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "build_routes smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
@@ -267,7 +267,7 @@ extern "C" int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx
   IPSR_REQUIRE(B > 0 && N > 0 && exc_cap > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_build_exceptions: bad dims");
   const size_t smem = ((size_t)((N + 3) & ~3) + ((M + 3) & ~3) + 3 * kExcChunk) * sizeof(int);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_build_exceptions: N=%d too large", N);
-  if (smem > 48 * 1024) {
+  if (smem + 1024 > 48 * 1024) {                            // + the kernel's static shared memory
     cudaError_t e = cudaFuncSetAttribute(build_exceptions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "build_exceptions smem attribute: %s", cudaGetErrorString(e));
   }

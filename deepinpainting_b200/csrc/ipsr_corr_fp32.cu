@@ -335,7 +335,7 @@ extern "C" int ipsr_correlate_argmax_fp32(const float* x, const float* ref, cons
     // sparse row lists (tensor-mode recheck)
     const size_t smem = ((size_t)C * kSkRows + 4 * (size_t)kSkCols * kSkRows) * sizeof(float);
     IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_fp32: C=%d too large", C);
-    if (smem > 48 * 1024) {
+    if (smem + 2048 > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(corr_fp32_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_fp32_sparse smem attribute: %s", cudaGetErrorString(e));
     }

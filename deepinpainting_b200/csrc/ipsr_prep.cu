@@ -246,7 +246,7 @@ extern "C" int ipsr_extract_normalize(const float* x, const float* ref, int B, i
   const size_t smem = ((size_t)C * 33 + 2 * 8 * 32 + 32 + (size_t)(C / 8) * 32) * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_extract_normalize: C=%d too large", C);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "prep smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
@@ -268,7 +268,7 @@ extern "C" int ipsr_compact_rows(const float* ref, int B, int C, int N, const in
   const size_t smem = (size_t)C * 33 * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_compact_rows: C=%d too large", C);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
     cudaError_t e = cudaFuncSetAttribute(compact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "compact_rows smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
