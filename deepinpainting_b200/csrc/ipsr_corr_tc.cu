@@ -75,14 +75,16 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // work decomposition: blockIdx.x -> (row-tile group, b, split), row-tile group slowest: with a compacted operand
-  // (row_limit) the populated tiles are the FIRST of every image, so every CTA that has work is scheduled before
-  // the ones that only find out that they have none
+  // work decomposition: blockIdx.x -> (.., split).  With a compacted operand (row_limit) the populated tiles are the
+  // FIRST of every image: row-tile group slowest, so every CTA that has work is scheduled before the ones that
+  // only find out that they have none
   const int RBG = RB / ROWT;
   int t = blockIdx.x;
   const int split = t % prm.psplit; t /= prm.psplit;
-  const int b = t % prm.B;
-  const int rbg = t / prm.B;
+  // full operand: image slowest, so that the CTAs resident together share one image's bank tiles in L2;
+  // compacted operand: row-tile group slowest (see above)
+  const int b = prm.row_limit ? t % prm.B : t / RBG;
+  const int rbg = prm.row_limit ? t / prm.B : t % RBG;
   if (prm.row_limit && rbg * ROWT * kTileRows >= prm.row_limit[b]) return;     // compacted operand: nothing here
   const int per = (prm.blocks_total + prm.psplit - 1) / prm.psplit;
   const int blk0 = split * per;
