@@ -302,11 +302,12 @@ def run_ours(args):
     flops = 2.0 * N * N * C * B                                    # algorithmic: one N x N x C correlation per image
     achieved = flops / (corr_ms * 1e-3) / 1e12
     traffic = None                                                 # DRAM bytes per launch from the committed ncu --set full capture
+    tj_all = {}
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath) and (B, C, H) == (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"]):
         with open(tpath) as fh:
-            tj = json.load(fh)
-        traffic = next((v for k, v in tj.items() if "corr_tc" in k), None) if tensor_mode else None
+            tj_all = json.load(fh)
+        traffic = next((v for k, v in tj_all.items() if "corr_tc" in k), None) if tensor_mode else None
     roofline = {"bound": "tensor", "kernel": ("corr_tc_kernel pass 1 (tcgen05 fp16 hi*hi over every row; ambiguous rows are redone by the 3-pass split)" if cascade else "corr_tc_kernel (tcgen05 fp16, 3-pass split hi*lo + lo*hi + hi*hi over every row: small problem, ceiling = 1/3 of peak)") if tensor_mode else "corr_fp32_kernel (FFMA)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "traffic": traffic, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
@@ -378,7 +379,8 @@ def run_ours(args):
                             ("shift_bwd_kernel (e)", t_bwd, 2 * nc4)):
         gbs = byts / (ms_ * 1e-3) / 1e9
         kernels.append({"kernel": name, "bound": "hbm", "ms": ms_, "algorithmic_bytes": byts, "achieved": gbs,
-                        "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]})
+                        "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                        "traffic": next((v for k, v in tj_all.items() if name.split("_kernel")[0] in k), None)})
 
     # ---- e2e: reference-shaped module API, host pinned buffers, H2D + D2H inside the timed region ----
     Ref = collections.namedtuple("Ref", ["relu4_3"])
