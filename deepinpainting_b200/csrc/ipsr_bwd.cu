@@ -45,7 +45,7 @@ constexpr int kBwdLight = 24;            // entries a single thread sums; heavie
 constexpr int kBwdQueue = 512;
 
 template <int CT>
-__global__ void __launch_bounds__(CT >= 8 ? 512 : 1024)
+__global__ void __launch_bounds__(CT >= 8 ? 512 : 1024, CT >= 8 ? 2 : 1)
 shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per_cta, const int* __restrict__ route_ptr,
                  const int* __restrict__ route_q, const int* __restrict__ exc_start, const int* __restrict__ exc_cnt,
                  const int* __restrict__ exc_l, const float* __restrict__ exc_w, const int* __restrict__ exc_total,
