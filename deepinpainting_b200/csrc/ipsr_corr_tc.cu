@@ -45,9 +45,14 @@ struct TcParams {
   float* s_dump;
 };
 
-template <int ROWT, int PASSES, bool A_RESIDENT>
+// CL = 2: clusters of two CTAs (adjacent row-tile groups of the same image and column range) share every streamed
+// bank tile: each CTA fetches half of a stage and multicasts it into both shared memories, which halves the
+// L2 -> SM traffic (the limiter of the small and of the compacted launches).  A ring slot is refilled only after the
+// MMAs of BOTH CTAs have retired it (multicast commits onto both empty barriers).
+template <int ROWT, int PASSES, bool A_RESIDENT, int CL>
 __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcParams prm) {
   static_assert(PASSES == 1 || PASSES == 3, "one hi*hi pass or the three-pass split");
+  static_assert(CL == 1 || CL == 2, "single CTAs or CTA pairs");
   static_assert(ROWT == 1 || (A_RESIDENT && ROWT == 2), "two row tiles need the resident A operand");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // manual 1024-byte alignment (SWIZZLE_128B atoms repeat every 1024 bytes)
@@ -75,17 +80,21 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // work decomposition: blockIdx.x -> (.., split).  With a compacted operand (row_limit) the populated tiles are the
-  // FIRST of every image: row-tile group slowest, so every CTA that has work is scheduled before the ones that
-  // only find out that they have none
-  const int RBG = RB / ROWT;
-  int t = blockIdx.x;
+  // work decomposition: blockIdx.x -> (.., split[, rank in the pair]).  With a compacted operand (row_limit) the
+  // populated tiles are the FIRST of every image: row-tile group slowest, so every CTA that has work is scheduled
+  // before the ones that only find out that they have none
+  const int RBG = RB / ROWT;                 // row-tile groups per image
+  const int RBGc = RBG / CL;                 // ... per cluster
+  const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
+  int t = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int split = t % prm.psplit; t /= prm.psplit;
-  // full operand: image slowest, so that the CTAs resident together share one image's bank tiles in L2;
-  // compacted operand: row-tile group slowest (see above)
-  const int b = prm.row_limit ? t % prm.B : t / RBG;
-  const int rbg = prm.row_limit ? t / prm.B : t % RBG;
-  if (prm.row_limit && rbg * ROWT * kTileRows >= prm.row_limit[b]) return;     // compacted operand: nothing here
+  // full operand: image slowest, so that the CTAs resident together share one image's bank tiles in L2
+  const int b = prm.row_limit ? t % prm.B : t / RBGc;
+  const int rbgc = prm.row_limit ? t / prm.B : t % RBGc;
+  const int rbg = rbgc * CL + (int)crank;
+  // (a pair leaves only together: the decision looks at the pair's first tile; a CTA whose own tile lies beyond the
+  // limit multiplies stale rows, which nobody reads)
+  if (prm.row_limit && rbgc * CL * ROWT * kTileRows >= prm.row_limit[b]) return;
   const int per = (prm.blocks_total + prm.psplit - 1) / prm.psplit;
   const int blk0 = split * per;
   const int blk1 = min(prm.blocks_total, blk0 + per);
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
   if (threadIdx.x == 0) {
     for (int s = 0; s < prm.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);             // one commit per CTA of the cluster
     }
     mbar_init(a_full_bar, 1);
     for (int s = 0; s < 2; ++s) {
@@ -108,6 +117,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (CL == 2) cluster_sync_all();             // the peer's barriers exist before anything is sent to them
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
@@ -133,8 +143,17 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
             for (int hl = 0; hl < AH; ++hl, dst += kTileBytes)
               bulk_g2s(dst, prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg, KB, RB, prm.a_parts), kTileBytes, full_bar(s));
           }
-          for (int hl = 0; hl < AH; ++hl, dst += kTileBytes)
-            bulk_g2s(dst, prm.x_tiles + tile_offset_bytes(b, kb, hl, cb, KB, RB), kTileBytes, full_bar(s));
+          if (CL == 1) {
+            for (int hl = 0; hl < AH; ++hl, dst += kTileBytes)
+              bulk_g2s(dst, prm.x_tiles + tile_offset_bytes(b, kb, hl, cb, KB, RB), kTileBytes, full_bar(s));
+          } else if (AH == 2) {                  // this CTA fetches the hi (rank 0) or the lo (rank 1) tile for both
+            bulk_g2s_multicast(dst + crank * kTileBytes, prm.x_tiles + tile_offset_bytes(b, kb, (int)crank, cb, KB, RB), kTileBytes,
+                               full_bar(s), (uint16_t)0x3);
+          } else {                               // ... the upper or the lower 64 rows of the hi tile
+            bulk_g2s_multicast(dst + crank * (kTileBytes / 2),
+                               prm.x_tiles + tile_offset_bytes(b, kb, 0, cb, KB, RB) + crank * (kTileBytes / 2), kTileBytes / 2,
+                               full_bar(s), (uint16_t)0x3);
+          }
         }
       }
     }
@@ -185,7 +204,8 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
                 umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(empty_bar(s));          // ring slot reusable once these MMAs retire
+          if (CL == 2) umma_commit_multicast(empty_bar(s), (uint16_t)0x3);   // both CTAs must retire the slot
+          else umma_commit(empty_bar(s));     // ring slot reusable once these MMAs retire
         }
         umma_commit(tfull_bar(as));           // accumulators complete -> epilogue
       }
@@ -258,6 +278,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();             // nobody leaves while the peer may still write into this CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -377,7 +398,7 @@ static int tc_stage_count(size_t a_bytes, size_t stage, size_t* smem_out) {
   return stages;
 }
 
-template <int ROWT, int PASSES, bool A_RES>
+template <int ROWT, int PASSES, bool A_RES, int CL>
 static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
   constexpr int AH = (PASSES == 3) ? 2 : 1;
   const size_t a_bytes = A_RES ? (size_t)ROWT * (C / kTileK) * AH * kTileBytes : 0;
@@ -385,10 +406,29 @@ static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
   size_t smem = 0;
   prm.stages = tc_stage_count(a_bytes, stage, &smem);
   IPSR_REQUIRE(prm.stages >= 2, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: C=%d leaves %d pipeline stages", C, prm.stages);
-  cudaError_t e = cudaFuncSetAttribute(corr_tc_kernel<ROWT, PASSES, A_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
-  corr_tc_kernel<ROWT, PASSES, A_RES><<<(unsigned)ctas, 64 + 128 * ROWT, smem, st>>>(prm);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(64 + 128 * ROWT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, prm);
+  IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_correlate_argmax_tc: launch failed: %s", cudaGetErrorString(e));
   return check_launch("ipsr_correlate_argmax_tc");
+}
+
+template <int ROWT, int PASSES, bool A_RES>
+static int launch_tc_cl(const TcParams& prm, int C, long long ctas, bool pairs, cudaStream_t st) {
+  return pairs ? launch_tc<ROWT, PASSES, A_RES, 2>(prm, C, ctas, st) : launch_tc<ROWT, PASSES, A_RES, 1>(prm, C, ctas, st);
 }
 
 }  // namespace ipsr
@@ -433,15 +473,17 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   if (passes == 3) {
     const long long ctas = (long long)B * prm.RB * psplit;
     IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
-    return a_res ? launch_tc<1, 3, true>(prm, C, ctas, st) : launch_tc<1, 3, false>(prm, C, ctas, st);
+    const bool pairs = (prm.RB % 2 == 0) && s_dump == nullptr;
+    return a_res ? launch_tc_cl<1, 3, true>(prm, C, ctas, pairs, st) : launch_tc_cl<1, 3, false>(prm, C, ctas, pairs, st);
   }
   // two row tiles per CTA when the grid still fills most of the machine and both fit next to >= 4 ring stages
   const bool two = a_res && (prm.RB % 2 == 0) && (2 * a_one + 4 * (size_t)kTileBytes + 2048 <= 227 * 1024) &&
                    ((long long)B * (prm.RB / 2) * psplit >= 100) && s_dump == nullptr;
   const long long ctas = (long long)B * (two ? prm.RB / 2 : prm.RB) * psplit;
   IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
-  if (two) return launch_tc<2, 1, true>(prm, C, ctas, st);
-  return a_res ? launch_tc<1, 1, true>(prm, C, ctas, st) : launch_tc<1, 1, false>(prm, C, ctas, st);
+  const bool pairs = ((two ? prm.RB / 2 : prm.RB) % 2 == 0) && s_dump == nullptr;
+  if (two) return launch_tc_cl<2, 1, true>(prm, C, ctas, pairs, st);
+  return a_res ? launch_tc_cl<1, 1, true>(prm, C, ctas, pairs, st) : launch_tc_cl<1, 1, false>(prm, C, ctas, pairs, st);
 }
 
 extern "C" int ipsr_finalize_argmax(const float* part_best, const int32_t* part_idx, const float* part_second,
