@@ -311,8 +311,10 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": ("corr_tc_kernel pass 1 (tcgen05 fp16 hi*hi over every row; ambiguous rows are redone by the 3-pass split)" if cascade else "corr_tc_kernel (tcgen05 fp16, 3-pass split hi*lo + lo*hi + hi*hi over every row: small problem, ceiling = 1/3 of peak)") if tensor_mode else "corr_fp32_kernel (FFMA)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "traffic": traffic, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
+                "issued_passes": (1 if cascade else 3) if tensor_mode else 1,
+                "tensor_pipe_utilisation": (achieved * ((1 if cascade else 3) if tensor_mode else 1)) / pk["tf_sustained"],
                 "peak_source": pk["source"] + " bf16 dense, sustained",
-                "note": "algorithmic FLOPs = 2*N^2*C per image over the pass-1 launch (event pair recorded by the library around it)"}
+                "note": "achieved = algorithmic FLOPs (2*N^2*C per image) / time of the timed correlation launch (event pair recorded by the library around it); tensor_pipe_utilisation counts the MMA passes actually issued (3 for the split over every row that small problems run, 1 for pass 1 of the cascade)"}
 
     # ---- workload diagnostics (one eager step): rows deferred to the exact path, attention entries that survive the
     # reference's int64 truncation ("exceptions" of the backward), hub columns
