@@ -462,13 +462,17 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (correlation: tcgen05 fp16 precision cascade -- 1 pass + 3-pass split on ambiguous rows, fp32 accumulate -- with exact fp32 resolve)" if tensor_mode else "f32",
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD["name"] if (B, C, H) == (16, 256, 32) else
                        "shift layer fwd+bwd, batch %d per GPU, %dx%dx%d features, centre mask" % (B, H, H, C),
                        "batch_per_gpu": B, "global_batch": B * world, "C": C, "H": H, "W": H, "N": N, "M": M,
                        "parallelism": "batch-sharded x%d, no data-path collective" % world,
                        "mode": args.mode, "cuda_graphs": graphs is not None,
+                       "correlation": ("fp32 results; tcgen05 fp16 hi/lo split with fp32 accumulation ("
+                                       + ("precision cascade: 1 pass, 3-pass split on the ambiguous rows" if cascade
+                                          else "3-pass split over every row") + "), ties and ambiguous rows resolved in exact fp32")
+                                      if tensor_mode else "fp32 FFMA",
                        "l2": "rotating pool of %d input sets (%d MB) > 126 MB L2" % (pool, pool * bytes_per_set >> 20)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "diagnostics": diag, "kernels": kernels,
             "gpu_launches": launches_per_step * K,
