@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: min(steps, 200))")
     ap.add_argument("--cpu-images", type=int, default=0, help="images of the CPU-baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=1234, help="synthetic data seed (rank r uses seed + r)")
     return ap.parse_args()
 
 
@@ -210,7 +211,7 @@ def run_ours(args):
     mi = shift_ops.mask_index_from_flag(torch.from_numpy(flag), dev)
 
     # ---- synthetic inputs: a rotating pool larger than L2 so every step starts from HBM ----
-    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    gen = torch.Generator(device="cpu").manual_seed(args.seed + rank)
     bytes_per_set = 3 * B * C * N * 4
     pool = max(2, -(-2 * 126 * (1 << 20) // bytes_per_set) + 1)
     pool = min(pool, 16)
@@ -278,6 +279,8 @@ def run_ours(args):
     sync_all()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    if world > 1:
+        sys.stderr.write("rank %d: %.3f ms per step on the device\n" % (rank, ms / K))
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

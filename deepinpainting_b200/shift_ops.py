@@ -23,7 +23,9 @@ config = {
     "tol_rel": -1.0,              # < 0: library default (5e-5 * ||R[q]||)
     "tol_abs": -1.0,
     "psplit": 0,                  # <= 0: auto
-    "exc_cap_factor": 8,          # exception capacity = factor * N per image
+    "exc_cap_factor": 32,         # exception capacity = factor * N entries (8 bytes each) per image: signed inputs make a few
+                                  # images chaotic (tens of thousands of attention entries survive the int64 store); beyond
+                                  # the capacity the backward replays the recurrence per column (correct, ~10x slower)
 }
 
 
