@@ -24,6 +24,18 @@ class IPSR_model(nn.Module):
         self._flag_key = None
 
     def set_mask(self, mask_global, layer_to_last, threshold):
+        """Reference contract: ``mask_global`` is [1,1,S,S] and is shared by the whole batch
+        (models/IPSR_model.py:30-34, models/IPSRFunction.py:32).  Extension (BASELINE.json configs[4], free-form
+        masks per sample): a [B,1,S,S] mask gives every sample its own feature mask; the forward then runs the
+        operator sample by sample (images are independent, models/IPSRFunction.py:46)."""
+        if mask_global.dim() == 4 and mask_global.size(0) > 1:
+            per = [util.cal_feat_mask(mask_global[i:i + 1], layer_to_last, threshold).squeeze() for i in range(mask_global.size(0))]
+            self.masks = per
+            self.mask = per[0]
+            self._per_sample = [None] * len(per)
+            self._flag_key = None
+            return torch.stack(per)
+        self.masks = None
         mask = util.cal_feat_mask(mask_global, layer_to_last, threshold)
         self.mask = mask.squeeze()
         self._flag_key = None                      # a new mask invalidates the cached flag vectors
@@ -32,7 +44,34 @@ class IPSR_model(nn.Module):
     def set_ref(self, latent_ref):
         self.ref = latent_ref
 
+    def _forward_per_sample(self, input):
+        """One operator call per sample, each with its own flag vectors (cached per mask)."""
+        if len(self.masks) != input.size(0):
+            raise ValueError("%d per-sample masks for a batch of %d" % (len(self.masks), input.size(0)))
+        _, self.c, self.h, self.w = input.size()
+        if not (torch.is_tensor(self.sp_x) or torch.is_tensor(self.sp_y)):
+            self.sp_x, self.sp_y = util.cal_sps_for_Advanced_Indexing(self.h, self.w)
+        Ref = type(self.ref)
+        outs = []
+        for i, m in enumerate(self.masks):
+            key = (id(m), m._version, self.h, self.w, self.shift_sz, self.stride, self.mask_thred, input.device)
+            cached = self._per_sample[i]
+            if cached is None or cached[0] != key:
+                m_dev = m.to(input.device) if m.device != input.device else m
+                vecs = util.cal_mask_given_mask_thred(input.narrow(0, i, 1).data.squeeze(0), m_dev, self.shift_sz, self.stride,
+                                                      self.mask_thred)
+                cached = (key, vecs)
+                self._per_sample[i] = cached
+            flag, nonmask_point_idx, flatten_offsets, mask_point_idx = cached[1]
+            ref_i = Ref(*[t.narrow(0, i, 1) if torch.is_tensor(t) and t.dim() == 4 and t.size(0) == input.size(0) else t
+                          for t in self.ref]) if isinstance(self.ref, tuple) else self.ref
+            outs.append(IPSRFunction.apply(input.narrow(0, i, 1), m, ref_i, self.shift_sz, self.stride, self.triple_weight,
+                                           flag, nonmask_point_idx, mask_point_idx, flatten_offsets, self.sp_x, self.sp_y))
+        return torch.cat(outs, 0)
+
     def forward(self, input):
+        if getattr(self, "masks", None) is not None:
+            return self._forward_per_sample(input)
         _, self.c, self.h, self.w = input.size()
         # The reference recomputes the flag vectors on every forward (cal_fixed_flag never turns
         # False, IPSR_model.py:23,45,53).  They depend only on (mask, h, w, shift_sz, stride,
