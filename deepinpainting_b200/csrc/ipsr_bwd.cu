@@ -305,27 +305,14 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   if (M <= 1) nexc_s = 0;
   const size_t smem = base_smem + (size_t)ninfo * 16 + (size_t)nexc_s * 8;
   const int threads = N > 2048 ? 1024 : 512;
-  // split every image's tiles over `parts` CTAs so that the grid fills whole waves of resident CTAs
+  // Tiles per CTA: every CTA pays a fixed set-up (staging the image's index lists) and the per-image work is uneven
+  // (hub columns, long exception runs), so the grid is cut into about 1.75 CTAs per SM -- measured best on the B200 for
+  // 32x32 (B = 16) and 64x64 (B = 64) maps alike -- with at least two tiles per CTA to keep the two-stage ring busy.
   const int ntiles = C / CT;
-  int resident = (int)((227 * 1024) / (smem + 12 * 1024));
-  if (resident < 1) resident = 1;
-  if (resident > 2048 / threads) resident = 2048 / threads;
-  const int slots = 148 * resident;
-  int parts = 1;
-  double best_cost = 1e300;
-  for (int pcand = 1; pcand <= ntiles; ++pcand) {
-    const int tpc = (ntiles + pcand - 1) / pcand;
-    const int np = (ntiles + tpc - 1) / tpc;
-    const long long ctas = (long long)B * np;
-    const long long waves = (ctas + slots - 1) / slots;
-    // time ~ waves * (tiles per CTA + the fixed cost of building the column list, about one tile)
-    const double cost = (double)waves * (tpc + 1.0);
-    if (cost < best_cost * 0.9999) {
-      best_cost = cost;
-      parts = np;
-    }
-  }
-  const int tiles_per_cta = (ntiles + parts - 1) / parts;
+  int tiles_per_cta = (int)(((long long)B * ntiles + 258) / 259);
+  if (tiles_per_cta < 2) tiles_per_cta = 2;
+  if (tiles_per_cta > ntiles) tiles_per_cta = ntiles;
+  const int parts = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
   void (*kern)(const float*, int, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
                const int*, int, const int*, const int*, const float*, const float*, float, float*, int, int) = nullptr;
   switch (CT) {
