@@ -252,8 +252,10 @@ def shift_backward(grad_out: np.ndarray, attn_trunc: np.ndarray, triple_w: float
 
 
 # --------------------------------------------------------------------------------------
-# general patch size (forward only; the reference fails at IPSRFunction.py:133-134 for k != 1,
-# so only lines :54-131 define semantics) -- PARITY UNPINNED for k != 1
+# general patch size, FORWARD ONLY.  For k != 1 the reference computes the whole output (lines :46-133) and then
+# fails storing the attention for backward (:134, a LongTensor sized for k = 1); its backward (:158-163) indexes
+# with the k = 1 geometry.  The forward is pinned against the reference's own output (oracle/make_golden.py
+# run_patch_case replaces only that container; tests/golden/k*.npz); the backward is undefined and not restated.
 # --------------------------------------------------------------------------------------
 def shift_forward_patches(x: np.ndarray, ref: np.ndarray, mask2d: np.ndarray, patch_size: int, stride: int,
                           mask_thred: int = 1, dtype=np.float32):

@@ -118,6 +118,66 @@ def run_case(name, kind, B, C, H, mask_kind, triple_w=1.0, seed=0):
     print(f"{name}: M={int(m.flag.sum())} out|max|={np.abs(y.detach().numpy()).max():.3g} nnz(A_trunc)={len(vals)}")
 
 
+class _AnyStore(dict):
+    """Stands in for the reference's ``ind_lst`` LongTensor when shift_sz != 1."""
+
+    def cuda(self, *a, **k):
+        return self
+
+
+def run_patch_case(name, B, C, H, k, s, thr, mask_kind, seed):
+    """Forward for shift_sz = k / stride = s.  The unmodified reference computes the whole output and then fails
+    when it stores the attention for backward (``ind_lst[idx] = kbar.squeeze()``, IPSRFunction.py:134: the
+    LongTensor was sized for k = 1, :36).  Only that container is replaced here (a dict that accepts the store), so
+    lines :46-133 run as written and the forward output is the reference's own.  There is no backward to record:
+    the reference's backward indexes the attention with the k = 1 geometry (:158-163)."""
+    IPSR_model, _, _, F, U = _import_reference()
+    S = H * 8
+    mg = centre_mask(S) if mask_kind == "centre" else irregular_mask(S, seed + 77)
+    x, r, _ = make_inputs("P1", B, C, H, seed)
+    rec = {"ind": [], "vmax": []}
+    orig = F.MaxCoord.update_output
+
+    def spy(self, inp, sp_x, sp_y):
+        o = orig(self, inp, sp_x, sp_y)
+        rec["ind"].append(o[1].clone().numpy())
+        rec["vmax"].append(o[2].clone().numpy())
+        return o
+
+    real_long = torch.LongTensor
+
+    def long_or_store(*shape):
+        return _AnyStore() if len(shape) == 4 else real_long(*shape)
+
+    F.MaxCoord.update_output = spy
+    torch.LongTensor = long_or_store
+    try:
+        m = IPSR_model(5 / 16.0, 1, k, s, thr, 1.0)
+        fm = m.set_mask(torch.from_numpy(mg), 3, 5 / 16.0)
+        m.set_ref(collections.namedtuple("R", ["relu4_3"])(torch.from_numpy(r)))
+        y = m(torch.from_numpy(x))
+    finally:
+        torch.LongTensor = real_long
+        F.MaxCoord.update_output = orig
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        kind="P1", patch=k, stride=s, mask_thred=thr, mask_global=np.packbits(mg), mask_size=S,
+        x=x, ref=r, feat_mask=fm.numpy(), flag=m.flag.numpy(), mask_point_idx=m.mask_point_idx.numpy(),
+        out=y.detach().numpy(), ind=np.stack(rec["ind"]), vmax=np.stack(rec["vmax"]),
+    )
+    print(f"{name}: k={k} s={s} M={int(m.flag.sum())} P={len(m.flag)} out|max|={np.abs(y.detach().numpy()).max():.3g}")
+
+
+PATCH_CASES = [
+    # name, B, C, H, k, s, mask_thred, mask, seed
+    ("k3_c32_h8_irr_b1", 1, 32, 8, 3, 1, 1, "irr", 21),
+    ("k3_c16_h16_irr_b2_t5", 2, 16, 16, 3, 1, 5, "irr", 22),
+    ("k2s2_c16_h16_irr_b1", 1, 16, 16, 2, 2, 1, "irr", 23),
+    ("k4s2_c16_h12_irr_b1_t3", 1, 16, 12, 4, 2, 3, "irr", 24),
+    ("k3_c64_h16_centre_b1", 1, 64, 16, 3, 1, 1, "centre", 25),
+]
+
+
 def run_innercos(name, B, H, seed):
     _, InnerCos, InnerCos2, _, U = _import_reference()
     rng = np.random.default_rng(seed)
@@ -176,6 +236,10 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    for case in PATCH_CASES:
+        run_patch_case(*case)
+    if "--patches-only" in sys.argv:
+        sys.exit(0)
     run_masks("masks")
     run_innercos("innercos_b2_h8", 2, 8, 5)
     run_case("p1_c64_h16_centre_b1", "P1", 1, 64, 16, "centre", seed=10)

@@ -28,3 +28,12 @@ SHIFT_CASES = [
     "p1_c512_h16_centre_b1",
     "p1_c256_h32_centre_b1",
 ]
+
+# shift_sz != 1 / stride != 1: forward outputs of the reference (oracle/make_golden.py run_patch_case)
+PATCH_CASES = [
+    "k3_c32_h8_irr_b1",
+    "k3_c16_h16_irr_b2_t5",
+    "k2s2_c16_h16_irr_b1",
+    "k4s2_c16_h12_irr_b1_t3",
+    "k3_c64_h16_centre_b1",
+]
