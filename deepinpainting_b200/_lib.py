@@ -69,6 +69,12 @@ SIGNATURES = {
     "ipsr_build_routes": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "ipsr_build_exceptions": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "ipsr_shift_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _f, _p, _p]),
+    "ipsr_patch_row_len": (_i, [_i, _i]),
+    "ipsr_unfold_patches": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "ipsr_fold_patches": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "ipsr_patch_rows": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "ipsr_blend_wide": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ipsr_fold_patch_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "innercos_loss_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p]),
     "innercos_loss_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p]),
     "ipsr_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i, _i]),

@@ -21,13 +21,17 @@ class IPSRFunction(torch.autograd.Function):
                 flatten_offsets, sp_x, sp_y):
         assert input.dim() == 4, "Input Dim has to be 4"
         assert mask.dim() == 2, "Mask dimension must be 2"
-        if shift_sz != 1 or stride != 1:
-            # the reference itself cannot execute these (IPSRFunction.py:133-134 shape errors)
-            raise NotImplementedError("IPSRFunction: only shift_sz = stride = 1 is defined by the reference")
         ctx.triple_w = triple_w
         ctx.flag = flag
         ctx.flatten_offsets = flatten_offsets
         ctx.bz, c_real, ctx.h, ctx.w = input.size()
+        ctx.saved_shift = None
+        if shift_sz != 1 or stride != 1:
+            # The reference computes the output for these settings (:46-133) and then fails storing the attention
+            # for backward (:134); its backward indexes with the 1 x 1 geometry (:158-163).  Forward only.
+            mi = shift_ops.lookup_mask_index(flag, input.device)
+            output, ctx.ind_lst = shift_ops.shift_forward_patches(input.detach(), ref.relu4_3.detach(), mi, shift_sz, stride)
+            return output
         # sp_x, sp_y, nonmask_point_idx, flatten_offsets and the 2-D mask are accepted and unused,
         # as in the reference; mask_point_idx is implied by flag.
         mi = shift_ops.lookup_mask_index(flag, input.device)
@@ -39,5 +43,8 @@ class IPSRFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_output):
+        if ctx.saved_shift is None:
+            raise NotImplementedError("IPSRFunction.backward is undefined for shift_sz != 1 / stride != 1: the reference "
+                                      "fails in forward before it can save the attention (IPSRFunction.py:134)")
         grad_input = shift_ops.shift_backward(grad_output, ctx.saved_shift, ctx.triple_w)
         return grad_input, None, None, None, None, None, None, None, None, None, None, None

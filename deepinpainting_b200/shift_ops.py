@@ -264,6 +264,100 @@ def shift_forward_sharded(x, ref, mi: MaskIndex, col_begin: int, col_end: int, r
     return call.out, call.saved
 
 
+# patch rows longer than this take the wide kernels (the shared-memory tiles of the 1 x 1 kernels hold <= 1024 channels)
+PATCH_ROW_LIMIT = 1024
+
+
+def patch_grid(H: int, W: int, patch: int, stride: int):
+    """(nH, nW) patch positions (util/NonparametricShift.py:63-64)."""
+    return (H - patch) // stride + 1, (W - patch) // stride + 1
+
+
+def shift_forward_patches(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, patch: int, stride: int,
+                          mode: Optional[str] = None, col_begin: int = 0, col_end: int = 0, reduce_max=None):
+    """models/IPSRFunction.py:46-133 for shift_sz = patch, stride = stride -- FORWARD ONLY (the reference computes
+    the output and then fails at :134; its backward is undefined for these settings).  ``mi`` holds the flag
+    vectors over the nH x nW patch positions (util.cal_mask_given_mask_thred with the same patch / stride).
+    ``reduce_max`` (with ``col_begin`` / ``col_end``): bank-sharded mode, as in ``shift_forward_sharded``.
+    Returns (out [B,C,H,W], ind [B,P] int32)."""
+    x = _require_cuda(x, "input", torch.float32)
+    ref = _require_cuda(ref, "ref.relu4_3", torch.float32)
+    if x.dim() != 4:
+        raise AssertionError("Input Dim has to be 4")
+    if ref.shape != x.shape:
+        raise ValueError("ref.relu4_3 %s must have the shape of the input %s" % (tuple(ref.shape), tuple(x.shape)))
+    B, Cc, H, W = x.shape
+    k, s = int(patch), int(stride)
+    nH, nW = patch_grid(H, W, k, s)
+    if nH < 1 or nW < 1 or (nH - 1) * s + k != H or (nW - 1) * s + k != W:
+        # the reference's conv-transpose output no longer has the input's shape (IPSRFunction.py:133 raises)
+        raise RuntimeError("shift_sz=%d / stride=%d patches do not tile a %d x %d feature map" % (k, s, H, W))
+    P = nH * nW
+    if mi.flag.numel() != P:
+        raise ValueError("flag has %d entries but there are %d patch positions" % (mi.flag.numel(), P))
+    dev, st = x.device, _stream_ptr(x.device)
+    K = Cc * k * k
+    sharded = reduce_max is not None
+    out = torch.empty_like(x)
+    if K <= PATCH_ROW_LIMIT:
+        # patch maps are feature maps with K channels on the nH x nW grid: the 1 x 1 pipeline runs on them unchanged
+        Kpad = -(-K // 64) * 64 if (P % 128 == 0 and -(-K // 64) * 64 <= PATCH_ROW_LIMIT) else -(-K // 32) * 32
+        cols_x = torch.empty((B, Kpad, nH, nW), dtype=torch.float32, device=dev)
+        cols_r = torch.empty((B, Kpad, nH, nW), dtype=torch.float32, device=dev)
+        _lib.call("ipsr_unfold_patches", x.data_ptr(), B, Cc, H, W, k, s, Kpad, cols_x.data_ptr(), st)
+        _lib.call("ipsr_unfold_patches", ref.data_ptr(), B, Cc, H, W, k, s, Kpad, cols_r.data_ptr(), st)
+        if sharded:
+            cols_o, saved = shift_forward_sharded(cols_x, cols_r, mi, col_begin, col_end, reduce_max, need_grad=False, mode=mode)
+        else:
+            cols_o, saved = shift_forward(cols_x, cols_r, mi, need_grad=False, mode=mode)
+        _lib.call("ipsr_fold_patches", cols_o.data_ptr(), B, Cc, H, W, k, s, Kpad, out.data_ptr(), st)
+        return out, saved.ind
+    # wide rows: position-major patches + norms, exact fp32 correlation on the patch maps, register-resident blend
+    cols_x = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+    cols_r = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+    _lib.call("ipsr_unfold_patches", x.data_ptr(), B, Cc, H, W, k, s, K, cols_x.data_ptr(), st)
+    _lib.call("ipsr_unfold_patches", ref.data_ptr(), B, Cc, H, W, k, s, K, cols_r.data_ptr(), st)
+    rows = torch.empty((B, P, K), dtype=torch.float32, device=dev)
+    inv = torch.empty((B, P), dtype=torch.float32, device=dev)
+    _lib.call("ipsr_patch_rows", x.data_ptr(), B, Cc, H, W, k, s, rows.data_ptr(), inv.data_ptr(), st)
+    packed = torch.empty((B, P), dtype=torch.int64, device=dev)
+    rlist = torch.empty((B, P), dtype=torch.int32, device=dev)
+    nrow = torch.empty((B,), dtype=torch.int32, device=dev)
+    _lib.call("ipsr_select_all_rows", B, P, rlist.data_ptr(), nrow.data_ptr(), packed.data_ptr(), st)
+    cb, ce = (int(col_begin), int(col_end) if col_end > 0 else P) if sharded else (0, P)
+    _lib.call("ipsr_correlate_argmax_fp32", cols_x.data_ptr(), cols_r.data_ptr(), inv.data_ptr(), B, K, P, cb, ce,
+              rlist.data_ptr(), nrow.data_ptr(), (P + 63) // 64, packed.data_ptr(), st)
+    if sharded:
+        reduce_max(packed)
+    ind = torch.empty((B, P), dtype=torch.int32, device=dev)
+    vmax = torch.empty((B, P), dtype=torch.float32, device=dev)
+    _lib.call("ipsr_unpack_maxidx", packed.data_ptr(), B * P, vmax.data_ptr(), ind.data_ptr(), st)
+    M = mi.M
+    y = None
+    if M > 0:
+        y = torch.empty((B, M, K), dtype=torch.float32, device=dev)
+        wn = torch.empty((B, M), dtype=torch.float32, device=dev)
+        wo = torch.empty((B, M), dtype=torch.float32, device=dev)
+        _lib.call("ipsr_blend_wide", rows.data_ptr(), inv.data_ptr(), vmax.data_ptr(), ind.data_ptr(), mi.mask_idx.data_ptr(),
+                  B, K, P, M, y.data_ptr(), wn.data_ptr(), wo.data_ptr(), st)
+    _lib.call("ipsr_fold_patch_rows", rows.data_ptr(), _ptr(y), ind.data_ptr(), mi.rank.data_ptr(), B, Cc, H, W, k, s, M,
+              out.data_ptr(), st)
+    return out, ind
+
+
+def patch_rows(img: torch.Tensor, patch: int, stride: int):
+    """util/NonparametricShift.py:59-68: all patches of ``img`` [B,C,H,W] as rows [B, P, C*k*k] in unfold order,
+    plus 1/(||patch|| + 1e-8) [B,P] (:40)."""
+    img = _require_cuda(img, "target_img", torch.float32)
+    B, Cc, H, W = img.shape
+    nH, nW = patch_grid(H, W, patch, stride)
+    rows = torch.empty((B, nH * nW, Cc * patch * patch), dtype=torch.float32, device=img.device)
+    inv = torch.empty((B, nH * nW), dtype=torch.float32, device=img.device)
+    _lib.call("ipsr_patch_rows", img.data_ptr(), B, Cc, H, W, int(patch), int(stride), rows.data_ptr(), inv.data_ptr(),
+              _stream_ptr(img.device))
+    return rows, inv
+
+
 def shift_backward(grad_out: torch.Tensor, saved: ShiftSaved, triple_w: float) -> torch.Tensor:
     """models/IPSRFunction.py:144-178."""
     g = _require_cuda(grad_out, "grad_output", torch.float32)

@@ -264,6 +264,39 @@ int ipsr_paste_with_bookkeeping(const float* x, const float* y, const int32_t* i
                                 int32_t* exc_total, int exc_cap, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * shift_sz = k > 1 / stride = s > 1 ("patch mode"), FORWARD ONLY   (models/IPSRFunction.py:46-133,
+ * util/NonparametricShift.py:59-73).  The reference computes the whole output for these settings and then fails
+ * storing the attention for its backward (:134); its backward is undefined.
+ *
+ * A patch is a row of K = C*k*k values in unfold order kk = (c*k + dy)*k + dx; P = nH*nW patch positions,
+ * nH = (H-k)/s + 1.  K <= 1024: unfold x and ref into patch maps, run ipsr_shift_forward on them as
+ * [B, Kpad, nH, nW] feature maps, fold the result.  K > 1024: ipsr_patch_rows, the exact correlation
+ * (ipsr_correlate_argmax_fp32 on the patch maps), ipsr_blend_wide, ipsr_fold_patch_rows.
+ * ------------------------------------------------------------------------------------------- */
+int ipsr_patch_row_len(int C, int patch);
+/* cols [B][Kpad][P]: cols[b][kk][i*nW+j] = x[b][c][i*s+dy][j*s+dx]; rows K <= kk < Kpad are zero-filled
+ * (Kpad <= 0: Kpad = K). */
+int ipsr_unfold_patches(const float* x, int B, int C, int H, int W, int patch, int stride, int Kpad,
+                        float* cols, void* stream);
+/* ConvTranspose2d(P, C, k, s) with the pasted patches as input (IPSRFunction.py:131): out[b][c][Y][X] = sum of
+ * cols[b][(c,dy,dx)][(i,j)] over the patches with i*s+dy = Y, j*s+dx = X.  Needs (nH-1)*s + k == H (the reference
+ * fails at :133 otherwise). */
+int ipsr_fold_patches(const float* cols, int B, int C, int H, int W, int patch, int stride, int Kpad,
+                      float* out, void* stream);
+/* rows [B][P][K] position-major raw patches and (optional) inv_norm [B][P] = 1/(||patch||_2 + 1e-8). */
+int ipsr_patch_rows(const float* x, int B, int C, int H, int W, int patch, int stride,
+                    float* rows, float* inv_norm, void* stream);
+/* The blend recurrence (IPSRFunction.py:82-126) on rows of K <= 8192 values, one CTA per image:
+ * y [B][M][K], wn / wo [B][M] (wn[b,0] = 0, wo[b,0] = 1).  vmax [B][P] = row maxima of the correlation. */
+int ipsr_blend_wide(const float* rows, const float* inv_norm, const float* vmax, const int32_t* ind,
+                    const int32_t* mask_idx, int B, int K, int P, int M,
+                    float* y, float* wn, float* wo, void* stream);
+/* Gather + fold in one pass: the patch pasted at position q is y[b][rank[q]] when rank[q] >= 0, else
+ * rows[b][ind[b][q]]. */
+int ipsr_fold_patch_rows(const float* rows, const float* y, const int32_t* ind, const int32_t* rank,
+                         int B, int C, int H, int W, int patch, int stride, int M, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * InnerCos / InnerCos2   (models/InnerCos.py:30-36, models/InnerCos2.py:34-41)
  *   loss = mean_{b, c < c_limit, q} crit(x[b,c,q]*mask[q]*strength - target[b,c,q]);
  *   crit: 0 = squared error (MSELoss), 1 = absolute error (L1Loss).
