@@ -12,14 +12,19 @@ from ..util import util
 class _InnerCosLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, in_data, mask, target, strength, crit, c_limit):
+        # fp16 / bf16 activations (autocast host network): the loss is computed in fp32
+        ctx.in_dtype = in_data.dtype
+        in_data, target = in_data.detach().float(), target.detach().float()
         ctx.save_for_backward(in_data, mask, target)
         ctx.strength, ctx.crit, ctx.c_limit = strength, crit, c_limit
-        return shift_ops.innercos_loss(in_data.detach(), mask, target.detach(), strength, crit, c_limit)
+        return shift_ops.innercos_loss(in_data, mask, target, strength, crit, c_limit)
 
     @staticmethod
     def backward(ctx, grad_loss):
         in_data, mask, target = ctx.saved_tensors
-        gx = shift_ops.innercos_loss_grad(in_data, mask, target, grad_loss.contiguous(), ctx.strength, ctx.crit, ctx.c_limit)
+        gx = shift_ops.innercos_loss_grad(in_data, mask, target, grad_loss.float().contiguous(), ctx.strength, ctx.crit, ctx.c_limit)
+        if ctx.in_dtype != torch.float32:
+            gx = gx.to(ctx.in_dtype)
         return gx, None, None, None, None, None
 
 
