@@ -443,6 +443,7 @@ def run_ours(args):
     for i in range(EK):
         e2e_step(i)
     f1.record(s_out)                                        # last operation: the last D2H copy has landed
+    enqueue = time.perf_counter() - t0                      # host time to ENQUEUE the region (Python + launches)
     sync_all()
     wall = time.perf_counter() - t0
     te = torch.tensor([f0.elapsed_time(f1) * 1e-3], dtype=torch.float64, device=dev)
@@ -450,7 +451,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * EK / float(te.item())
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * B * C * N * 4, "d2h_bytes_per_step": 2 * B * C * N * 4,
-           "steps": EK, "wall_s": wall, "timing": "CUDA events: first H2D copy -> last D2H copy of the region, max over ranks (3 streams overlap H2D / compute / D2H)",
+           "steps": EK, "wall_s": wall, "host_enqueue_ms_per_step": enqueue / EK * 1e3, "timing": "CUDA events: first H2D copy -> last D2H copy of the region, max over ranks (3 streams overlap H2D / compute / D2H)",
            "api": "IPSR_model.forward + autograd backward, pinned host buffers"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----

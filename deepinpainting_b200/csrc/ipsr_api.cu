@@ -6,6 +6,7 @@
 // paste, and the bookkeeping the backward needs -- on one stream, without host synchronisation or
 // allocation, so the whole layer is CUDA-graph capturable.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -195,8 +196,13 @@ extern "C" int ipsr_version(void) { return 100; }
 
 extern "C" int ipsr_tensor_cascade(int B, int C, int N) {
   if (!ipsr_tensor_path_supported(C, N)) return 0;
+  // tile MMAs of one single pass; tuning knob IPSR_CASCADE_MIN_WORK (read once) moves the switch-over
+  static const long long min_work = [] {
+    const char* e = getenv("IPSR_CASCADE_MIN_WORK");
+    return e ? atoll(e) : 12000ll;
+  }();
   const long long rb = N / ipsr::kTileRows;
-  return ((long long)B * rb * rb * (C / ipsr::kTileK) >= 12000) ? 1 : 0;
+  return ((long long)B * rb * rb * (C / ipsr::kTileK) >= min_work) ? 1 : 0;
 }
 
 extern "C" size_t ipsr_workspace_bytes(int B, int C, int H, int W, int M, int mode) {

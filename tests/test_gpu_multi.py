@@ -57,6 +57,22 @@ def _worker(rank, world, port):
             torch.cuda.synchronize()
             assert torch.equal(saved_k.ind, full_saved.ind), mode
             assert torch.equal(out_k, full_out) and torch.equal(gin_k, full_gin), mode
+        # ---- patch mode (BASELINE.json configs[3]: 3 x 3 patches, bank sharded, NCCL all-reduce MAX of the keys) ----
+        # both routes: rows of C*9 <= 1024 values through the 1 x 1 pipeline on patch maps, wider rows through the
+        # wide kernels; exact mode (P = nH*nW is not a multiple of 128), column shards of any size
+        for (Bp, Cp, Hp) in ((2, 64, 16), (1, 128, 12)):
+            xp = torch.randn(Bp, Cp, Hp, Hp, generator=gen).abs().to(dev)
+            rp = (torch.relu(torch.randn(Bp, Cp, Hp, Hp, generator=gen)) * 3).to(dev)
+            feat = torch.zeros(Hp, Hp, dtype=torch.uint8, device=dev)
+            feat[4:9, 3:10] = 1
+            mip = shift_ops.build_flags(feat, 3, 1, 1)
+            P = mip.flag.numel()
+            full_out, full_ind = shift_ops.shift_forward_patches(xp, rp, mip, 3, 1, mode="exact")
+            cb, ce = shard_bank(P, world, rank, align=1)
+            out_k, ind_k = shift_ops.shift_forward_patches(xp, rp, mip, 3, 1, mode="exact", col_begin=cb, col_end=ce,
+                                                           reduce_max=allreduce_max_keys)
+            torch.cuda.synchronize()
+            assert torch.equal(ind_k, full_ind) and torch.equal(out_k, full_out), (Cp, Hp)
         dist.barrier()
     finally:
         dist.destroy_process_group()
