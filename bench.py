@@ -21,6 +21,7 @@ import argparse
 import json
 import os
 import statistics
+import subprocess
 import sys
 import threading
 import time
@@ -50,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-images", type=int, default=0, help="images of the CPU-baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1234, help="synthetic data seed (rank r uses seed + r)")
+    ap.add_argument("--no-also", action="store_true",
+                    help="skip the short configs[2] (512^2: batch 64, 64x64x256) run appended to the default line as 'also'")
     return ap.parse_args()
 
 
@@ -462,6 +465,21 @@ def run_ours(args):
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d images of the workload (B=1 each), fwd+bwd, fp32, %.1f s" % (n_img, secs)}
 
+    # ---- the metric's second size (BASELINE.json: "at 256^2/512^2"): a short run of configs[2] in a fresh process,
+    # reported next to the headline line (N = 1 only; under torchrun pass --batch 64 --size 64 instead)
+    also = None
+    if (rank == 0 and world == 1 and not args.no_also and (B, C, H) == (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"])
+            and args.mode == "auto"):
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--batch", "64", "--size", "64", "--steps", "50",
+                                  "--warmup", "5", "--no-cpu-baseline", "--e2e-steps", "20", "--no-also", "--seed", str(args.seed)],
+                                 capture_output=True, text=True, timeout=600)
+            sub = json.loads(res.stdout.strip().splitlines()[-1])
+            also = [{k: sub[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "roofline",
+                                         "e2e", "kernels", "diagnostics", "gpu_launches")}]
+        except Exception as exc:
+            sys.stderr.write("configs[2] leg failed: %s\n" % exc)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
@@ -481,6 +499,8 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "diagnostics": diag, "kernels": kernels,
             "gpu_launches": launches_per_step * K,
         }
+        if also is not None:
+            line["also"] = also
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
