@@ -34,6 +34,7 @@ class FwdArgs(C.Structure):
         ("exc_start", _p), ("exc_cnt", _p), ("exc_l", _p), ("exc_w", _p), ("exc_total", _p),
         ("nrecheck_out", _p), ("npass2_out", _p), ("ev_corr_begin", _p), ("ev_corr_end", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
+        ("mask_stride", C.c_int32), ("m_count", _p),
     ]
 
 
@@ -75,6 +76,7 @@ SIGNATURES = {
     "ipsr_patch_rows": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ipsr_blend_wide": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "ipsr_fold_patch_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "ipsr_shift_bwd_masks": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p, _p]),
     "innercos_loss_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p]),
     "innercos_loss_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p]),
     "ipsr_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i, _i]),

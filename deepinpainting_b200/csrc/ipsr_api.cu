@@ -149,6 +149,8 @@ static int validate(const ipsr_fwd_args* a, Workspace* w, int* mode_out) {
     IPSR_REQUIRE(a->M <= 1 || (a->exc_start && a->exc_cnt && a->exc_l && a->exc_w && a->exc_total && a->exc_cap > 0),
                  IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: need_grad without exception buffers");
   }
+  IPSR_REQUIRE(a->mask_stride == 0 || (a->mask_stride == N && a->m_count), IPSR_ERR_INVALID_ARG,
+               "ipsr_shift_forward: per-image masks need mask_stride == H*W and m_count (got stride %d)", a->mask_stride);
   *w = carve(a->B, a->C, N, a->M, mode);
   IPSR_REQUIRE(a->workspace && a->workspace_bytes >= w->total, IPSR_ERR_WORKSPACE,
                "ipsr_shift_forward: workspace %zu B < required %zu B", a->workspace_bytes, w->total);
@@ -163,18 +165,20 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
   const int B = a->B, C = a->C, N = a->H * a->W, M = a->M;
   const bool grad = a->need_grad != 0;
   // the route builders depend on ind only: they ride in the stage launch
-  IPSR_FORWARD(ipsr_blend_stage_with_routes(at<float>(a, w.xt), at<float>(a, w.r_masked), at<float>(a, w.inv_norm), a->ind,
-                                            a->mask_idx, a->flag, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask),
-                                            grad ? a->route_ptr : nullptr, grad ? a->route_q : nullptr, stream));
-  if (M > 0) IPSR_FORWARD(ipsr_blend_scan(at<float>(a, w.staged), B, C, M, at<float>(a, w.y), a->wn, a->wo, stream));
+  const int ms = a->mask_stride;                           // 0: one mask for the batch; N: per-image flag / mask_idx / rank rows
+  const int32_t* mcount = ms ? a->m_count : nullptr;
+  IPSR_FORWARD(blend_stage_with_routes_ex(at<float>(a, w.xt), at<float>(a, w.r_masked), at<float>(a, w.inv_norm), a->ind,
+                                          a->mask_idx, a->flag, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask),
+                                          grad ? a->route_ptr : nullptr, grad ? a->route_q : nullptr, stream, ms, mcount));
+  if (M > 0) IPSR_FORWARD(blend_scan_ex(at<float>(a, w.staged), B, C, M, at<float>(a, w.y), a->wn, a->wo, stream, mcount));
   if (grad && M > 1) {
     // the exception lists depend on wn / wo only: build them on the side stream while the paste streams x -> out
     SideStream* ss = side_stream();
     cudaStream_t st = as_stream(stream);
     if (ss && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
-      int rc = ipsr_build_exceptions(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l, a->exc_w,
-                                     a->exc_total, a->exc_cap, ss->stream);
-      const int rc2 = ipsr_paste(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream);
+      int rc = build_exceptions_ex(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l, a->exc_w,
+                                   a->exc_total, a->exc_cap, ss->stream, ms, mcount);
+      const int rc2 = paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms);
       // always join, even after an error, so that a capture in progress is not left forked
       const bool joined = cudaEventRecord(ss->join, ss->stream) == cudaSuccess && cudaStreamWaitEvent(st, ss->join, 0) == cudaSuccess;
       if (rc == IPSR_OK) rc = rc2;
@@ -182,11 +186,11 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
       return rc;
     }
     (void)cudaGetLastError();
-    return ipsr_paste_with_bookkeeping(a->x, at<float>(a, w.y), a->ind, a->rank, a->flag, a->mask_idx, a->wn, a->wo, B, C,
-                                       N, M, a->out, nullptr, nullptr, a->exc_start, a->exc_cnt, a->exc_l,
-                                       a->exc_w, a->exc_total, a->exc_cap, stream);
+    return paste_with_bookkeeping_ex(a->x, at<float>(a, w.y), a->ind, a->rank, a->flag, a->mask_idx, a->wn, a->wo, B, C,
+                                     N, M, a->out, nullptr, nullptr, a->exc_start, a->exc_cnt, a->exc_l,
+                                     a->exc_w, a->exc_total, a->exc_cap, stream, ms, mcount);
   }
-  return ipsr_paste(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream);
+  return paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms);
 }
 
 }  // namespace ipsr
@@ -246,11 +250,12 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
     IPSR_REQUIRE(ee == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: event record: %s", cudaGetErrorString(ee));
     return IPSR_OK;
   };
-  IPSR_FORWARD(ipsr_extract_normalize(a->x, a->ref, B, C, N, a->rank, M, at<float>(a, w.inv_norm), at<float>(a, w.rnorm),
-                                      at<float>(a, w.xt), at<float>(a, w.r_masked),
-                                      tensor ? at<void>(a, w.x_tiles) : nullptr, tensor ? at<void>(a, w.r_tiles) : nullptr,
-                                      nonfinite, tensor ? at<float>(a, w.rscale) : nullptr,
-                                      tensor ? at<float>(a, w.rerr) : nullptr, nullptr, tensor ? xerr_max : nullptr, stream));
+  IPSR_FORWARD(extract_normalize_ex(a->x, a->ref, B, C, N, a->rank, M, at<float>(a, w.inv_norm), at<float>(a, w.rnorm),
+                                    at<float>(a, w.xt), at<float>(a, w.r_masked),
+                                    tensor ? at<void>(a, w.x_tiles) : nullptr, tensor ? at<void>(a, w.r_tiles) : nullptr,
+                                    nonfinite, tensor ? at<float>(a, w.rscale) : nullptr,
+                                    tensor ? at<float>(a, w.rerr) : nullptr, nullptr, tensor ? xerr_max : nullptr, stream,
+                                    a->mask_stride));
   if (tensor) {
     const int RB = N / kTileRows;
     auto auto_split = [&](long long tiles) {

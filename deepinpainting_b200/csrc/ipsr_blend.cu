@@ -41,13 +41,17 @@ struct StageArgs {
   float* staged; float* vmask;
   // optional routes builders riding in the same launch (they depend on ind only): CTAs [0, n_routes)
   int n_routes; const int* flag; int* route_ptr; int* route_q;
+  int ms; const int* mcount;        // per-image masks: flag / mask_idx rows ms = N apart, mcount[b] steps (ms = 0: shared)
 };
 
 template <int T>
 __device__ __forceinline__ void
 blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt, const float* __restrict__ r_masked,
                 const float* __restrict__ inv_norm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
-                int C, int N, int M, int nblocks, float* __restrict__ staged, float* __restrict__ vmask) {
+                int C, int N, int M, int nblocks, float* __restrict__ staged, float* __restrict__ vmask,
+                int ms, const int* __restrict__ mcount) {
+  mask_idx += (size_t)b * ms;
+  const int Mc = mcount ? mcount[b] : M;                 // steps of THIS image; M stays the row stride of the batch
   constexpr int kTiles = (T / 2) * (T / 2);              // 2 x 2 output tiles
   constexpr int kSplit = 256 / kTiles;                   // channel groups (1, 4 or 16)
   const int ld = C + 4;                                  // padded row: conflict-free float4 reads across rows
@@ -69,7 +73,7 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
     const int l = l0 + r;
     float* su = Us + (size_t)r * ld;
     float* sk = Ks + (size_t)r * ld;
-    if (l >= M) {                                        // tail of the last block: inert steps
+    if (l >= Mc) {                                       // tail of the last block: inert steps
       for (int c = lane * 4; c < C; c += 128) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(su + c) = z4;
@@ -162,12 +166,13 @@ __global__ void __launch_bounds__(256) blend_stage_kernel(const StageArgs a) {
   extern __shared__ __align__(16) float stage_smem[];
   int blk = blockIdx.x;
   if (blk < a.n_routes) {
-    build_routes_cta(blk, reinterpret_cast<int*>(stage_smem), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q);
+    build_routes_cta(blk, reinterpret_cast<int*>(stage_smem), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q, a.ms,
+                     a.mcount);
     return;
   }
   blk -= a.n_routes;
   blend_stage_cta<T>(blk % a.nblocks, blk / a.nblocks, stage_smem, a.xt, a.r_masked, a.inv_norm, a.ind, a.mask_idx, a.C, a.N,
-                     a.M, a.nblocks, a.staged, a.vmask);
+                     a.M, a.nblocks, a.staged, a.vmask, a.ms, a.mcount);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -198,8 +203,9 @@ constexpr int kScanMaxCpt = 4;           // channels per thread: C <= 1024
 
 template <int T>
 __global__ void __launch_bounds__(kScanThreads)
-blend_scan_kernel(const float* __restrict__ staged, int C, int M,
-                  float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out) {
+blend_scan_kernel(const float* __restrict__ staged, int C, int Mmax,
+                  float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out,
+                  const int* __restrict__ mcount) {
   extern __shared__ __align__(128) uint8_t scan_smem[];
   __shared__ __align__(8) unsigned long long bars[2];
   __shared__ float zs[T], wn_s[T], wo_s[T];
@@ -210,12 +216,14 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
   float* ytile = ysm + C;                                                        // [T][C+1] the block's y rows, transposed on the way out
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // per-image masks: strides come from the batch maximum, the steps walked from this image's own count
+  const int M = mcount ? mcount[b] : Mmax;
   const int nblocks = (M + T - 1) / T;
-  const float* src = staged + (size_t)b * nblocks * blk_floats;
-  const int Mp = padded_steps(M);
+  const float* src = staged + (size_t)b * ((Mmax + T - 1) / T) * blk_floats;
+  const int Mp = padded_steps(Mmax);
   float* yb = y + (size_t)b * C * Mp;                    // [C][Mp]: channel-major, so that the paste reads rows
-  float* wnb = wn_out + (size_t)b * M;
-  float* wob = wo_out + (size_t)b * M;
+  float* wnb = wn_out + (size_t)b * Mmax;
+  float* wob = wo_out + (size_t)b * Mmax;
 
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
@@ -229,7 +237,7 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
     mbar_expect_tx(smem_u32(&bars[s]), blk_bytes);
     bulk_g2s(smem_u32(scan_smem) + (uint32_t)s * stage_bytes, src + (size_t)k * blk_floats, blk_bytes, smem_u32(&bars[s]));
   };
-  if (tid == 0) {
+  if (tid == 0 && nblocks > 0) {
     issue(0);
     if (nblocks > 1) issue(1);
   }
@@ -360,7 +368,7 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
     __syncthreads();                                       // ysm / ytile complete; stage s no longer read
     if (tid == 0 && k + 2 < nblocks) issue(k + 2);
   }
-  store_ytile(nblocks - 1, 0, kScanThreads / 32);          // the last block: every warp helps
+  if (nblocks > 0) store_ytile(nblocks - 1, 0, kScanThreads / 32);   // the last block: every warp helps
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,8 +381,9 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int M,
 __device__ __forceinline__ void
 paste_cta(int part, int b, int tiles_per_cta, float* psm, const float* __restrict__ x, const float* __restrict__ y,
           const int* __restrict__ ind, const int* __restrict__ rank, int C, int N, int M, int CT,
-          float* __restrict__ out) {
+          float* __restrict__ out, int ms = 0) {
   __shared__ __align__(8) unsigned long long paste_bars[2];
+  rank += (size_t)b * ms;                                      // per-image masks: rank is [B][ms]
   const int ntiles = (C + CT - 1) / CT;
   const int t0 = part * tiles_per_cta;
   const int t1 = min(ntiles, t0 + tiles_per_cta);
@@ -462,9 +471,9 @@ static int tiles_per_cta_for(int B, int ntiles, int slots) {
 // grid = (parts, B)
 __global__ void __launch_bounds__(512)
 paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ ind,
-             const int* __restrict__ rank, int C, int N, int M, int CT, int tiles_per_cta, float* __restrict__ out) {
+             const int* __restrict__ rank, int C, int N, int M, int CT, int tiles_per_cta, float* __restrict__ out, int ms) {
   extern __shared__ __align__(128) float rows[];         // [2][CT][N] + ind[N] + rank[N]
-  paste_cta(blockIdx.x, blockIdx.y, tiles_per_cta, rows, x, y, ind, rank, C, N, M, CT, out);
+  paste_cta(blockIdx.x, blockIdx.y, tiles_per_cta, rows, x, y, ind, rank, C, N, M, CT, out, ms);
 }
 
 // The paste and the two bookkeeping builders of the backward are independent once the scan is done:
@@ -476,23 +485,24 @@ struct FusedPasteArgs {
   const int* flag; const int* mask_idx; int* route_ptr; int* route_q;
   const float* wn; const float* wo; int* exc_start; int* exc_cnt; int* exc_l; float* exc_w; int* exc_total; int exc_cap;
   int n_routes, n_exc, exc_per_img;
+  int ms; const int* mcount;
 };
 
 __global__ void __launch_bounds__(512) paste_fused_kernel(const FusedPasteArgs a) {
   extern __shared__ __align__(128) float fsm[];
   int blk = blockIdx.x;
   if (blk < a.n_routes) {
-    build_routes_cta(blk, reinterpret_cast<int*>(fsm), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q);
+    build_routes_cta(blk, reinterpret_cast<int*>(fsm), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q, a.ms, a.mcount);
     return;
   }
   blk -= a.n_routes;
   if (blk < a.n_exc) {
     build_exceptions_cta(blk / a.exc_per_img, blk % a.exc_per_img, a.exc_per_img, fsm, a.ind, a.mask_idx, a.wn, a.wo, a.N, a.M,
-                         a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total, a.exc_cap);
+                         a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total, a.exc_cap, a.ms, a.mcount);
     return;
   }
   blk -= a.n_exc;
-  paste_cta(blk % a.parts, blk / a.parts, a.tiles_per_cta, fsm, a.x, a.y, a.ind, a.rank, a.C, a.N, a.M, a.CT, a.out);
+  paste_cta(blk % a.parts, blk / a.parts, a.tiles_per_cta, fsm, a.x, a.y, a.ind, a.rank, a.C, a.N, a.M, a.CT, a.out, a.ms);
 }
 
 static int paste_ct(int C, int N) {
@@ -552,7 +562,8 @@ static int dispatch_stage(const StageArgs& a, cudaStream_t st) {
 }
 
 template <int T>
-static int launch_scan(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, cudaStream_t st) {
+static int launch_scan(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, cudaStream_t st,
+                       const int32_t* mcount) {
   const size_t blk_bytes = (size_t)staged_block_floats(C) * sizeof(float);
   const size_t smem = 2 * ((blk_bytes + 127) & ~(size_t)127) + ((size_t)C + (size_t)T * (C + 1)) * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
@@ -562,7 +573,7 @@ static int launch_scan(const float* staged, int B, int C, int M, float* y, float
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  blend_scan_kernel<T><<<B, kScanThreads, smem, st>>>(staged, C, M, y, wn, wo);
+  blend_scan_kernel<T><<<B, kScanThreads, smem, st>>>(staged, C, M, y, wn, wo, mcount);
   return check_launch("ipsr_blend_scan");
 }
 }  // namespace ipsr
@@ -578,10 +589,18 @@ extern "C" int ipsr_blend_stage_with_routes(const float* xt, const float* r_mask
                                             const int32_t* ind, const int32_t* mask_idx, const int32_t* flag,
                                             int B, int C, int N, int M, float* staged, float* vmask,
                                             int32_t* route_ptr, int32_t* route_q, void* stream) {
+  return ipsr::blend_stage_with_routes_ex(xt, r_masked, inv_norm, ind, mask_idx, flag, B, C, N, M, staged, vmask, route_ptr, route_q,
+                                          stream, 0, nullptr);
+}
+
+int ipsr::blend_stage_with_routes_ex(const float* xt, const float* r_masked, const float* inv_norm,
+                                     const int32_t* ind, const int32_t* mask_idx, const int32_t* flag,
+                                     int B, int C, int N, int M, float* staged, float* vmask,
+                                     int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount) {
   using namespace ipsr;
   const bool routes = route_ptr != nullptr;
   if (M == 0) {
-    if (routes) return ipsr_build_routes(ind, flag, mask_idx, B, N, M, route_ptr, route_q, stream);
+    if (routes) return build_routes_ex(ind, flag, mask_idx, B, N, M, route_ptr, route_q, stream, ms, mcount);
     return IPSR_OK;
   }
   IPSR_REQUIRE(xt && r_masked && inv_norm && ind && mask_idx && staged, IPSR_ERR_INVALID_ARG,
@@ -595,11 +614,17 @@ extern "C" int ipsr_blend_stage_with_routes(const float* xt, const float* r_mask
   a.B = B; a.C = C; a.N = N; a.M = M; a.nblocks = 0;
   a.staged = staged; a.vmask = vmask;
   a.n_routes = routes ? B : 0; a.flag = flag; a.route_ptr = route_ptr; a.route_q = route_q;
+  a.ms = ms; a.mcount = mcount;
   return dispatch_stage(a, as_stream(stream));
 }
 
 extern "C" int ipsr_blend_scan(const float* staged, int B, int C, int M,
                                float* y, float* wn, float* wo, void* stream) {
+  return ipsr::blend_scan_ex(staged, B, C, M, y, wn, wo, stream, nullptr);
+}
+
+int ipsr::blend_scan_ex(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, void* stream,
+                        const int32_t* mcount) {
   using namespace ipsr;
   if (M == 0) return IPSR_OK;
   IPSR_REQUIRE(staged && y && wn && wo, IPSR_ERR_INVALID_ARG, "ipsr_blend_scan: null pointer");
@@ -607,14 +632,19 @@ extern "C" int ipsr_blend_scan(const float* staged, int B, int C, int M,
   IPSR_REQUIRE(C % 32 == 0 && C <= 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d must be a multiple of 32, <= 1024", C);
   cudaStream_t st = as_stream(stream);
   switch (scan_block_steps(C)) {
-    case 32: return launch_scan<32>(staged, B, C, M, y, wn, wo, st);
-    case 16: return launch_scan<16>(staged, B, C, M, y, wn, wo, st);
-    default: return launch_scan<8>(staged, B, C, M, y, wn, wo, st);
+    case 32: return launch_scan<32>(staged, B, C, M, y, wn, wo, st, mcount);
+    case 16: return launch_scan<16>(staged, B, C, M, y, wn, wo, st, mcount);
+    default: return launch_scan<8>(staged, B, C, M, y, wn, wo, st, mcount);
   }
 }
 
 extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
                           int B, int C, int N, int M, float* out, void* stream) {
+  return ipsr::paste_ex(x, y, ind, rank, B, C, N, M, out, stream, 0);
+}
+
+int ipsr::paste_ex(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
+                   int B, int C, int N, int M, float* out, void* stream, int ms) {
   using namespace ipsr;
   IPSR_REQUIRE(x && ind && rank && out && (M == 0 || y), IPSR_ERR_INVALID_ARG, "ipsr_paste: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_paste: bad dims");
@@ -630,7 +660,7 @@ extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, co
   const int threads = paste_threads(N);
   const int ntiles = (C + CT - 1) / CT;
   const int tpc = tiles_per_cta_for(B, ntiles, paste_slots(smem, threads));
-  paste_kernel<<<dim3((ntiles + tpc - 1) / tpc, B), threads, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, tpc, out);
+  paste_kernel<<<dim3((ntiles + tpc - 1) / tpc, B), threads, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, tpc, out, ms);
   return check_launch("ipsr_paste");
 }
 
@@ -640,6 +670,15 @@ extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const
                                            int32_t* route_ptr, int32_t* route_q,
                                            int32_t* exc_start, int32_t* exc_cnt, int32_t* exc_l, float* exc_w,
                                            int32_t* exc_total, int exc_cap, void* stream) {
+  return ipsr::paste_with_bookkeeping_ex(x, y, ind, rank, flag, mask_idx, wn, wo, B, C, N, M, out, route_ptr, route_q, exc_start,
+                                         exc_cnt, exc_l, exc_w, exc_total, exc_cap, stream, 0, nullptr);
+}
+
+int ipsr::paste_with_bookkeeping_ex(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
+                                    const int32_t* flag, const int32_t* mask_idx, const float* wn, const float* wo,
+                                    int B, int C, int N, int M, float* out, int32_t* route_ptr, int32_t* route_q,
+                                    int32_t* exc_start, int32_t* exc_cnt, int32_t* exc_l, float* exc_w,
+                                    int32_t* exc_total, int exc_cap, void* stream, int ms, const int32_t* mcount) {
   using namespace ipsr;
   const bool routes = route_ptr != nullptr;       // NULL: already built (ipsr_blend_stage_with_routes)
   IPSR_REQUIRE(x && ind && rank && out && (!routes || (flag && route_q)) && (M == 0 || (y && mask_idx)), IPSR_ERR_INVALID_ARG,
@@ -662,6 +701,7 @@ extern "C" int ipsr_paste_with_bookkeeping(const float* x, const float* y, const
   a.flag = flag; a.mask_idx = mask_idx; a.route_ptr = route_ptr; a.route_q = route_q;
   a.wn = wn; a.wo = wo; a.exc_start = exc_start; a.exc_cnt = exc_cnt; a.exc_l = exc_l; a.exc_w = exc_w;
   a.exc_total = exc_total; a.exc_cap = exc_cap;
+  a.ms = ms; a.mcount = mcount;
   a.n_routes = routes ? B : 0;
   a.exc_per_img = exc ? exc_parts(M) : 0;
   a.n_exc = B * a.exc_per_img;

@@ -13,7 +13,12 @@ namespace ipsr {
 // one CTA (any multiple of 32 threads up to 1024) per image; rsm: (2N+1) ints of shared memory
 __device__ __forceinline__ void
 build_routes_cta(int b, int* rsm, const int* __restrict__ ind, const int* __restrict__ flag, const int* __restrict__ mask_idx,
-                 int N, int M, int* __restrict__ route_ptr, int* __restrict__ route_q) {
+                 int N, int M, int* __restrict__ route_ptr, int* __restrict__ route_q,
+                 int ms = 0, const int* __restrict__ mcount = nullptr) {
+  // per-image masks: flag / mask_idx are [B][ms] (ms = N), mcount[b] masked positions; ms = 0: one mask for the batch
+  flag += (size_t)b * ms;
+  mask_idx += (size_t)b * ms;
+  if (mcount) M = mcount[b];
   int* cursor = rsm;            // [N+1] counts -> exclusive offsets -> running cursors
   int* key = rsm + (N + 1);     // [N]   p = ind[q] for routed q, -1 otherwise
   __shared__ int warp_tot[32];
@@ -150,16 +155,20 @@ __device__ __forceinline__ void
 build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                      const float* __restrict__ wn, const float* __restrict__ wo, int N, int M,
                      int* __restrict__ exc_start, int* __restrict__ exc_cnt, int* __restrict__ exc_l,
-                     float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap) {
+                     float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap,
+                     int ms = 0, const int* __restrict__ mcount = nullptr) {
   int* first = reinterpret_cast<int*>(fsm);                 // [N] first masked step whose match is p, or INT_MAX
   int* owners = first + ((N + 3) & ~3);                     // [M] compact list of this part's owner steps
   float* s_wn = reinterpret_cast<float*>(owners + ((M + 3) & ~3));
+  const int Mstride = M;                                    // rows of wn / wo are M (the batch maximum) apart
+  mask_idx += (size_t)b * ms;                               // per-image masks (see build_routes_cta)
+  if (mcount) M = mcount[b];
   float* s_wo = s_wn + kExcChunk;
   int* s_p = reinterpret_cast<int*>(s_wo + kExcChunk);
   __shared__ int nonfinite_w, nown_s;
   const int* ind_b = ind + (size_t)b * N;
-  const float* wnb = wn + (size_t)b * M;
-  const float* wob = wo + (size_t)b * M;
+  const float* wnb = wn + (size_t)b * Mstride;
+  const float* wob = wo + (size_t)b * Mstride;
   for (int p = threadIdx.x; p < N; p += blockDim.x) first[p] = 0x7FFFFFFF;
   if (threadIdx.x == 0) {
     nonfinite_w = 0;

@@ -12,19 +12,19 @@ namespace ipsr {
 
 __global__ void __launch_bounds__(256)
 build_routes_kernel(const int* __restrict__ ind, const int* __restrict__ flag, const int* __restrict__ mask_idx,
-                    int N, int M, int* __restrict__ route_ptr, int* __restrict__ route_q) {
+                    int N, int M, int* __restrict__ route_ptr, int* __restrict__ route_q, int ms, const int* __restrict__ mcount) {
   extern __shared__ int rsm[];
-  build_routes_cta(blockIdx.x, rsm, ind, flag, mask_idx, N, M, route_ptr, route_q);
+  build_routes_cta(blockIdx.x, rsm, ind, flag, mask_idx, N, M, route_ptr, route_q, ms, mcount);
 }
 
 __global__ void __launch_bounds__(kExcThreads)
 build_exceptions_kernel(const int* __restrict__ ind, const int* __restrict__ mask_idx, const float* __restrict__ wn,
                         const float* __restrict__ wo, int N, int M, int* __restrict__ exc_start, int* __restrict__ exc_cnt,
                         int* __restrict__ exc_l, float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap,
-                        int nparts) {
+                        int nparts, int ms, const int* __restrict__ mcount) {
   extern __shared__ __align__(16) int esm[];               // [N] + [M] + 3*kExcChunk words
   build_exceptions_cta(blockIdx.x / nparts, blockIdx.x % nparts, nparts, esm, ind, mask_idx, wn, wo, N, M, exc_start,
-                       exc_cnt, exc_l, exc_w, exc_total, exc_cap);
+                       exc_cnt, exc_l, exc_w, exc_total, exc_cap, ms, mcount);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -51,13 +51,16 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
                  const int* __restrict__ exc_l, const float* __restrict__ exc_w, const int* __restrict__ exc_total,
                  int exc_cap, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                  const float* __restrict__ wn, const float* __restrict__ wo, float triple_w, float* __restrict__ gin,
-                 int ninfo, int nexc_s) {
+                 int ninfo, int nexc_s, int ms, const int* __restrict__ mcount) {
   extern __shared__ __align__(128) float bwd_smem[];      // rows[2][CT*N] | spec[N] | info[N] int4 | rq[N] | el[E] | ew[E]
   __shared__ int heavy[kBwdQueue];
   __shared__ int4 heavy_info[kBwdQueue];
   __shared__ int nheavy, nspec_s;
   __shared__ __align__(8) unsigned long long bars[2];
   const int b = blockIdx.y;
+  // per-image masks: mask_idx is [B][ms], mcount[b] steps; M stays the row stride of wn / wo
+  const int Mc = mcount ? mcount[b] : M;
+  if (mask_idx) mask_idx += (size_t)b * ms;
   const int ntiles = C / CT;
   const int t0 = blockIdx.x * tiles_per_cta;
   const int t1 = min(ntiles, t0 + tiles_per_cta);
@@ -190,7 +193,7 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
       }
       if (overflow) {                                        // rare, slow, bit-faithful replay of the recurrence
         float e = (ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
-        for (int l = 1; l < M; ++l) {
+        for (int l = 1; l < Mc; ++l) {
           const int ql = mask_idx[l];
           e = __fmul_rn(e, wn[(size_t)b * M + l]);
           if (ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, wo[(size_t)b * M + l]);
@@ -242,6 +245,11 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
 
 extern "C" int ipsr_build_routes(const int32_t* ind, const int32_t* flag, const int32_t* mask_idx,
                                  int B, int N, int M, int32_t* route_ptr, int32_t* route_q, void* stream) {
+  return ipsr::build_routes_ex(ind, flag, mask_idx, B, N, M, route_ptr, route_q, stream, 0, nullptr);
+}
+
+int ipsr::build_routes_ex(const int32_t* ind, const int32_t* flag, const int32_t* mask_idx, int B, int N, int M,
+                          int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount) {
   using namespace ipsr;
   IPSR_REQUIRE(ind && flag && route_ptr && route_q && (M == 0 || mask_idx), IPSR_ERR_INVALID_ARG, "ipsr_build_routes: null pointer");
   IPSR_REQUIRE(B > 0 && N > 0, IPSR_ERR_INVALID_ARG, "ipsr_build_routes: bad dims");
@@ -253,13 +261,20 @@ extern "C" int ipsr_build_routes(const int32_t* ind, const int32_t* flag, const 
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "build_routes smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  build_routes_kernel<<<B, 256, smem, as_stream(stream)>>>(ind, flag, mask_idx, N, M, route_ptr, route_q);
+  build_routes_kernel<<<B, 256, smem, as_stream(stream)>>>(ind, flag, mask_idx, N, M, route_ptr, route_q, ms, mcount);
   return check_launch("ipsr_build_routes");
 }
 
 extern "C" int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
                                      int B, int N, int M, int32_t* exc_start, int32_t* exc_cnt,
                                      int32_t* exc_l, float* exc_w, int32_t* exc_total, int exc_cap, void* stream) {
+  return ipsr::build_exceptions_ex(ind, mask_idx, wn, wo, B, N, M, exc_start, exc_cnt, exc_l, exc_w, exc_total, exc_cap, stream, 0,
+                                   nullptr);
+}
+
+int ipsr::build_exceptions_ex(const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo, int B, int N, int M,
+                              int32_t* exc_start, int32_t* exc_cnt, int32_t* exc_l, float* exc_w, int32_t* exc_total,
+                              int exc_cap, void* stream, int ms, const int32_t* mcount) {
   using namespace ipsr;
   if (M <= 1) return IPSR_OK;                               // rows l >= 1 do not exist
   IPSR_REQUIRE(ind && mask_idx && wn && wo && exc_start && exc_cnt && exc_l && exc_w && exc_total, IPSR_ERR_INVALID_ARG,
@@ -273,7 +288,7 @@ extern "C" int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx
   }
   const int nparts = exc_parts(M);
   build_exceptions_kernel<<<B * nparts, kExcThreads, smem, as_stream(stream)>>>(ind, mask_idx, wn, wo, N, M, exc_start, exc_cnt,
-                                                                               exc_l, exc_w, exc_total, exc_cap, nparts);
+                                                                               exc_l, exc_w, exc_total, exc_cap, nparts, ms, mcount);
   return check_launch("ipsr_build_exceptions");
 }
 
@@ -283,7 +298,19 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
                               const int32_t* exc_total, int exc_cap,
                               const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
                               float triple_w, float* gin, void* stream) {
+  return ipsr_shift_bwd_masks(g, B, C, N, M, route_ptr, route_q, exc_start, exc_cnt, exc_l, exc_w, exc_total, exc_cap, ind, mask_idx,
+                              wn, wo, triple_w, gin, 0, nullptr, stream);
+}
+
+extern "C" int ipsr_shift_bwd_masks(const float* g, int B, int C, int N, int M,
+                                    const int32_t* route_ptr, const int32_t* route_q,
+                                    const int32_t* exc_start, const int32_t* exc_cnt, const int32_t* exc_l, const float* exc_w,
+                                    const int32_t* exc_total, int exc_cap,
+                                    const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
+                                    float triple_w, float* gin, int mask_stride, const int32_t* m_count, void* stream) {
   using namespace ipsr;
+  IPSR_REQUIRE(mask_stride == 0 || (mask_stride == N && m_count), IPSR_ERR_INVALID_ARG,
+               "ipsr_shift_bwd_masks: per-image masks need mask_stride == N and m_count");
   IPSR_REQUIRE(g && gin && route_ptr && route_q, IPSR_ERR_INVALID_ARG, "ipsr_shift_bwd: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_shift_bwd: bad dims");
   if (M > 1)
@@ -314,7 +341,7 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   if (tiles_per_cta > ntiles) tiles_per_cta = ntiles;
   const int parts = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
   void (*kern)(const float*, int, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
-               const int*, int, const int*, const int*, const float*, const float*, float, float*, int, int) = nullptr;
+               const int*, int, const int*, const int*, const float*, const float*, float, float*, int, int, int, const int*) = nullptr;
   switch (CT) {
     case 8: kern = shift_bwd_kernel<8>; break;
     case 4: kern = shift_bwd_kernel<4>; break;
@@ -327,6 +354,6 @@ extern "C" int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
   }
   kern<<<dim3(parts, B), threads, smem, as_stream(stream)>>>(g, C, N, M, tiles_per_cta, route_ptr, route_q, exc_start, exc_cnt,
                                                             exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn, wo, triple_w,
-                                                            gin, ninfo, nexc_s);
+                                                            gin, ninfo, nexc_s, mask_stride, m_count);
   return check_launch("ipsr_shift_bwd");
 }

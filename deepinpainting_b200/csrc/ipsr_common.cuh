@@ -33,6 +33,30 @@ int check_launch(const char* what);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Launchers with PER-IMAGE masks (extension of the reference's one mask per batch): flag / mask_idx / rank are
+// [B][ms] (ms = N) and mcount[b] is the number of masked positions of image b, M the batch maximum (the row stride of
+// every [B][M] buffer).  ms = 0, mcount = NULL: the shared-mask behaviour of the C entry points of the same name.
+int extract_normalize_ex(const float* x, const float* ref, int B, int C, int N, const int32_t* rank_i32, int M,
+                         float* inv_norm, float* rnorm, float* xt, float* r_masked, void* x_tiles, void* r_tiles,
+                         int32_t* nonfinite, float* rscale, float* rerr, float* xerr, float* xerr_max, void* stream, int ms);
+int blend_stage_with_routes_ex(const float* xt, const float* r_masked, const float* inv_norm, const int32_t* ind,
+                               const int32_t* mask_idx, const int32_t* flag, int B, int C, int N, int M, float* staged,
+                               float* vmask, int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount);
+int blend_scan_ex(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, void* stream,
+                  const int32_t* mcount);
+int paste_ex(const float* x, const float* y, const int32_t* ind, const int32_t* rank, int B, int C, int N, int M,
+             float* out, void* stream, int ms);
+int paste_with_bookkeeping_ex(const float* x, const float* y, const int32_t* ind, const int32_t* rank, const int32_t* flag,
+                              const int32_t* mask_idx, const float* wn, const float* wo, int B, int C, int N, int M,
+                              float* out, int32_t* route_ptr, int32_t* route_q, int32_t* exc_start, int32_t* exc_cnt,
+                              int32_t* exc_l, float* exc_w, int32_t* exc_total, int exc_cap, void* stream, int ms,
+                              const int32_t* mcount);
+int build_routes_ex(const int32_t* ind, const int32_t* flag, const int32_t* mask_idx, int B, int N, int M,
+                    int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount);
+int build_exceptions_ex(const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo, int B, int N, int M,
+                        int32_t* exc_start, int32_t* exc_cnt, int32_t* exc_l, float* exc_w, int32_t* exc_total,
+                        int exc_cap, void* stream, int ms, const int32_t* mcount);
+
 // ---------------------------------------------------------------------------------------------
 // tile-image geometry of the fp16 hi/lo operands (written by prep, read by the tcgen05 GEMM)
 //   [B][KB = C/64][2 (hi, lo)][RB = N/128][128 rows x 128 bytes, 128B swizzle]

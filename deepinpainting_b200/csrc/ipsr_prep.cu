@@ -67,7 +67,7 @@ prep_kernel(const float* __restrict__ x, const float* __restrict__ ref, int C, i
             float* __restrict__ inv_norm, float* __restrict__ rnorm, float* __restrict__ xt,
             float* __restrict__ r_masked, uint8_t* __restrict__ x_tiles, uint8_t* __restrict__ r_tiles,
             int* __restrict__ nonfinite, float* __restrict__ rscale, float* __restrict__ rerr,
-            float* __restrict__ xerr, int* __restrict__ xerr_max) {
+            float* __restrict__ xerr, int* __restrict__ xerr_max, int ms) {
   extern __shared__ float smem[];
   float* tile = smem;                      // [C][33]
   float* part = smem + (size_t)C * 33;     // [8][32] sums of squares, then [8][32] maxima
@@ -76,6 +76,7 @@ prep_kernel(const float* __restrict__ x, const float* __restrict__ ref, int C, i
 
   const int is_ref = blockIdx.z;
   const int b = blockIdx.y;
+  if (rank) rank += (size_t)b * ms;                  // per-image masks: rank is [B][ms]
   const int p0 = blockIdx.x * kPrepPos;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* src = (is_ref ? ref : x) + (size_t)b * C * N;
@@ -232,6 +233,14 @@ extern "C" int ipsr_extract_normalize(const float* x, const float* ref, int B, i
                                       float* inv_norm, float* rnorm, float* xt, float* r_masked,
                                       void* x_tiles, void* r_tiles, int32_t* nonfinite,
                                       float* rscale, float* rerr, float* xerr, float* xerr_max, void* stream) {
+  return ipsr::extract_normalize_ex(x, ref, B, C, N, rank_i32, M, inv_norm, rnorm, xt, r_masked, x_tiles, r_tiles, nonfinite, rscale,
+                                    rerr, xerr, xerr_max, stream, 0);
+}
+
+int ipsr::extract_normalize_ex(const float* x, const float* ref, int B, int C, int N, const int32_t* rank_i32, int M,
+                               float* inv_norm, float* rnorm, float* xt, float* r_masked, void* x_tiles, void* r_tiles,
+                               int32_t* nonfinite, float* rscale, float* rerr, float* xerr, float* xerr_max, void* stream,
+                               int ms) {
   using namespace ipsr;
   IPSR_REQUIRE(x && ref && inv_norm, IPSR_ERR_INVALID_ARG, "ipsr_extract_normalize: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_extract_normalize: bad dims B=%d C=%d N=%d", B, C, N);
@@ -255,7 +264,7 @@ extern "C" int ipsr_extract_normalize(const float* x, const float* ref, int B, i
   prep_kernel<<<grid, kPrepThreads, smem, as_stream(stream)>>>(
       x, ref, C, N, rank_i32, M, inv_norm, rnorm, xt, (M > 0 ? r_masked : nullptr),
       reinterpret_cast<uint8_t*>(x_tiles), reinterpret_cast<uint8_t*>(r_tiles), nonfinite, rscale, rerr, xerr,
-      reinterpret_cast<int*>(xerr_max));
+      reinterpret_cast<int*>(xerr_max), ms);
   return check_launch("ipsr_extract_normalize");
 }
 

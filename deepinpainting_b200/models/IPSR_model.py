@@ -5,6 +5,7 @@ and calls IPSRFunction.  It owns no parameters or buffers, so state_dicts are un
 import torch
 import torch.nn as nn
 
+from .. import shift_ops
 from ..util import util
 from .IPSRFunction import IPSRFunction
 
@@ -26,8 +27,9 @@ class IPSR_model(nn.Module):
     def set_mask(self, mask_global, layer_to_last, threshold):
         """Reference contract: ``mask_global`` is [1,1,S,S] and is shared by the whole batch
         (models/IPSR_model.py:30-34, models/IPSRFunction.py:32).  Extension (BASELINE.json configs[4], free-form
-        masks per sample): a [B,1,S,S] mask gives every sample its own feature mask; the forward then runs the
-        operator sample by sample (images are independent, models/IPSRFunction.py:46)."""
+        masks per sample): a [B,1,S,S] mask gives every sample its own feature mask; the forward is still ONE batched
+        operator call -- every kernel indexes its image's own flag / index rows (images are independent,
+        models/IPSRFunction.py:46)."""
         if mask_global.dim() == 4 and mask_global.size(0) > 1:
             per = [util.cal_feat_mask(mask_global[i:i + 1], layer_to_last, threshold).squeeze() for i in range(mask_global.size(0))]
             self.masks = per
@@ -45,29 +47,31 @@ class IPSR_model(nn.Module):
         self.ref = latent_ref
 
     def _forward_per_sample(self, input):
-        """One operator call per sample, each with its own flag vectors (cached per mask)."""
+        """One batched operator call with a flag row per sample (flag vectors cached per mask)."""
         if len(self.masks) != input.size(0):
             raise ValueError("%d per-sample masks for a batch of %d" % (len(self.masks), input.size(0)))
         _, self.c, self.h, self.w = input.size()
         if not (torch.is_tensor(self.sp_x) or torch.is_tensor(self.sp_y)):
             self.sp_x, self.sp_y = util.cal_sps_for_Advanced_Indexing(self.h, self.w)
-        Ref = type(self.ref)
-        outs = []
-        for i, m in enumerate(self.masks):
-            key = (id(m), m._version, self.h, self.w, self.shift_sz, self.stride, self.mask_thred, input.device)
-            cached = self._per_sample[i]
-            if cached is None or cached[0] != key:
+        key = tuple((id(m), m._version) for m in self.masks) + (self.h, self.w, self.shift_sz, self.stride, self.mask_thred,
+                                                                 input.device)
+        if key != self._flag_key:
+            per = []
+            for i, m in enumerate(self.masks):
                 m_dev = m.to(input.device) if m.device != input.device else m
-                vecs = util.cal_mask_given_mask_thred(input.narrow(0, i, 1).data.squeeze(0), m_dev, self.shift_sz, self.stride,
-                                                      self.mask_thred)
-                cached = (key, vecs)
-                self._per_sample[i] = cached
-            flag, nonmask_point_idx, flatten_offsets, mask_point_idx = cached[1]
-            ref_i = Ref(*[t.narrow(0, i, 1) if torch.is_tensor(t) and t.dim() == 4 and t.size(0) == input.size(0) else t
-                          for t in self.ref]) if isinstance(self.ref, tuple) else self.ref
-            outs.append(IPSRFunction.apply(input.narrow(0, i, 1), m, ref_i, self.shift_sz, self.stride, self.triple_weight,
-                                           flag, nonmask_point_idx, mask_point_idx, flatten_offsets, self.sp_x, self.sp_y))
-        return torch.cat(outs, 0)
+                per.append(util.cal_mask_given_mask_thred(input.narrow(0, i, 1).data.squeeze(0), m_dev, self.shift_sz, self.stride,
+                                                          self.mask_thred))
+            self._per_sample = per
+            # the reference's vectors, one row per sample; mask_point_idx rows are ragged, so it stays a list
+            self.flag = torch.stack([v[0] for v in per])
+            self.nonmask_point_idx = per[0][1]
+            self.flatten_offsets = torch.stack([v[2] for v in per])
+            self.mask_point_idx = [v[3] for v in per]
+            shift_ops.register_mask_index(self.flag, shift_ops.stack_mask_indices(
+                shift_ops.lookup_mask_index(v[0], input.device) for v in per))
+            self._flag_key = key
+        return IPSRFunction.apply(input, self.masks[0], self.ref, self.shift_sz, self.stride, self.triple_weight, self.flag,
+                                  self.nonmask_point_idx, self.mask_point_idx, self.flatten_offsets, self.sp_x, self.sp_y)
 
     def forward(self, input):
         if getattr(self, "masks", None) is not None:

@@ -73,6 +73,13 @@ class MaskIndex:
     M: int
     nH: int
     nW: int
+    # per-image masks (extension of the reference's one mask per batch): flag / mask_idx / rank are [B, N],
+    # m_count [B] holds the masked positions per image and M their maximum
+    m_count: Optional[torch.Tensor] = None
+
+    @property
+    def batched(self) -> bool:
+        return self.m_count is not None
 
 
 def build_flags(feat: torch.Tensor, patch: int, stride: int, mask_thred: int) -> MaskIndex:
@@ -91,6 +98,24 @@ def build_flags(feat: torch.Tensor, patch: int, stride: int, mask_thred: int) ->
               midx.data_ptr(), rank.data_ptr(), count.data_ptr(), _stream_ptr(dev))
     M = int(count.item())            # one host sync per NEW mask, never per forward
     return MaskIndex(flag=flag, mask_idx=midx[:M].contiguous(), rank=rank, M=M, nH=nH, nW=nW)
+
+
+def stack_mask_indices(items) -> MaskIndex:
+    """One MaskIndex for a batch whose images have their OWN masks: rows of flag / mask_idx / rank per image."""
+    items = list(items)
+    N = items[0].flag.numel()
+    dev = items[0].flag.device
+    if any(mi.flag.numel() != N or mi.batched for mi in items):
+        raise ValueError("per-image masks must share the feature-map size")
+    B = len(items)
+    midx = torch.zeros((B, N), dtype=torch.int32, device=dev)
+    for b, mi in enumerate(items):
+        if mi.M:
+            midx[b, :mi.M] = mi.mask_idx
+    return MaskIndex(flag=torch.stack([mi.flag for mi in items]).contiguous(), mask_idx=midx,
+                     rank=torch.stack([mi.rank for mi in items]).contiguous(), M=max(mi.M for mi in items),
+                     nH=items[0].nH, nW=items[0].nW,
+                     m_count=torch.tensor([mi.M for mi in items], dtype=torch.int32, device=dev))
 
 
 _mask_registry = {}
@@ -115,7 +140,9 @@ def lookup_mask_index(flag: torch.Tensor, device) -> MaskIndex:
 
 def mask_index_from_flag(flag: torch.Tensor, device) -> MaskIndex:
     """Device vectors from a reference-style ``flag`` vector (any integer dtype, any device):
-    the flag is its own 1 x N feature mask with 1 x 1 patches."""
+    the flag is its own 1 x N feature mask with 1 x 1 patches.  A 2-D ``flag`` [B, N] holds one mask per image."""
+    if flag.dim() == 2:
+        return stack_mask_indices(mask_index_from_flag(row, device) for row in flag)
     f8 = (flag.to(device=device) != 0).to(torch.uint8).reshape(1, -1).contiguous()
     return build_flags(f8, 1, 1, 1)
 
@@ -144,6 +171,7 @@ class ShiftSaved:
     exc_cap: int = 0
     nrecheck: Optional[torch.Tensor] = None
     npass2: Optional[torch.Tensor] = None
+    m_count: Optional[torch.Tensor] = None      # per-image masks: mask_idx is [B, N], m_count [B]
 
 
 class _Call:
@@ -155,14 +183,17 @@ class _Call:
         N = H * W
         dev = x.device
         M = mi.M
-        if mi.flag.numel() != N:
+        if mi.batched:
+            if tuple(mi.flag.shape) != (B, N):
+                raise ValueError("per-image flags are %s but the batch is %d images of %d positions" % (tuple(mi.flag.shape), B, N))
+        elif mi.flag.numel() != N:
             raise ValueError("flag has %d entries but the feature map has %d positions" % (mi.flag.numel(), N))
         self.out = torch.empty_like(x)
         self.saved = ShiftSaved(B=B, C=Cc, H=H, W=W, M=M,
                                 ind=torch.empty((B, N), dtype=torch.int32, device=dev),
                                 wn=torch.empty((B, max(M, 1)), dtype=torch.float32, device=dev),
                                 wo=torch.empty((B, max(M, 1)), dtype=torch.float32, device=dev),
-                                mask_idx=mi.mask_idx)
+                                mask_idx=mi.mask_idx, m_count=mi.m_count)
         s = self.saved
         if need_grad:
             s.route_ptr = torch.empty((B, N + 1), dtype=torch.int32, device=dev)
@@ -198,6 +229,7 @@ class _Call:
         if events is not None:                       # (begin, end) torch.cuda.Event pair, already materialised
             a.ev_corr_begin, a.ev_corr_end = events[0].cuda_event, events[1].cuda_event
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), nbytes
+        a.mask_stride, a.m_count = (N, mi.m_count.data_ptr()) if mi.batched else (0, None)
         self.args = a
         self.keep = (x, ref, mi)
         self.device = dev
@@ -293,6 +325,8 @@ def shift_forward_patches(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, pat
         # the reference's conv-transpose output no longer has the input's shape (IPSRFunction.py:133 raises)
         raise RuntimeError("shift_sz=%d / stride=%d patches do not tile a %d x %d feature map" % (k, s, H, W))
     P = nH * nW
+    if mi.batched:
+        raise NotImplementedError("per-image masks are implemented for shift_sz = stride = 1 only")
     if mi.flag.numel() != P:
         raise ValueError("flag has %d entries but there are %d patch positions" % (mi.flag.numel(), P))
     dev, st = x.device, _stream_ptr(x.device)
@@ -366,10 +400,10 @@ def shift_backward(grad_out: torch.Tensor, saved: ShiftSaved, triple_w: float) -
         raise RuntimeError("forward was run with need_grad=False: nothing saved for backward")
     gin = torch.empty_like(g)
     N = s.H * s.W
-    _lib.call("ipsr_shift_bwd", g.data_ptr(), s.B, s.C, N, s.M, s.route_ptr.data_ptr(), s.route_q.data_ptr(),
+    _lib.call("ipsr_shift_bwd_masks", g.data_ptr(), s.B, s.C, N, s.M, s.route_ptr.data_ptr(), s.route_q.data_ptr(),
               _ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l), _ptr(s.exc_w), _ptr(s.exc_total), s.exc_cap,
               s.ind.data_ptr(), _ptr(s.mask_idx) if s.M else None, s.wn.data_ptr(), s.wo.data_ptr(),
-              float(triple_w), gin.data_ptr(), _stream_ptr(g.device))
+              float(triple_w), gin.data_ptr(), N if s.m_count is not None else 0, _ptr(s.m_count), _stream_ptr(g.device))
     return gin
 
 

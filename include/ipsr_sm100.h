@@ -253,6 +253,15 @@ int ipsr_shift_bwd(const float* g, int B, int C, int N, int M,
                    const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
                    float triple_w, float* gin, void* stream);
 
+/* ipsr_shift_bwd with per-image masks (see ipsr_fwd_args.mask_stride): mask_idx is [B][mask_stride], m_count [B];
+ * mask_stride = 0, m_count = NULL is ipsr_shift_bwd. */
+int ipsr_shift_bwd_masks(const float* g, int B, int C, int N, int M,
+                         const int32_t* route_ptr, const int32_t* route_q,
+                         const int32_t* exc_start, const int32_t* exc_cnt, const int32_t* exc_l, const float* exc_w,
+                         const int32_t* exc_total, int exc_cap,
+                         const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
+                         float triple_w, float* gin, int mask_stride, const int32_t* m_count, void* stream);
+
 /* ipsr_paste (+ ipsr_build_routes) + ipsr_build_exceptions as ONE launch (independent once the scan has
  * finished; the latency-bound builders overlap the bandwidth-bound paste).  route_ptr == NULL: the routes
  * were already built (ipsr_blend_stage_with_routes).  exc_total must be zero on entry. */
@@ -343,6 +352,13 @@ typedef struct ipsr_fwd_args {
   void* ev_corr_begin;     /* optional cudaEvent_t pair recorded on `stream` around the      */
   void* ev_corr_end;       /*   correlation kernel ((b,c)), for live roofline measurement    */
   void* workspace; size_t workspace_bytes;
+  /* Per-image masks -- an EXTENSION of the reference, whose 2-D mask is shared by the batch (IPSRFunction.py:32):
+   * mask_stride = 0: flag [N], mask_idx [M], rank [N] serve every image (reference behaviour);
+   * mask_stride = N: flag, mask_idx and rank are [B][N] (row b for image b; mask_idx rows hold m_count[b] valid
+   *   entries), m_count [B] is the number of masked positions per image and M = max_b m_count[b] (the row stride of
+   *   wn, wo and of the workspace's per-step buffers). */
+  int32_t mask_stride;
+  const int32_t* m_count;
 } ipsr_fwd_args;
 
 size_t ipsr_workspace_bytes(int B, int C, int H, int W, int M, int mode);
