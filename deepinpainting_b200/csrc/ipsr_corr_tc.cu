@@ -21,6 +21,8 @@
 // A_RESIDENT: the R row tiles stay in shared memory for the whole CTA and only bank tiles stream (with
 // ROWT = 2 every streamed bank tile feeds 2 x 128 rows: half the L2 -> SM traffic per FLOP); otherwise both
 // operands stream per 64-channel block.
+#include <stdlib.h>
+
 #include "ipsr_common.cuh"
 
 namespace ipsr {
@@ -49,8 +51,13 @@ struct TcParams {
 // bank tile: each CTA fetches half of a stage and multicasts it into both shared memories, which halves the
 // L2 -> SM traffic (the limiter of the small and of the compacted launches).  A ring slot is refilled only after the
 // MMAs of BOTH CTAs have retired it (multicast commits onto both empty barriers).
-template <int ROWT, int PASSES, bool A_RESIDENT, int CL>
+// BN: bank columns per accumulator block = N of the tcgen05.mma instruction (128, or 256 with ROWT = 1 and one pass: two
+// adjacent bank tiles per stage, one 128 x 256 x 16 instruction instead of two 128 x 128 x 16 ones).
+template <int ROWT, int PASSES, bool A_RESIDENT, int CL, int BN = 128>
 __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcParams prm) {
+  static_assert(BN == 128 || (BN == 256 && ROWT == 1 && PASSES == 1), "256-column blocks: one row tile, one pass");
+  constexpr int kBlockN = BN;                                  // shadows the namespace constant inside this kernel
+  constexpr int kBT = BN / 128;                                // bank tiles per block
   static_assert(PASSES == 1 || PASSES == 3, "one hi*hi pass or the three-pass split");
   static_assert(CL == 1 || CL == 2, "single CTAs or CTA pairs");
   static_assert(ROWT == 1 || (A_RESIDENT && ROWT == 2), "two row tiles need the resident A operand");
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
   uint8_t* smem = smem_raw + (base - raw_addr);
 
   constexpr int AH = (PASSES == 3) ? 2 : 1;                    // operand parts per 64-channel block (hi[, lo])
-  constexpr uint32_t kStageBytes = (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes) + (uint32_t)AH * kTileBytes;
+  constexpr uint32_t kStageBytes = (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes) + (uint32_t)AH * kTileBytes * kBT;
   constexpr int kEpiWarps = 4 * ROWT;
   constexpr uint32_t kTmemCols = (uint32_t)ROWT * 2u * kBlockN;
   const int KB = prm.KB, RB = prm.RB;
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
       }
       int it = 0;
       for (int blk = blk0; blk < blk1; ++blk) {
-        const int cb = (prm.col_begin >> 7) + blk;                // 128-row bank tile of the block
+        const int cb = (prm.col_begin >> 7) + blk * kBT;          // first 128-row bank tile of the block
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % prm.stages;
           const uint32_t ph = (uint32_t)(it / prm.stages) & 1u;
@@ -143,7 +150,11 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
             for (int hl = 0; hl < AH; ++hl, dst += kTileBytes)
               bulk_g2s(dst, prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg, KB, RB, prm.a_parts), kTileBytes, full_bar(s));
           }
-          if (CL == 1) {
+          if (kBT == 2) {                        // two adjacent bank tiles (contiguous in the tile image); a pair fetches one each
+            if (CL == 1) bulk_g2s(dst, prm.x_tiles + tile_offset_bytes(b, kb, 0, cb, KB, RB), 2 * kTileBytes, full_bar(s));
+            else bulk_g2s_multicast(dst + crank * kTileBytes, prm.x_tiles + tile_offset_bytes(b, kb, 0, cb + (int)crank, KB, RB),
+                                    kTileBytes, full_bar(s), (uint16_t)0x3);
+          } else if (CL == 1) {
             for (int hl = 0; hl < AH; ++hl, dst += kTileBytes)
               bulk_g2s(dst, prm.x_tiles + tile_offset_bytes(b, kb, hl, cb, KB, RB), kTileBytes, full_bar(s));
           } else if (AH == 2) {                  // this CTA fetches the hi (rank 0) or the lo (rank 1) tile for both
@@ -226,11 +237,22 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const int colb = prm.col_begin + (blk0 + j) * kBlockN;
-#pragma unroll 1
+      // the TMEM load of chunk ch+1 is in flight while chunk ch is compared; the accumulator is handed back to the MMA
+      // warp as soon as its last chunk sits in registers
+      uint32_t rbuf[2][32];
+      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((rt * 2 + as) * kBlockN);
+      tmem_ld32(tsrc, rbuf[0]);
+#pragma unroll
       for (int ch = 0; ch < kBlockN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((rt * 2 + as) * kBlockN + ch * 32), r);
+        uint32_t (&r)[32] = rbuf[ch & 1];
         tmem_ld_wait();
+        if (ch + 1 < kBlockN / 32) {
+          tmem_ld32(tsrc + (uint32_t)((ch + 1) * 32), rbuf[(ch + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
         const int c0 = colb + ch * 32;
         if (top3) {
 #pragma unroll
@@ -262,9 +284,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
                             __uint_as_float(r[e + 3]));
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+
     }
     const size_t o = ((size_t)split * prm.B + b) * prm.N + q;
     prm.part_best[o] = best;
@@ -398,15 +418,15 @@ static int tc_stage_count(size_t a_bytes, size_t stage, size_t* smem_out) {
   return stages;
 }
 
-template <int ROWT, int PASSES, bool A_RES, int CL>
+template <int ROWT, int PASSES, bool A_RES, int CL, int BN = 128>
 static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
   constexpr int AH = (PASSES == 3) ? 2 : 1;
   const size_t a_bytes = A_RES ? (size_t)ROWT * (C / kTileK) * AH * kTileBytes : 0;
-  const size_t stage = (A_RES ? 0 : (size_t)AH * kTileBytes) + (size_t)AH * kTileBytes;
+  const size_t stage = (A_RES ? 0 : (size_t)AH * kTileBytes) + (size_t)AH * kTileBytes * (BN / 128);
   size_t smem = 0;
   prm.stages = tc_stage_count(a_bytes, stage, &smem);
   IPSR_REQUIRE(prm.stages >= 2, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: C=%d leaves %d pipeline stages", C, prm.stages);
-  auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL>;
+  auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL, BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
   cudaLaunchConfig_t cfg = {};
@@ -482,6 +502,20 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   const long long ctas = (long long)B * (two ? prm.RB / 2 : prm.RB) * psplit;
   IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
   const bool pairs = ((two ? prm.RB / 2 : prm.RB) % 2 == 0) && s_dump == nullptr;
+  // One row tile per CTA and 128 x 256 x 16 instructions (two adjacent bank tiles per stage) instead of two row tiles
+  // and 128 x 128 x 16 instructions: measured 487 us against 550 us at B = 64, 64 x 64 x 256 (0.81 against 0.72 of the
+  // cuBLAS rate) -- the wider instruction amortises its issue cost, and the CTA pairs still halve the L2 -> SM traffic.
+  // Taken when the resident row tile leaves >= 4 stages of 32 KiB (C <= 384), the splits stay whole blocks and the grid
+  // fills the machine.  IPSR_TC_BN256=0 in the environment turns it off (A/B measurements).
+  static const bool wide_ok = [] { const char* e = getenv("IPSR_TC_BN256"); return !(e && e[0] == '0'); }();
+  const int blocks256 = (col_end - col_begin) / 256;
+  if (wide_ok && s_dump == nullptr && (col_end - col_begin) % 256 == 0 && blocks256 % psplit == 0 &&
+      a_one + 4 * (size_t)(2 * kTileBytes) + 2048 <= 227 * 1024 && (long long)B * prm.RB * psplit >= 100) {
+    prm.blocks_total = blocks256;
+    const long long ctas1 = (long long)B * prm.RB * psplit;
+    IPSR_REQUIRE(ctas1 <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
+    return (prm.RB % 2 == 0) ? launch_tc<1, 1, true, 2, 256>(prm, C, ctas1, st) : launch_tc<1, 1, true, 1, 256>(prm, C, ctas1, st);
+  }
   if (two) return launch_tc_cl<2, 1, true>(prm, C, ctas, pairs, st);
   return a_res ? launch_tc_cl<1, 1, true>(prm, C, ctas, pairs, st) : launch_tc_cl<1, 1, false>(prm, C, ctas, pairs, st);
 }
