@@ -314,6 +314,10 @@ def run_ours(args):
         with open(tpath) as fh:
             tj_all = json.load(fh)
         traffic = next((v for k, v in tj_all.items() if "corr_tc" in k), None) if tensor_mode else None
+    tpath_b = os.path.join(ROOT, "profiles", "roofline_traffic_configB.json")      # configs[2]: the pass-1 launch
+    if os.path.exists(tpath_b) and (B, C, H) == (64, 256, 64) and tensor_mode:
+        with open(tpath_b) as fh:
+            traffic = next((v for k, v in json.load(fh).items() if "pass 1" in k), None)
     roofline = {"bound": "tensor", "kernel": ("corr_tc_kernel pass 1 (tcgen05 fp16 hi*hi over every row; ambiguous rows are redone by the 3-pass split)" if cascade else "corr_tc_kernel (tcgen05 fp16, 3-pass split hi*lo + lo*hi + hi*hi over every row: small problem, ceiling = 1/3 of peak)") if tensor_mode else "corr_fp32_kernel (FFMA)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "traffic": traffic, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),

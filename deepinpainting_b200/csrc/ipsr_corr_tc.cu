@@ -506,11 +506,14 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   // and 128 x 128 x 16 instructions: measured 487 us against 550 us at B = 64, 64 x 64 x 256 (0.81 against 0.72 of the
   // cuBLAS rate) -- the wider instruction amortises its issue cost, and the CTA pairs still halve the L2 -> SM traffic.
   // Taken when the resident row tile leaves >= 4 stages of 32 KiB (C <= 384), the splits stay whole blocks and the grid
-  // fills the machine.  IPSR_TC_BN256=0 in the environment turns it off (A/B measurements).
-  static const bool wide_ok = [] { const char* e = getenv("IPSR_TC_BN256"); return !(e && e[0] == '0'); }();
+  // fills the machine.  IPSR_TC_BN256=<n> in the environment sets the minimum ring depth (0 turns it off; A/B runs).
+  static const int wide_stages = [] {            // minimum ring depth; 0 = never
+    const char* e = getenv("IPSR_TC_BN256");
+    return e ? atoi(e) : 4;
+  }();
   const int blocks256 = (col_end - col_begin) / 256;
-  if (wide_ok && s_dump == nullptr && (col_end - col_begin) % 256 == 0 && blocks256 % psplit == 0 &&
-      a_one + 4 * (size_t)(2 * kTileBytes) + 2048 <= 227 * 1024 && (long long)B * prm.RB * psplit >= 100) {
+  if (wide_stages > 0 && s_dump == nullptr && (col_end - col_begin) % 256 == 0 && blocks256 % psplit == 0 &&
+      a_one + (size_t)wide_stages * (2 * kTileBytes) + 1280 <= 227 * 1024 && (long long)B * prm.RB * psplit >= 100) {
     prm.blocks_total = blocks256;
     const long long ctas1 = (long long)B * prm.RB * psplit;
     IPSR_REQUIRE(ctas1 <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
