@@ -505,11 +505,12 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   // One row tile per CTA and 128 x 256 x 16 instructions (two adjacent bank tiles per stage) instead of two row tiles
   // and 128 x 128 x 16 instructions: measured 487 us against 550 us at B = 64, 64 x 64 x 256 (0.81 against 0.72 of the
   // cuBLAS rate) -- the wider instruction amortises its issue cost, and the CTA pairs still halve the L2 -> SM traffic.
-  // Taken when the resident row tile leaves >= 4 stages of 32 KiB (C <= 384), the splits stay whole blocks and the grid
-  // fills the machine.  IPSR_TC_BN256=<n> in the environment sets the minimum ring depth (0 turns it off; A/B runs).
+  // At C = 512 (128 KiB resident row tile, only 3 stages of 32 KiB): 440 us against 739 us at B = 32, 64 x 64 x 512 (0.90
+  // against 0.54).  Taken when the resident row tile leaves >= 3 stages of 32 KiB (C <= 512), the splits stay whole
+  // blocks and the grid fills the machine.  IPSR_TC_BN256=<n> in the environment sets the minimum ring depth (0 turns it off; A/B runs).
   static const int wide_stages = [] {            // minimum ring depth; 0 = never
     const char* e = getenv("IPSR_TC_BN256");
-    return e ? atoi(e) : 4;
+    return e ? atoi(e) : 3;
   }();
   const int blocks256 = (col_end - col_begin) / 256;
   if (wide_stages > 0 && s_dump == nullptr && (col_end - col_begin) % 256 == 0 && blocks256 % psplit == 0 &&
