@@ -290,7 +290,8 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
       // pass 1: hi * hi over every row.  Two row tiles per CTA halve the L2 -> SM traffic of the streamed bank tiles:
       // prefer them (with a column split that brings the CTA count back up) whenever that still occupies most SMs
       int ps1 = auto_split((long long)B * RB);
-      if (RB % 2 == 0 && a->psplit <= 0) {
+      // (with 128 x 256 x 16 instructions a CTA owns ONE row tile: the split above is already the right one)
+      if (RB % 2 == 0 && a->psplit <= 0 && !tc_pass1_wide(B, C, N, cb, ce, ps1)) {
         const int ps_two = auto_split((long long)B * (RB / 2));
         if ((long long)B * (RB / 2) * ps_two >= 100) ps1 = ps_two;
       }

@@ -51,6 +51,7 @@ int paste_with_bookkeeping_ex(const float* x, const float* y, const int32_t* ind
                               float* out, int32_t* route_ptr, int32_t* route_q, int32_t* exc_start, int32_t* exc_cnt,
                               int32_t* exc_l, float* exc_w, int32_t* exc_total, int exc_cap, void* stream, int ms,
                               const int32_t* mcount);
+bool tc_pass1_wide(int B, int C, int N, int col_begin, int col_end, int psplit);
 int build_routes_ex(const int32_t* ind, const int32_t* flag, const int32_t* mask_idx, int B, int N, int M,
                     int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount);
 int build_exceptions_ex(const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo, int B, int N, int M,

@@ -453,6 +453,20 @@ static int launch_tc_cl(const TcParams& prm, int C, long long ctas, bool pairs, 
 
 }  // namespace ipsr
 
+// Does the single pass over [col_begin, col_end) with this column split run the 128 x 256 x 16 variant?  (Also asked by
+// the fused forward, which sizes the split for one row tile per CTA in that case.)
+bool ipsr::tc_pass1_wide(int B, int C, int N, int col_begin, int col_end, int psplit) {
+  static const int wide_stages = [] {            // minimum ring depth; 0 = never
+    const char* e = getenv("IPSR_TC_BN256");
+    return e ? atoi(e) : 3;
+  }();
+  if (wide_stages <= 0 || psplit < 1 || (col_end - col_begin) % 256 != 0) return false;
+  const int blocks256 = (col_end - col_begin) / 256;
+  const size_t a_one = (size_t)(C / kTileK) * kTileBytes;
+  return blocks256 % psplit == 0 && a_one + (size_t)wide_stages * (2 * kTileBytes) + 1280 <= 227 * 1024 &&
+         (long long)B * (N / kTileRows) * psplit >= 100;
+}
+
 extern "C" int ipsr_tensor_path_supported(int C, int N) {
   return (C > 0 && N > 0 && C % ipsr::kTileK == 0 && N % ipsr::kTileRows == 0 && N <= 65536) ? 1 : 0;
 }
@@ -508,14 +522,8 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   // At C = 512 (128 KiB resident row tile, only 3 stages of 32 KiB): 440 us against 739 us at B = 32, 64 x 64 x 512 (0.90
   // against 0.54).  Taken when the resident row tile leaves >= 3 stages of 32 KiB (C <= 512), the splits stay whole
   // blocks and the grid fills the machine.  IPSR_TC_BN256=<n> in the environment sets the minimum ring depth (0 turns it off; A/B runs).
-  static const int wide_stages = [] {            // minimum ring depth; 0 = never
-    const char* e = getenv("IPSR_TC_BN256");
-    return e ? atoi(e) : 3;
-  }();
-  const int blocks256 = (col_end - col_begin) / 256;
-  if (wide_stages > 0 && s_dump == nullptr && (col_end - col_begin) % 256 == 0 && blocks256 % psplit == 0 &&
-      a_one + (size_t)wide_stages * (2 * kTileBytes) + 1280 <= 227 * 1024 && (long long)B * prm.RB * psplit >= 100) {
-    prm.blocks_total = blocks256;
+  if (s_dump == nullptr && tc_pass1_wide(B, C, N, col_begin, col_end, psplit)) {
+    prm.blocks_total = (col_end - col_begin) / 256;
     const long long ctas1 = (long long)B * prm.RB * psplit;
     IPSR_REQUIRE(ctas1 <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
     return (prm.RB % 2 == 0) ? launch_tc<1, 1, true, 2, 256>(prm, C, ctas1, st) : launch_tc<1, 1, true, 1, 256>(prm, C, ctas1, st);
