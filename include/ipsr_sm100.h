@@ -102,7 +102,9 @@ int ipsr_compact_rows(const float* ref, int B, int C, int N, const int32_t* list
  * ------------------------------------------------------------------------------------------- */
 
 /* tcgen05/TMEM GEMM over bank columns [col_begin, col_end) (multiples of 128), split into `psplit` column
- * ranges per row tile.  passes = 1: hi * hi only; passes = 3: hi*lo + lo*hi + hi*hi.  r_parts: parts per
+ * ranges per row tile.  passes = 1: hi * hi only (128 x 256 x 16 instructions, one row tile per CTA, when the column
+ * range is a multiple of 256, the splits stay whole 256-column blocks and C <= 512; two row tiles per CTA with
+ * 128 x 128 x 16 instructions otherwise); passes = 3: hi*lo + lo*hi + hi*hi.  r_parts: parts per
  * 64-channel block in the r_tiles image (2; 1 is accepted for a hi-only image with passes = 1).
  * row_limit (optional, [B]): only the first row_limit[b] rows of r_tiles are populated (compacted operand).
  * Writes per row and per split the best SCALED score, its (global) column index and the runner-up score:
