@@ -18,9 +18,10 @@
 //   warp 1       TMEM allocation + single-thread tcgen05.mma issue, commits free the ring slots
 //   warps 2..    epilogue, 4 warps per row tile: tcgen05.ld of the finished accumulator (double-buffered in
 //                TMEM) and the running (best, idx, second) per row in registers -- thread == row, no shuffles.
-// A_RESIDENT: the R row tiles stay in shared memory for the whole CTA and only bank tiles stream (with
-// ROWT = 2 every streamed bank tile feeds 2 x 128 rows: half the L2 -> SM traffic per FLOP); otherwise both
-// operands stream per 64-channel block.
+// A_RESIDENT: the R row tiles stay in shared memory for the whole CTA and only bank tiles stream; otherwise both
+// operands stream per 64-channel block.  Pass 1 runs BN = 256 (one row tile, two adjacent bank tiles per stage, one
+// 128 x 256 x 16 instruction per K step) whenever the shape allows it, else ROWT = 2 with BN = 128 (every streamed bank
+// tile feeds 2 x 128 rows); the three-pass launches run ROWT = 1, BN = 128.
 #include <stdlib.h>
 
 #include "ipsr_common.cuh"
