@@ -156,6 +156,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is one process and may use every host thread
+    pool = None
+    try:
+        import numpy  # noqa: F401  (the BLAS pool must be loaded before it can be resized)
+        from threadpoolctl import threadpool_limits
+        pool = threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception as exc:                                       # keep the launcher's setting
+        sys.stderr.write("threadpoolctl unavailable (%s): BLAS threads as configured by the environment\n" % exc)
     C, H = args.channels, args.size
     per_step = max(1, min(args.batch, 2 if H <= 32 else 1))          # bounded sample of the batch per step
     steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 1))
@@ -182,6 +190,7 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+    del pool
 
 
 # ------------------------------------------------------------------------------------------------
