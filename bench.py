@@ -126,33 +126,67 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the reference's CPU path (numpy port pinned against the reference's own outputs, oracle/)
 # ------------------------------------------------------------------------------------------------
-def cpu_path_images_per_sec(C, H, W, n_images, seed=1234):
-    import numpy as np
-    from oracle import ipsr_oracle as O
+def _host_threads():
     try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return len(os.sched_getaffinity(0))
     except Exception:
-        threads = os.cpu_count() or 1
+        return os.cpu_count() or 1
+
+
+def cpu_path_images_per_sec(C, H, W, n_images, seed=1234, kind=None):
+    """fwd+bwd images/s of the reference's CPU path on this box's host cores, one image per call (the reference
+    loops over the batch, models/IPSRFunction.py:46).  kind "reference": the reference's own unmodified PyTorch code
+    staged under oracle/_ref (oracle/build_ref.py); kind "port": the numpy restatement oracle/ipsr_oracle.py (pinned on
+    the reference's golden outputs) when the staged copy did not travel.  Returns (images/s, threads, seconds, kind)."""
+    import numpy as np
+    from oracle import ref_runner
+    if kind is None:
+        kind = "reference" if ref_runner.available() else "port"
     rng = np.random.default_rng(seed)
     flag = centre_flag(H, W)
 
-    def one():
+    def inputs():
         x = rng.standard_normal((1, C, H, W)).astype(np.float32)
         ref = (np.maximum(rng.standard_normal((1, C, H, W)), 0) * 3).astype(np.float32)
         g = rng.standard_normal((1, C, H, W)).astype(np.float32)
-        t0 = time.perf_counter()
-        res = O.shift_forward(x, ref, flag, np.float32, keep_attn=True, with_gap=False)
-        O.shift_backward(g, res.attn_trunc, 1.0)
-        return time.perf_counter() - t0
+        return x, ref, g
 
-    one()                                       # warm-up (BLAS thread pool, page faults)
+    if kind == "reference":
+        import torch
+        threads = _host_threads()
+        torch.set_num_threads(threads)               # torchrun exports OMP_NUM_THREADS=1; this arm is ONE process
+        S = H * 8
+        mg = torch.zeros(1, 1, S, S, dtype=torch.bool)
+        mg[:, :, S // 4:3 * S // 4, S // 4:3 * S // 4] = True
+
+        def one():
+            x, ref, g = (torch.from_numpy(a) for a in inputs())
+            t0 = time.perf_counter()
+            ref_runner.shift_fwd_bwd(x, ref, g, mg)
+            return time.perf_counter() - t0
+    else:
+        from oracle import ipsr_oracle as O
+        try:
+            from threadpoolctl import threadpool_info
+            threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        except Exception:
+            threads = os.cpu_count() or 1
+
+        def one():
+            x, ref, g = inputs()
+            t0 = time.perf_counter()
+            res = O.shift_forward(x, ref, flag, np.float32, keep_attn=True, with_gap=False)
+            O.shift_backward(g, res.attn_trunc, 1.0)
+            return time.perf_counter() - t0
+
+    one()                                       # warm-up (thread pools, lazy imports, page faults)
     total = sum(one() for _ in range(n_images))
-    return n_images / total, threads, total
+    return n_images / total, threads, total, kind
 
 
 def run_reference(args):
-    """--impl reference: the CPU path on this box's host cores, same metric / config."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, same metric and
+    config as our arm.  Each step is a bounded sample of the batch (the reference processes images one by one)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -161,36 +195,48 @@ def run_reference(args):
     try:
         import numpy  # noqa: F401  (the BLAS pool must be loaded before it can be resized)
         from threadpoolctl import threadpool_limits
-        pool = threadpool_limits(limits=os.cpu_count() or 1)
+        pool = threadpool_limits(limits=_host_threads())
     except Exception as exc:                                       # keep the launcher's setting
         sys.stderr.write("threadpoolctl unavailable (%s): BLAS threads as configured by the environment\n" % exc)
     C, H = args.channels, args.size
     per_step = max(1, min(args.batch, 2 if H <= 32 else 1))          # bounded sample of the batch per step
     steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 1))
+    kind = "port"
     for _ in range(warm):
-        cpu_path_images_per_sec(C, H, H, 1)
+        kind = cpu_path_images_per_sec(C, H, H, 1)[3]
     t_imgs, t_secs, threads = 0, 0.0, 1
     for _ in range(steps):
-        ips, threads, secs = cpu_path_images_per_sec(C, H, H, per_step)
+        ips, threads, secs, kind = cpu_path_images_per_sec(C, H, H, per_step)
         t_imgs += per_step
         t_secs += secs
     value = t_imgs / t_secs
+    cfg = workload_config(args.batch, C, H, 1, args.mode)
+    cfg["note"] = ("reference arm = the reference's own unmodified PyTorch implementation (oracle/_ref, staged by oracle/build_ref.py) "
+                   "on the host CPU" if kind == "reference" else
+                   "reference arm = numpy port (oracle/ipsr_oracle.py) pinned on the reference's golden outputs; oracle/_ref "
+                   "was not staged on this box")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * t_secs / steps * (args.batch / per_step), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"] if (args.batch, C, H) == (16, 256, 32) else
-                   "shift layer fwd+bwd, batch %d, %dx%dx%d features, centre mask" % (args.batch, H, H, C),
-                   "batch_per_gpu": args.batch, "C": C, "H": H, "W": H,
-                   "note": "reference CPU path = numpy port (oracle/ipsr_oracle.py) pinned on the reference's golden outputs; "
-                           "the Python reference itself cannot travel to the GPU box"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": "%d steps x %d image(s) of the batch, fwd+bwd, fp32" % (steps, per_step)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     del pool
+
+
+def workload_config(B, C, H, world, mode):
+    """The `config` object both arms print (same keys, so the driver can compare them)."""
+    N = H * H
+    M = int(centre_flag(H, H).sum())
+    return {"workload": WORKLOAD["name"] if (B, C, H) == (16, 256, 32) else
+            "shift layer fwd+bwd, batch %d per GPU, %dx%dx%d features, centre mask" % (B, H, H, C),
+            "batch_per_gpu": B, "global_batch": B * world, "C": C, "H": H, "W": H, "N": N, "M": M,
+            "parallelism": "batch-sharded x%d, no data-path collective" % world, "mode": mode}
 
 
 # ------------------------------------------------------------------------------------------------

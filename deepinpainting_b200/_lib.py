@@ -42,6 +42,7 @@ class FwdArgs(C.Structure):
 SIGNATURES = {
     "ipsr_last_error_string": (C.c_char_p, []),
     "ipsr_version": (_i, []),
+    "ipsr_abi_fwd_args_bytes": (_i, []),
     "ipsr_tensor_path_supported": (_i, [_i, _i]),
     "ipsr_tensor_cascade": (_i, [_i, _i, _i]),
     "ipsr_feat_mask": (_i, [_p, _i, _i, _i, _f, _p, _p, _p]),
@@ -104,11 +105,19 @@ def load(build_if_missing: bool = True):
             if not build_if_missing:
                 raise IpsrError("libipsr_sm100.so not found at %s and building was disabled" % path)
             path = _build.build_library()
+        elif not _build.is_current():
+            # a library older than csrc/ or the header: argument lists and the ipsr_fwd_args layout may have moved
+            if not build_if_missing:
+                raise IpsrError("libipsr_sm100.so at %s is stale (sources changed) and building was disabled" % path)
+            path = _build.build_library()
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here == ABI drift, fail loudly
             fn.restype = res
             fn.argtypes = args
+        if lib.ipsr_abi_fwd_args_bytes() != C.sizeof(FwdArgs):
+            raise IpsrError("ABI drift: ipsr_fwd_args is %d bytes in %s but %d bytes in the ctypes mirror"
+                            % (lib.ipsr_abi_fwd_args_bytes(), path, C.sizeof(FwdArgs)))
         _lib = lib
         return _lib
 

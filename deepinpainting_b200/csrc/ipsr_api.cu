@@ -102,6 +102,8 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  std::mutex use;          // held by a caller from its fork record to its join wait: the event pair is shared by every
+                           // host thread using this device, and a record / wait pair must not be interleaved with another's
 };
 static SideStream* side_stream() {
   static SideStream table[64];
@@ -126,6 +128,11 @@ static T* at(const ipsr_fwd_args* a, size_t off) {
   return reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(a->workspace) + off);
 }
 
+// col_end < 0, or col_begin == col_end == 0 (a zero-initialised struct): the whole bank
+static int shard_end(const ipsr_fwd_args* a, int N) {
+  return (a->col_end < 0 || (a->col_end == 0 && a->col_begin == 0)) ? N : a->col_end;
+}
+
 static int validate(const ipsr_fwd_args* a, Workspace* w, int* mode_out) {
   IPSR_REQUIRE(a != nullptr, IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: args is null");
   IPSR_REQUIRE(a->x && a->ref && a->flag && a->rank && a->out && a->ind, IPSR_ERR_INVALID_ARG,
@@ -140,8 +147,11 @@ static int validate(const ipsr_fwd_args* a, Workspace* w, int* mode_out) {
   IPSR_REQUIRE(mode == IPSR_MODE_TENSOR || mode == IPSR_MODE_EXACT, IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: bad mode %d", a->mode);
   IPSR_REQUIRE(mode != IPSR_MODE_TENSOR || ipsr_tensor_path_supported(a->C, N), IPSR_ERR_UNSUPPORTED,
                "ipsr_shift_forward: tensor mode needs C %% 64 == 0 and N %% 128 == 0 (C=%d N=%d)", a->C, N);
-  const int cb = a->col_begin, ce = (a->col_end > 0 ? a->col_end : N);
-  IPSR_REQUIRE(cb >= 0 && cb < ce && ce <= N, IPSR_ERR_INVALID_ARG, "ipsr_shift_forward: bad column shard [%d,%d)", cb, ce);
+  const int cb = a->col_begin, ce = shard_end(a, N);
+  // an EMPTY shard (cb == ce > 0: more ranks than 128-column tiles) is legal in the bank-sharded mode only: the rank
+  // contributes identity keys to the exchange and runs everything after it like the others
+  IPSR_REQUIRE(cb >= 0 && cb <= ce && ce <= N && (cb < ce || a->stop_after_corr), IPSR_ERR_INVALID_ARG,
+               "ipsr_shift_forward: bad column shard [%d,%d)", cb, ce);
   IPSR_REQUIRE(mode != IPSR_MODE_TENSOR || (cb % 128 == 0 && ce % 128 == 0), IPSR_ERR_UNSUPPORTED,
                "ipsr_shift_forward: tensor mode needs 128-aligned column shards, got [%d,%d)", cb, ce);
   if (a->need_grad) {
@@ -175,6 +185,8 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
     // the exception lists depend on wn / wo only: build them on the side stream while the paste streams x -> out
     SideStream* ss = side_stream();
     cudaStream_t st = as_stream(stream);
+    std::unique_lock<std::mutex> in_use;
+    if (ss) in_use = std::unique_lock<std::mutex>(ss->use);
     if (ss && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
       int rc = build_exceptions_ex(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l, a->exc_w,
                                    a->exc_total, a->exc_cap, ss->stream, ms, mcount);
@@ -186,6 +198,7 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
       return rc;
     }
     (void)cudaGetLastError();
+    if (in_use.owns_lock()) in_use.unlock();
     return paste_with_bookkeeping_ex(a->x, at<float>(a, w.y), a->ind, a->rank, a->flag, a->mask_idx, a->wn, a->wo, B, C,
                                      N, M, a->out, nullptr, nullptr, a->exc_start, a->exc_cnt, a->exc_l,
                                      a->exc_w, a->exc_total, a->exc_cap, stream, ms, mcount);
@@ -196,7 +209,8 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
 }  // namespace ipsr
 
 extern "C" const char* ipsr_last_error_string(void) { return ipsr::g_err; }
-extern "C" int ipsr_version(void) { return 100; }
+extern "C" int ipsr_version(void) { return 200; }
+extern "C" int ipsr_abi_fwd_args_bytes(void) { return (int)sizeof(ipsr_fwd_args); }
 
 extern "C" int ipsr_tensor_cascade(int B, int C, int N) {
   if (!ipsr_tensor_path_supported(C, N)) return 0;
@@ -226,7 +240,7 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   int mode = 0;
   IPSR_FORWARD(validate(a, &w, &mode));
   const int B = a->B, C = a->C, N = a->H * a->W, M = a->M;
-  const int cb = a->col_begin, ce = (a->col_end > 0 ? a->col_end : N);
+  const int cb = a->col_begin, ce = shard_end(a, N);
   cudaStream_t st = as_stream(stream);
   int32_t* nonfinite = at<int32_t>(a, w.counters);
   int32_t* nrecheck = nonfinite + B;
@@ -239,7 +253,7 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   cudaError_t e = cudaMemsetAsync(nonfinite, 0, (size_t)5 * B * sizeof(int32_t), st);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memset: %s", cudaGetErrorString(e));
   if (a->need_grad && M > 1) {
-    e = cudaMemsetAsync(a->exc_total, 0, (size_t)B * sizeof(int32_t), st);
+    e = cudaMemsetAsync(a->exc_total, 0, ((size_t)2 * B + 2) * sizeof(int32_t), st);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memset: %s", cudaGetErrorString(e));
   }
 
@@ -256,6 +270,10 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
                                     nonfinite, tensor ? at<float>(a, w.rscale) : nullptr,
                                     tensor ? at<float>(a, w.rerr) : nullptr, nullptr, tensor ? xerr_max : nullptr, stream,
                                     a->mask_stride));
+  if (cb == ce) {
+    // empty bank shard: identity keys for the exchange (the operands prepared above serve the steps after it)
+    return ipsr_select_all_rows(B, N, list, nrecheck, packed, stream);
+  }
   if (tensor) {
     const int RB = N / kTileRows;
     auto auto_split = [&](long long tiles) {

@@ -477,14 +477,15 @@ paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int
 }
 
 // The paste and the two bookkeeping builders of the backward are independent once the scan is done:
-// one launch, block ranges = [routes: B CTAs][exceptions: B CTAs][paste: B * C/CT CTAs].
+// one launch, block ranges = [routes: B CTAs][exceptions: B CTAs][paste: B * C/CT CTAs]  (exc_total is the
+// [2B + 2] exception state of ipsr_build_exceptions, zero on entry).
 // The latency-bound bookkeeping CTAs are scheduled first and overlap the bandwidth-bound paste.
 struct FusedPasteArgs {
   const float* x; const float* y; const int* ind; const int* rank; float* out;
   int B, C, N, M, CT, parts, tiles_per_cta;
   const int* flag; const int* mask_idx; int* route_ptr; int* route_q;
   const float* wn; const float* wo; int* exc_start; int* exc_cnt; int* exc_l; float* exc_w; int* exc_total; int exc_cap;
-  int n_routes, n_exc, exc_per_img;
+  int n_routes, n_exc;
   int ms; const int* mcount;
 };
 
@@ -497,8 +498,8 @@ __global__ void __launch_bounds__(512) paste_fused_kernel(const FusedPasteArgs a
   }
   blk -= a.n_routes;
   if (blk < a.n_exc) {
-    build_exceptions_cta(blk / a.exc_per_img, blk % a.exc_per_img, a.exc_per_img, fsm, a.ind, a.mask_idx, a.wn, a.wo, a.N, a.M,
-                         a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total, a.exc_cap, a.ms, a.mcount);
+    build_exceptions_cta(blk, a.B, fsm, a.ind, a.mask_idx, a.wn, a.wo, a.N, a.M, a.exc_start, a.exc_cnt, a.exc_l, a.exc_w,
+                         a.exc_total, a.exc_cap, a.ms, a.mcount);
     return;
   }
   blk -= a.n_exc;
@@ -540,11 +541,9 @@ static int launch_stage(StageArgs a, cudaStream_t st) {
     if (smem_routes > smem) smem = smem_routes;
   }
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: C=%d / N=%d too large", a.C, a.N);
-  static size_t configured = 0;
-  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
+  if (smem + 2048 > 48 * 1024) {   // dynamic + static shared memory above the default limit (set per call: the attribute is per device)
     cudaError_t e = cudaFuncSetAttribute(blend_stage_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_stage smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   a.nblocks = (a.M + T - 1) / T;
   const long long ctas = (long long)a.n_routes + (long long)a.nblocks * a.B;
@@ -567,11 +566,9 @@ static int launch_scan(const float* staged, int B, int C, int M, float* y, float
   const size_t blk_bytes = (size_t)staged_block_floats(C) * sizeof(float);
   const size_t smem = 2 * ((blk_bytes + 127) & ~(size_t)127) + ((size_t)C + (size_t)T * (C + 1)) * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
-  static size_t configured = 0;
-  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
+  if (smem + 2048 > 48 * 1024) {   // dynamic + static shared memory above the default limit (set per call: the attribute is per device)
     cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   blend_scan_kernel<T><<<B, kScanThreads, smem, st>>>(staged, C, M, y, wn, wo, mcount);
   return check_launch("ipsr_blend_scan");
@@ -651,11 +648,9 @@ int ipsr::paste_ex(const float* x, const float* y, const int32_t* ind, const int
   const int CT = paste_ct(C, N);
   const size_t smem = paste_smem(CT, N, M);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste: N=%d too large", N);
-  static size_t configured = 0;
-  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
+  if (smem + 2048 > 48 * 1024) {   // dynamic + static shared memory above the default limit (set per call: the attribute is per device)
     cudaError_t e = cudaFuncSetAttribute(paste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   const int threads = paste_threads(N);
   const int ntiles = (C + CT - 1) / CT;
@@ -703,18 +698,15 @@ int ipsr::paste_with_bookkeeping_ex(const float* x, const float* y, const int32_
   a.exc_total = exc_total; a.exc_cap = exc_cap;
   a.ms = ms; a.mcount = mcount;
   a.n_routes = routes ? B : 0;
-  a.exc_per_img = exc ? exc_parts(M) : 0;
-  a.n_exc = B * a.exc_per_img;
+  a.n_exc = exc ? B : 0;
   size_t smem = paste_smem(a.CT, N, M);
-  const size_t smem_routes = (size_t)(2 * N + 1) * sizeof(int), smem_exc = ((size_t)((N + 3) & ~3) + ((M + 3) & ~3) + 3 * kExcChunk) * sizeof(int);
+  const size_t smem_routes = (size_t)(2 * N + 1) * sizeof(int), smem_exc = exc_smem_words(N, M) * sizeof(int);
   if (routes && smem_routes > smem) smem = smem_routes;
   if (exc && smem_exc > smem) smem = smem_exc;
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: N=%d too large", N);
-  static size_t configured = 0;
-  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
+  if (smem + 2048 > 48 * 1024) {   // dynamic + static shared memory above the default limit (set per call: the attribute is per device)
     cudaError_t e = cudaFuncSetAttribute(paste_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste_fused smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   const long long ctas = (long long)a.n_routes + a.n_exc + (long long)B * a.parts;
   IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_paste_with_bookkeeping: grid too large");

@@ -92,12 +92,15 @@ build_routes_cta(int b, int* rsm, const int* __restrict__ ind, const int* __rest
 // exceptions: replay row_l[p] = row_{l-1}[p]*wn_l (+ wo_l if p == p_l) -- only columns that are the
 // match of some masked position can ever be non-zero, so the work is one thread per masked position
 // l0 that is the FIRST occurrence of its column p_{l0}, walking l = l0+1 .. M-1.
-// One CTA per image; shared memory: 3*kExcChunk words of staging.
+// One CTA per image.  Entries go into ONE POOL shared by the whole batch (exc_l / exc_w [exc_cap]): an image takes
+// the contiguous range [base, base + count) it reserves with one atomicAdd on the pool cursor, so a chaotic image
+// (tens of thousands of surviving entries with signed inputs) borrows the room the well-behaved images do not use.
+// exc_state is int32 [2B + 2]: [b] = entries of image b (>= kExcReplay: the lists are unusable -- pool exhausted or
+// non-finite weights -- and the backward replays the recurrence), [B + b] = base of image b, [2B] = pool cursor.
 // ---------------------------------------------------------------------------------------------
 constexpr int kExcChunk = 1024;
-constexpr int kExcThreads = 256;
-// CTAs per image: one per 256 masked steps (every owner thread then walks the whole tail of the recurrence once)
-__host__ __device__ inline int exc_parts(int M) { return M <= kExcThreads ? 1 : (M + kExcThreads - 1) / kExcThreads; }
+constexpr int kExcThreads = 1024;
+constexpr int kExcReplay = 0x3FFFFFFF;
 
 // One owner = one bank column p, identified by the first masked step l0 whose match is p.  Walks
 // row_l[p] = row_{l-1}[p] * wn_l (+ wo_l if p_l == p) for l = l0 .. M-1 in the reference's operation order and
@@ -149,51 +152,53 @@ __device__ __forceinline__ int replay_owner(int l0, int p, int base, int n, cons
   return cnt;
 }
 
-// CTA `part` of `nparts` of image b owns the masked steps l0 with l0 % nparts == part.
-// fsm: first-occurrence table [N] ints, owner list [M] ints (padded to 4), then 3*kExcChunk staging words (16-byte aligned)
+// shared memory of one exceptions CTA, in 4-byte words
+__host__ __device__ inline size_t exc_smem_words(int N, int M) {
+  return (size_t)((N + 3) & ~3) + 2 * (size_t)((M + 3) & ~3) + 3 * kExcChunk;
+}
+
+// fsm: first-occurrence table [N] ints, owner list [M] ints, slot offsets [M] ints (both padded to 4), then
+// 3*kExcChunk staging words (16-byte aligned)
 __device__ __forceinline__ void
-build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
+build_exceptions_cta(int b, int B, void* fsm, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                      const float* __restrict__ wn, const float* __restrict__ wo, int N, int M,
                      int* __restrict__ exc_start, int* __restrict__ exc_cnt, int* __restrict__ exc_l,
-                     float* __restrict__ exc_w, int* __restrict__ exc_total, int exc_cap,
+                     float* __restrict__ exc_w, int* __restrict__ exc_state, int exc_cap,
                      int ms = 0, const int* __restrict__ mcount = nullptr) {
   int* first = reinterpret_cast<int*>(fsm);                 // [N] first masked step whose match is p, or INT_MAX
-  int* owners = first + ((N + 3) & ~3);                     // [M] compact list of this part's owner steps
-  float* s_wn = reinterpret_cast<float*>(owners + ((M + 3) & ~3));
+  int* owners = first + ((N + 3) & ~3);                     // [M] compact list of the owner steps
+  int* slot = owners + ((M + 3) & ~3);                      // [M] offset of owner k's entries inside the image's range
+  float* s_wn = reinterpret_cast<float*>(slot + ((M + 3) & ~3));
   const int Mstride = M;                                    // rows of wn / wo are M (the batch maximum) apart
   mask_idx += (size_t)b * ms;                               // per-image masks (see build_routes_cta)
   if (mcount) M = mcount[b];
   float* s_wo = s_wn + kExcChunk;
   int* s_p = reinterpret_cast<int*>(s_wo + kExcChunk);
-  __shared__ int nonfinite_w, nown_s;
+  __shared__ int nonfinite_w, nown_s, total_s, base_s;
   const int* ind_b = ind + (size_t)b * N;
   const float* wnb = wn + (size_t)b * Mstride;
   const float* wob = wo + (size_t)b * Mstride;
-  for (int p = threadIdx.x; p < N; p += blockDim.x) first[p] = 0x7FFFFFFF;
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    first[p] = 0x7FFFFFFF;
+    exc_start[(size_t)b * N + p] = 0;                       // default: no exceptions in this column
+    exc_cnt[(size_t)b * N + p] = 0;
+  }
   if (threadIdx.x == 0) {
     nonfinite_w = 0;
     nown_s = 0;
+    total_s = 0;
+    base_s = 0;
   }
   __syncthreads();
   for (int l = threadIdx.x; l < M; l += blockDim.x) atomicMin(&first[ind_b[mask_idx[l]]], l);
   __syncthreads();
-  // default: no exceptions in this column.  Columns are zeroed by the part that owns their first occurrence
-  // (or, for columns never matched by a masked position, by part 0), so no two CTAs write the same entry.
-  for (int p = threadIdx.x; p < N; p += blockDim.x) {
-    const int f = first[p];
-    const int owner_part = (f == 0x7FFFFFFF) ? 0 : (f % nparts);
-    if (owner_part == part) {
-      exc_start[(size_t)b * N + p] = 0;
-      exc_cnt[(size_t)b * N + p] = 0;
-    }
-  }
   // compact owner list: only the first occurrence of a column walks it, and only a fraction of the masked steps
   // are first occurrences -- compaction keeps every lane of the walking warps busy
-  for (int l0 = part + nparts * (int)threadIdx.x; l0 < M; l0 += nparts * (int)blockDim.x)
+  for (int l0 = threadIdx.x; l0 < M; l0 += blockDim.x)
     if (first[ind_b[mask_idx[l0]]] == l0) owners[atomicAdd(&nown_s, 1)] = l0;
   // A non-finite weight turns EVERY column of the later rows into NaN (0 * inf), which the sparse
-  // "first occurrence" walk below cannot represent: flag the image as overflowed so that the backward
-  // replays the full recurrence per column (bit-faithful, slow, chaotic inputs only).
+  // "first occurrence" walk below cannot represent: flag the image so that the backward replays the full
+  // recurrence per column (bit-faithful, slow, chaotic inputs only).
   int cur_base = -1;                                        // chunk currently staged (uniform)
   auto stage = [&](int base) {
     if (base == cur_base) return;
@@ -211,11 +216,12 @@ build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restri
   };
   stage(0);                                                 // also publishes the owner list
   const int nown = nown_s;
+  // walk 1: count the surviving entries of every owned column and hand out slots inside the image's range
+  // (placement between columns is arbitrary, the order inside a column is ascending l)
   for (int round = 0; round < nown; round += blockDim.x) {
     const int k = round + threadIdx.x;
     const int l0 = (k < nown) ? owners[k] : M;
     const int p = (k < nown) ? ind_b[mask_idx[l0]] : -1;
-    // walk 1: count the surviving entries of this column
     float e = 0.f;
     int found = 0;
     for (int base = 0; base < M; base += kExcChunk) {
@@ -223,31 +229,43 @@ build_exceptions_cta(int b, int part, int nparts, void* fsm, const int* __restri
       if (p >= 0) found = replay_owner<false>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, found, nullptr,
                                               nullptr);
     }
-    // reserve a contiguous slot range (placement is arbitrary, order inside is ascending l)
-    int start = 0;
-    bool fits = false;
-    if (p >= 0 && found > 0) {
-      start = atomicAdd(exc_total + b, found);
-      fits = (start + found <= exc_cap);
-      if (fits) {
-        exc_start[(size_t)b * N + p] = start;
-        exc_cnt[(size_t)b * N + p] = found;
-      }
-    }
-    // walk 2: only the owners that have something to write (uniform decision)
-    if (__syncthreads_or(fits ? 1 : 0)) {
-      e = 0.f;
-      int cnt = 0;
-      for (int base = 0; base < M; base += kExcChunk) {
-        stage(base);
-        if (fits)
-          cnt = replay_owner<true>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, cnt,
-                                   exc_l + (size_t)b * exc_cap + start, exc_w + (size_t)b * exc_cap + start);
-      }
-    }
+    if (k < nown) slot[k] = found > 0 ? atomicAdd(&total_s, found) : -1;
   }
   __syncthreads();
-  if (threadIdx.x == 0 && nonfinite_w) atomicMax(exc_total + b, 0x3FFFFFFF);
+  const int total = total_s;
+  if (threadIdx.x == 0) {
+    int base = 0;
+    bool ok = !nonfinite_w;
+    if (ok && total > 0) {
+      base = atomicAdd(exc_state + 2 * B, total);           // one reservation per image
+      ok = (long long)base + total <= (long long)exc_cap;
+    }
+    base_s = ok ? base : -1;
+    exc_state[b] = ok ? total : kExcReplay;
+    exc_state[B + b] = ok ? base : 0;
+  }
+  __syncthreads();
+  const int ibase = base_s;
+  if (ibase < 0 || total == 0) return;
+  // walk 2: write
+  for (int round = 0; round < nown; round += blockDim.x) {
+    const int k = round + threadIdx.x;
+    const int l0 = (k < nown) ? owners[k] : M;
+    const int p = (k < nown) ? ind_b[mask_idx[l0]] : -1;
+    const int sl = (k < nown) ? slot[k] : -1;
+    float e = 0.f;
+    int cnt = 0;
+    for (int base = 0; base < M; base += kExcChunk) {
+      stage(base);
+      if (sl >= 0)
+        cnt = replay_owner<true>(l0, p, base, min(kExcChunk, M - base), s_wn, s_wo, s_p, mask_idx, e, cnt,
+                                 exc_l + (size_t)ibase + sl, exc_w + (size_t)ibase + sl);
+    }
+    if (sl >= 0) {
+      exc_start[(size_t)b * N + p] = sl;                    // relative to the image's base
+      exc_cnt[(size_t)b * N + p] = cnt;
+    }
+  }
 }
 
 }  // namespace ipsr

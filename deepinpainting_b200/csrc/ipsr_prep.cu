@@ -254,11 +254,9 @@ int ipsr::extract_normalize_ex(const float* x, const float* ref, int B, int C, i
   }
   const size_t smem = ((size_t)C * 33 + 2 * 8 * 32 + 32 + (size_t)(C / 8) * 32) * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_extract_normalize: C=%d too large", C);
-  static size_t configured = 0;
-  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
+  if (smem + 2048 > 48 * 1024) {   // dynamic + static shared memory above the default limit (set per call: the attribute is per device)
     cudaError_t e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "prep smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   dim3 grid((N + kPrepPos - 1) / kPrepPos, B, 2);
   prep_kernel<<<grid, kPrepThreads, smem, as_stream(stream)>>>(
@@ -276,11 +274,9 @@ extern "C" int ipsr_compact_rows(const float* ref, int B, int C, int N, const in
                "ipsr_compact_rows: need C %% 64 == 0 and N %% 128 == 0 (C=%d N=%d)", C, N);
   const size_t smem = (size_t)C * 33 * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_compact_rows: C=%d too large", C);
-  static size_t configured = 0;
-  if (smem + 2048 > 48 * 1024 && smem > configured) {   // dynamic + static shared memory above the default limit
+  if (smem + 2048 > 48 * 1024) {   // dynamic + static shared memory above the default limit (set per call: the attribute is per device)
     cudaError_t e = cudaFuncSetAttribute(compact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "compact_rows smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   compact_rows_kernel<<<dim3(N / kPrepPos, B), kPrepThreads, smem, as_stream(stream)>>>(
       ref, C, N, list, nlist, rscale, reinterpret_cast<uint8_t*>(c_tiles));

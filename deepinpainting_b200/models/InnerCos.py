@@ -51,7 +51,7 @@ class InnerCos(nn.Module):
         if not self.skip:
             self.bs = in_data.size(0)
             self.c = in_data.size(1) if self._c_limit is None else min(self._c_limit, in_data.size(1))
-            self.former = in_data
+            self.former = in_data if self._c_limit is None else in_data.narrow(1, 0, self.c)   # InnerCos2.py:38
             mask = self.mask if self.mask.device == in_data.device else self.mask.to(in_data.device)
             self.loss = _InnerCosLoss.apply(in_data, mask, self.target, float(self.strength), self.crit, self._c_limit)
             self.output = in_data
@@ -59,6 +59,12 @@ class InnerCos(nn.Module):
             self.loss = 0
             self.output = in_data
         return self.output
+
+    @property
+    def former_in_mask(self):
+        """``torch.mul(self.former, self.mask)`` of the reference (InnerCos.py:33): kept as an attribute for the contract,
+        materialised only when somebody reads it (the loss kernel never writes the product to memory)."""
+        return torch.mul(self.former, self.mask.to(self.former.dtype))
 
     def backward(self, retain_graph=True):
         if not self.skip:

@@ -7,6 +7,7 @@ CUDA tensors and the library must load.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import weakref
 from dataclasses import dataclass
 from typing import Optional
@@ -23,10 +24,25 @@ config = {
     "tol_rel": -1.0,              # < 0: library default (5e-5 * ||R[q]||)
     "tol_abs": -1.0,
     "psplit": 0,                  # <= 0: auto
-    "exc_cap_factor": 32,         # exception capacity = factor * N entries (8 bytes each) per image: signed inputs make a few
-                                  # images chaotic (tens of thousands of attention entries survive the int64 store); beyond
-                                  # the capacity the backward replays the recurrence per column (correct, ~10x slower)
+    "exc_cap_factor": 32,         # exception POOL of the batch = factor * N * B + M * min(M, N) entries (8 bytes each): signed
+                                  # inputs make a few images chaotic (tens of thousands of attention entries survive the int64
+                                  # store); they borrow the room of the others, and one image can always be fully chaotic.
+                                  # Only when the whole pool is exhausted does the backward of the images that found no room
+                                  # replay the recurrence per column (correct, slow)
 }
+
+EXC_REPLAY = 0x3FFFFFFF           # exc_total[b] >= this: the lists of image b are unusable, the backward replays
+
+
+def exc_pool_entries(B: int, N: int, M: int) -> int:
+    """Capacity of the exception pool of one call (entries of 8 bytes)."""
+    if M <= 1:
+        return 0
+    f = float(config["exc_cap_factor"])
+    shared = min(int(f * N * B), 1 << 26)
+    single = min(M * min(M, N), 1 << 26) if f >= 1 else 0      # (tests shrink the pool with factors < 1)
+    return max(1, shared + single)
+
 
 
 def _stream_ptr(device) -> int:
@@ -167,71 +183,157 @@ class ShiftSaved:
     exc_cnt: Optional[torch.Tensor] = None
     exc_l: Optional[torch.Tensor] = None
     exc_w: Optional[torch.Tensor] = None
-    exc_total: Optional[torch.Tensor] = None
-    exc_cap: int = 0
+    exc_total: Optional[torch.Tensor] = None    # [B] entries per image (>= EXC_REPLAY: replay); view of exc_state
+    exc_state: Optional[torch.Tensor] = None    # [2B + 2]: counts, bases inside the pool, pool cursor
+    exc_cap: int = 0                            # pool capacity (entries, shared by the batch)
     nrecheck: Optional[torch.Tensor] = None
     npass2: Optional[torch.Tensor] = None
     m_count: Optional[torch.Tensor] = None      # per-image masks: mask_idx is [B, N], m_count [B]
 
+    def exceptions_of(self, b: int):
+        """(positions q_l, truncated weights) of the attention entries of image ``b`` that survive the reference's int64
+        store (rows l >= 1), or None when the image's lists are unusable and the backward replays (host sync: tests)."""
+        if self.exc_state is None:
+            return (torch.empty(0, dtype=torch.int32, device=self.ind.device),
+                    torch.empty(0, dtype=torch.float32, device=self.ind.device))
+        st = self.exc_state.cpu()
+        n, base = int(st[b]), int(st[self.B + b])
+        if n >= EXC_REPLAY:
+            return None
+        return self.exc_l[base:base + n], self.exc_w[base:base + n]
 
-class _Call:
-    """Owns the argument struct and every buffer of one forward call."""
 
-    def __init__(self, x, ref, mi: MaskIndex, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics,
-                 events=None):
-        B, Cc, H, W = x.shape
-        N = H * W
-        dev = x.device
-        M = mi.M
+def _carve(blob: torch.Tensor, layout, name):
+    off, shape, dtype = layout[name]
+    n = 1
+    for d in shape:
+        n *= d
+    return blob[off:off + n * 4].view(dtype).view(shape)
+
+
+class _Plan:
+    """Everything of a forward call that depends only on (device, stream, shape, mask, mode): the workspace, the filled
+    argument struct and the layout of the per-call blob that holds what the backward needs.  Cached per thread, so that
+    a forward through the module API costs two allocations (output + blob) and ONE ctypes call."""
+
+    def __init__(self, dev, B, Cc, H, W, mi: MaskIndex, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics):
+        N, M = H * W, mi.M
         if mi.batched:
             if tuple(mi.flag.shape) != (B, N):
                 raise ValueError("per-image flags are %s but the batch is %d images of %d positions" % (tuple(mi.flag.shape), B, N))
         elif mi.flag.numel() != N:
             raise ValueError("flag has %d entries but the feature map has %d positions" % (mi.flag.numel(), N))
-        self.out = torch.empty_like(x)
-        self.saved = ShiftSaved(B=B, C=Cc, H=H, W=W, M=M,
-                                ind=torch.empty((B, N), dtype=torch.int32, device=dev),
-                                wn=torch.empty((B, max(M, 1)), dtype=torch.float32, device=dev),
-                                wo=torch.empty((B, max(M, 1)), dtype=torch.float32, device=dev),
-                                mask_idx=mi.mask_idx, m_count=mi.m_count)
-        s = self.saved
+        self.B, self.C, self.H, self.W, self.M, self.N = B, Cc, H, W, M, N
+        self.mi, self.need_grad, self.diagnostics = mi, need_grad, diagnostics
+        Mr = max(M, 1)
+        layout, cur = {}, 0
+
+        def add(name, shape, dtype):
+            nonlocal cur
+            n = 1
+            for d in shape:
+                n *= d
+            layout[name] = (cur, shape, dtype)
+            cur += (n * 4 + 255) & ~255
+
+        add("ind", (B, N), torch.int32)
+        add("wn", (B, Mr), torch.float32)
+        add("wo", (B, Mr), torch.float32)
+        self.exc_cap = 0
         if need_grad:
-            s.route_ptr = torch.empty((B, N + 1), dtype=torch.int32, device=dev)
-            s.route_q = torch.empty((B, N), dtype=torch.int32, device=dev)
+            add("route_ptr", (B, N + 1), torch.int32)
+            add("route_q", (B, N), torch.int32)
             if M > 1:
-                s.exc_cap = max(1, int(config["exc_cap_factor"] * N))
-                s.exc_start = torch.empty((B, N), dtype=torch.int32, device=dev)
-                s.exc_cnt = torch.empty((B, N), dtype=torch.int32, device=dev)
-                s.exc_l = torch.empty((B, s.exc_cap), dtype=torch.int32, device=dev)
-                s.exc_w = torch.empty((B, s.exc_cap), dtype=torch.float32, device=dev)
-                s.exc_total = torch.empty((B,), dtype=torch.int32, device=dev)
+                self.exc_cap = exc_pool_entries(B, N, M)
+                add("exc_start", (B, N), torch.int32)
+                add("exc_cnt", (B, N), torch.int32)
+                add("exc_state", (2 * B + 2,), torch.int32)
+                add("exc_l", (self.exc_cap,), torch.int32)
+                add("exc_w", (self.exc_cap,), torch.float32)
         if diagnostics:
-            s.nrecheck = torch.empty((B,), dtype=torch.int32, device=dev)
-            s.npass2 = torch.zeros((B,), dtype=torch.int32, device=dev)
+            add("nrecheck", (B,), torch.int32)
+            add("npass2", (B,), torch.int32)
+        self.layout, self.blob_bytes = layout, cur
         lib = _lib.load()
         mode_id = _lib.MODES[mode]
-        nbytes = lib.ipsr_workspace_bytes(B, Cc, H, W, M, mode_id)
-        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        self.workspace_bytes = lib.ipsr_workspace_bytes(B, Cc, H, W, M, mode_id)
+        self.workspace = torch.empty((self.workspace_bytes,), dtype=torch.uint8, device=dev)
         a = _lib.FwdArgs()
-        a.x, a.ref = x.data_ptr(), ref.data_ptr()
         a.flag, a.mask_idx, a.rank = mi.flag.data_ptr(), _ptr(mi.mask_idx) if M else None, mi.rank.data_ptr()
         a.B, a.C, a.H, a.W, a.M = B, Cc, H, W, M
         a.mode, a.need_grad = mode_id, int(bool(need_grad))
         a.col_begin, a.col_end, a.stop_after_corr = int(col_begin), int(col_end), int(bool(stop_after_corr))
-        a.psplit, a.exc_cap = int(config["psplit"]), s.exc_cap
+        a.exc_cap = self.exc_cap
+        a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace_bytes
+        a.mask_stride, a.m_count = (N, mi.m_count.data_ptr()) if mi.batched else (0, None)
+        self.args = a
+
+
+_plans = threading.local()
+PLAN_CACHE_SIZE = 16
+
+
+def _plan_for(x, mi, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics) -> _Plan:
+    B, Cc, H, W = x.shape
+    dev = x.device
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, B, Cc, H, W, id(mi), bool(need_grad), mode, int(col_begin),
+           int(col_end), bool(stop_after_corr), bool(diagnostics))
+    cache = getattr(_plans, "cache", None)
+    if cache is None:
+        cache = _plans.cache = {}
+    plan = None if capturing else cache.get(key)      # a workspace captured into a CUDA graph belongs to that graph
+    if plan is not None and plan.mi is mi:
+        return plan
+    plan = _Plan(dev, B, Cc, H, W, mi, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics)
+    if not capturing:
+        if len(cache) >= PLAN_CACHE_SIZE:
+            cache.pop(next(iter(cache)))
+        cache[key] = plan
+    return plan
+
+
+class _Call:
+    """One forward call: the output, the blob with what the backward needs, and the plan's argument struct pointed at them."""
+
+    def __init__(self, x, ref, mi: MaskIndex, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics,
+                 events=None):
+        plan = _plan_for(x, mi, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics)
+        dev = x.device
+        self.plan = plan
+        self.out = torch.empty_like(x)
+        blob = torch.empty((plan.blob_bytes,), dtype=torch.uint8, device=dev)
+        lay = plan.layout
+        s = ShiftSaved(B=plan.B, C=plan.C, H=plan.H, W=plan.W, M=plan.M, ind=_carve(blob, lay, "ind"), wn=_carve(blob, lay, "wn"),
+                       wo=_carve(blob, lay, "wo"), mask_idx=mi.mask_idx, m_count=mi.m_count, exc_cap=plan.exc_cap)
+        if "route_ptr" in lay:
+            s.route_ptr, s.route_q = _carve(blob, lay, "route_ptr"), _carve(blob, lay, "route_q")
+        if "exc_state" in lay:
+            s.exc_start, s.exc_cnt = _carve(blob, lay, "exc_start"), _carve(blob, lay, "exc_cnt")
+            s.exc_l, s.exc_w = _carve(blob, lay, "exc_l"), _carve(blob, lay, "exc_w")
+            s.exc_state = _carve(blob, lay, "exc_state")
+            s.exc_total = s.exc_state[:plan.B]
+        if "nrecheck" in lay:
+            s.nrecheck, s.npass2 = _carve(blob, lay, "nrecheck"), _carve(blob, lay, "npass2")
+            s.npass2.zero_()
+        self.saved = s
+        a = plan.args
+        a.x, a.ref = x.data_ptr(), ref.data_ptr()
+        a.psplit = int(config["psplit"])
         a.tol_rel, a.tol_abs = float(config["tol_rel"]), float(config["tol_abs"])
         a.out, a.ind, a.wn, a.wo = self.out.data_ptr(), s.ind.data_ptr(), s.wn.data_ptr(), s.wo.data_ptr()
         a.route_ptr, a.route_q = _ptr(s.route_ptr), _ptr(s.route_q)
         a.exc_start, a.exc_cnt, a.exc_l, a.exc_w, a.exc_total = (_ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l),
-                                                               _ptr(s.exc_w), _ptr(s.exc_total))
+                                                               _ptr(s.exc_w), _ptr(s.exc_state))
         a.nrecheck_out = _ptr(s.nrecheck)
         a.npass2_out = _ptr(s.npass2)
         if events is not None:                       # (begin, end) torch.cuda.Event pair, already materialised
             a.ev_corr_begin, a.ev_corr_end = events[0].cuda_event, events[1].cuda_event
-        a.workspace, a.workspace_bytes = self.workspace.data_ptr(), nbytes
-        a.mask_stride, a.m_count = (N, mi.m_count.data_ptr()) if mi.batched else (0, None)
+        else:
+            a.ev_corr_begin, a.ev_corr_end = None, None
         self.args = a
-        self.keep = (x, ref, mi)
+        self.workspace = plan.workspace
+        self.keep = (x, ref, mi, blob)
         self.device = dev
 
     def packed_keys(self) -> torch.Tensor:
@@ -252,7 +354,7 @@ def shift_forward(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, need_grad: 
         raise AssertionError("Input Dim has to be 4")
     if ref.shape != x.shape:
         raise ValueError("ref.relu4_3 %s must have the shape of the input %s" % (tuple(ref.shape), tuple(x.shape)))
-    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], 0, 0, False, diagnostics, events)
+    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], 0, -1, False, diagnostics, events)
     _lib.call("ipsr_shift_forward", C.byref(call.args), _stream_ptr(x.device))
     return call.out, call.saved
 
@@ -306,7 +408,7 @@ def patch_grid(H: int, W: int, patch: int, stride: int):
 
 
 def shift_forward_patches(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, patch: int, stride: int,
-                          mode: Optional[str] = None, col_begin: int = 0, col_end: int = 0, reduce_max=None):
+                          mode: Optional[str] = None, col_begin: int = 0, col_end: int = -1, reduce_max=None):
     """models/IPSRFunction.py:46-133 for shift_sz = patch, stride = stride -- FORWARD ONLY (the reference computes
     the output and then fails at :134; its backward is undefined for these settings).  ``mi`` holds the flag
     vectors over the nH x nW patch positions (util.cal_mask_given_mask_thred with the same patch / stride).
@@ -358,9 +460,10 @@ def shift_forward_patches(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, pat
     rlist = torch.empty((B, P), dtype=torch.int32, device=dev)
     nrow = torch.empty((B,), dtype=torch.int32, device=dev)
     _lib.call("ipsr_select_all_rows", B, P, rlist.data_ptr(), nrow.data_ptr(), packed.data_ptr(), st)
-    cb, ce = (int(col_begin), int(col_end) if col_end > 0 else P) if sharded else (0, P)
-    _lib.call("ipsr_correlate_argmax_fp32", cols_x.data_ptr(), cols_r.data_ptr(), inv.data_ptr(), B, K, P, cb, ce,
-              rlist.data_ptr(), nrow.data_ptr(), (P + 63) // 64, packed.data_ptr(), st)
+    cb, ce = (int(col_begin), P if (col_end < 0 or (col_end == 0 and col_begin == 0)) else int(col_end)) if sharded else (0, P)
+    if cb < ce:                                   # an empty shard (more ranks than columns) contributes identity keys
+        _lib.call("ipsr_correlate_argmax_fp32", cols_x.data_ptr(), cols_r.data_ptr(), inv.data_ptr(), B, K, P, cb, ce,
+                  rlist.data_ptr(), nrow.data_ptr(), (P + 63) // 64, packed.data_ptr(), st)
     if sharded:
         reduce_max(packed)
     ind = torch.empty((B, P), dtype=torch.int32, device=dev)
@@ -401,7 +504,7 @@ def shift_backward(grad_out: torch.Tensor, saved: ShiftSaved, triple_w: float) -
     gin = torch.empty_like(g)
     N = s.H * s.W
     _lib.call("ipsr_shift_bwd_masks", g.data_ptr(), s.B, s.C, N, s.M, s.route_ptr.data_ptr(), s.route_q.data_ptr(),
-              _ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l), _ptr(s.exc_w), _ptr(s.exc_total), s.exc_cap,
+              _ptr(s.exc_start), _ptr(s.exc_cnt), _ptr(s.exc_l), _ptr(s.exc_w), _ptr(s.exc_state), s.exc_cap,
               s.ind.data_ptr(), _ptr(s.mask_idx) if s.M else None, s.wn.data_ptr(), s.wo.data_ptr(),
               float(triple_w), gin.data_ptr(), N if s.m_count is not None else 0, _ptr(s.m_count), _stream_ptr(g.device))
     return gin

@@ -22,6 +22,15 @@ def _device_of(t: torch.Tensor):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _require_binary(m: torch.Tensor, name: str) -> None:
+    """The reference box-filters / sums ``mask.float()`` as given; the device kernels work on 0/1 masks in exact integer
+    arithmetic.  Soft masks would silently give other flags, so they are refused (one host sync per NEW mask)."""
+    if m.dtype == torch.bool:
+        return
+    if bool(((m != 0) & (m != 1)).any()):
+        raise ValueError("%s must hold only 0 / 1 values (soft masks are not supported by the device mask kernels)" % name)
+
+
 def cal_feat_mask(inMask, conv_layers, threshold):
     """util/util.py:68-84.  inMask [1,1,S,S] (bool / byte / float) -> ByteTensor [1,1,S>>L,S>>L]
     holding 1 where the L-times box-filtered mask exceeds ``threshold``."""
@@ -29,6 +38,7 @@ def cal_feat_mask(inMask, conv_layers, threshold):
     assert inMask.size(0) == 1, "the first dimension must be 1 for mask"
     dev = _device_of(inMask)
     m2 = inMask.to(dev)[0, 0]
+    _require_binary(m2, "inMask")
     out = shift_ops.feat_mask(m2, conv_layers, threshold)
     return out.view(1, 1, out.size(0), out.size(1))
 
@@ -58,11 +68,13 @@ def cal_mask_given_mask_thred(img, mask, patch_size, stride, mask_thred):
     assert img.dim() == 3, 'img has to be 3 dimenison!'
     assert mask.dim() == 2, 'mask has to be 2 dimenison!'
     dev = _device_of(mask)
+    _require_binary(mask, "mask")
     m8 = (mask.to(dev) != 0).to(torch.uint8).contiguous()
     H, W = img.size(1), img.size(2)
     if (m8.size(0), m8.size(1)) != (H, W):
         raise ValueError("mask %s does not match the feature map %dx%d" % (tuple(m8.shape), H, W))
-    mi = shift_ops.build_flags(m8, patch_size, stride, mask_thred)
+    # the window sums are integers: sum >= mask_thred  <=>  sum >= ceil(mask_thred)   (util/util.py:113-118)
+    mi = shift_ops.build_flags(m8, patch_size, stride, int(math.ceil(mask_thred)))
     N = mi.flag.numel()
     flag = mi.flag.long()
     shift_ops.register_mask_index(flag, mi)       # lets IPSRFunction.apply reuse the device vectors

@@ -38,6 +38,8 @@ extern "C" {
 
 const char* ipsr_last_error_string(void);
 int ipsr_version(void);
+/* sizeof(ipsr_fwd_args) as this library was compiled: a binding checks its own mirror of the struct against it. */
+int ipsr_abi_fwd_args_bytes(void);
 /* 1 when (C, N) can run on the tcgen05 path (C % 64 == 0, N % 128 == 0, N <= 65536). */
 int ipsr_tensor_path_supported(int C, int N);
 /* 1 when the tensor path of ipsr_shift_forward runs the precision cascade (single pass + three-pass split on the
@@ -238,10 +240,13 @@ int ipsr_build_routes(const int32_t* ind, const int32_t* flag, const int32_t* ma
                       int B, int N, int M, int32_t* route_ptr, int32_t* route_q, void* stream);
 
 /* Replay the attention rows (:123-125: row_l = row_{l-1}*wn_l; row_l[p_l] += wo_l) per bank
- * column and emit every entry of rows l >= 1 that survives the float -> int64 store:
- * exc_start/exc_cnt [B][N], exc_l / exc_w [B][exc_cap] (exc_l holds the POSITION q_l = mask_idx[l] of the row the
- * entry belongs to, exc_w its truncated weight), exc_total [B] (zero on entry;
- * > exc_cap afterwards means the lists are incomplete and the backward replays instead). */
+ * column and emit every entry of rows l >= 1 that survives the float -> int64 store.  The entries of the WHOLE BATCH
+ * share one pool exc_l / exc_w [exc_cap] (exc_l holds the POSITION q_l = mask_idx[l] of the row the entry belongs to,
+ * exc_w its truncated weight): image b reserves the contiguous range [base_b, base_b + count_b) with one atomic on
+ * the pool cursor, so a chaotic image borrows the room the others do not need.  exc_start / exc_cnt [B][N]: range of
+ * column p inside its image's range.  exc_total is the exception STATE, int32 [2B + 2], zero on entry:
+ *   [b] = count_b (>= 0x3FFFFFFF: the lists of image b are unusable -- pool exhausted or non-finite weights -- and
+ *   the backward replays the recurrence for that image), [B + b] = base_b, [2B] = pool cursor. */
 int ipsr_build_exceptions(const int32_t* ind, const int32_t* mask_idx, const float* wn, const float* wo,
                           int B, int N, int M, int32_t* exc_start, int32_t* exc_cnt,
                           int32_t* exc_l, float* exc_w, int32_t* exc_total, int exc_cap, void* stream);
@@ -266,7 +271,7 @@ int ipsr_shift_bwd_masks(const float* g, int B, int C, int N, int M,
 
 /* ipsr_paste (+ ipsr_build_routes) + ipsr_build_exceptions as ONE launch (independent once the scan has
  * finished; the latency-bound builders overlap the bandwidth-bound paste).  route_ptr == NULL: the routes
- * were already built (ipsr_blend_stage_with_routes).  exc_total must be zero on entry. */
+ * were already built (ipsr_blend_stage_with_routes).  exc_total ([2B + 2] state) must be zero on entry. */
 int ipsr_paste_with_bookkeeping(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
                                 const int32_t* flag, const int32_t* mask_idx, const float* wn, const float* wo,
                                 int B, int C, int N, int M, float* out,
@@ -335,7 +340,8 @@ typedef struct ipsr_fwd_args {
   int32_t B, C, H, W, M;
   int32_t mode;            /* IPSR_MODE_*                                                */
   int32_t need_grad;       /* build backward routes / exceptions                         */
-  int32_t col_begin, col_end; /* bank column shard; 0, N for the whole bank              */
+  int32_t col_begin, col_end; /* bank column shard [begin, end); end < 0 (or 0, 0): the whole bank; begin == end > 0: an
+                               * EMPTY shard (stop_after_corr only): identity keys for the exchange */
   int32_t stop_after_corr; /* bank-sharded mode: stop after (b,c) with packed keys ready */
   int32_t psplit;          /* column splits per row tile on the tensor path (<=0: auto)  */
   int32_t exc_cap;
@@ -347,8 +353,8 @@ typedef struct ipsr_fwd_args {
   int32_t* route_ptr;      /* [B,N+1]                                                    */
   int32_t* route_q;        /* [B,N]                                                      */
   int32_t* exc_start; int32_t* exc_cnt;   /* [B,N]                                       */
-  int32_t* exc_l; float* exc_w;           /* [B,exc_cap]                                 */
-  int32_t* exc_total;      /* [B]                                                        */
+  int32_t* exc_l; float* exc_w;           /* [exc_cap] pool shared by the batch          */
+  int32_t* exc_total;      /* [2B+2] exception state (ipsr_build_exceptions)             */
   int32_t* nrecheck_out;   /* [B] optional: rows that took the exact path (diagnostics)  */
   int32_t* npass2_out;     /* [B] optional: rows redone by the three-pass split          */
   void* ev_corr_begin;     /* optional cudaEvent_t pair recorded on `stream` around the      */

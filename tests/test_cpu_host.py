@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ipsr_version() == 100
+    assert lib.ipsr_version() == 200
     assert isinstance(_lib.last_error(), str)
 
 
