@@ -19,9 +19,9 @@ layer and cannot travel to the GPU box; the pinned numpy port of it in oracle/ s
 """
 import argparse
 import json
+import math
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -242,28 +242,17 @@ def workload_config(B, C, H, world, mode):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def measure(args, B, C, H, K, W_, world, rank, local, dev, dist, pk, with_cpu, e2e_seconds):
+    """One workload (batch B per GPU, C channels, H x H map, centre mask) on this rank; collective-free except for the
+    barriers / MAX reductions of the timing contract.  Returns the fields of the JSON line (rank 0) or None."""
     import collections
-    import numpy as np
     import torch
-    import torch.distributed as dist
     from deepinpainting_b200 import shift_ops
-    from deepinpainting_b200 import _lib as _lib_mod
+    from deepinpainting_b200 import _lib as L
+    from deepinpainting_b200.graphed import GraphedShiftStep
     from deepinpainting_b200.models import IPSR_model
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    B, C, H = args.batch, args.channels, args.size
     N = H * H
-    shift_ops.config["correlation_mode"] = args.mode
     flag = centre_flag(H, H)
     M = int(flag.sum())
     mi = shift_ops.mask_index_from_flag(torch.from_numpy(flag), dev)
@@ -322,8 +311,21 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(v)]
+        outl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outl, t)
+        return [float(o.item()) for o in outl]
+
     # ---- warm-up, then EXACTLY K timed steps ----
-    W_, K = max(3, args.warmup), args.steps
     for i in range(W_):
         step(i)
     sync_all()
@@ -337,12 +339,8 @@ def run_ours(args):
     sync_all()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
-    if world > 1:
-        sys.stderr.write("rank %d: %.3f ms per step on the device\n" % (rank, ms / K))
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    per_rank_ms = gather_ranks(ms / K)
+    ms_max = max_over_ranks(ms)
     value = world * B * K / (ms_max * 1e-3)
 
     # ---- live roofline of the correlation kernel: event pairs recorded by the library around it ----
@@ -357,28 +355,30 @@ def run_ours(args):
         step_eager(i, events=pairs[i])
     torch.cuda.synchronize()
     corr_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in pairs)
-    pk = peaks()
     tensor_mode = args.mode == "tensor" or (args.mode == "auto" and C % 64 == 0 and N % 128 == 0)
-    cascade = tensor_mode and _lib_mod.load().ipsr_tensor_cascade(B, C, N) == 1
+    cascade = tensor_mode and L.load().ipsr_tensor_cascade(B, C, N) == 1
     flops = 2.0 * N * N * C * B                                    # algorithmic: one N x N x C correlation per image
     achieved = flops / (corr_ms * 1e-3) / 1e12
-    traffic = None                                                 # DRAM bytes per launch from the committed ncu --set full capture
-    tj_all = {}
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath) and (B, C, H) == (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"]):
-        with open(tpath) as fh:
-            tj_all = json.load(fh)
-        traffic = next((v for k, v in tj_all.items() if "corr_tc" in k), None) if tensor_mode else None
-    tpath_b = os.path.join(ROOT, "profiles", "roofline_traffic_configB.json")      # configs[2]: the pass-1 launch
-    if os.path.exists(tpath_b) and (B, C, H) == (64, 256, 64) and tensor_mode:
-        with open(tpath_b) as fh:
-            traffic = next((v for k, v in json.load(fh).items() if "pass 1" in k), None)
+    # DRAM bytes per launch: NOT measured in this run -- read from the committed ncu --set full capture of the same
+    # command line (profiles/), the source is named in the line
+    traffic, traffic_src, tj_all = None, None, {}
+    for fname, shape, pick in (("roofline_traffic.json", (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"]), "corr_tc"),
+                               ("roofline_traffic_configB.json", (64, 256, 64), "pass 1")):
+        tpath = os.path.join(ROOT, "profiles", fname)
+        if os.path.exists(tpath) and (B, C, H) == shape:
+            with open(tpath) as fh:
+                tj_all = json.load(fh)
+            if tensor_mode:
+                traffic = next((v for k, v in tj_all.items() if pick in k), None)
+                traffic_src = "profiles/" + fname + " (ncu --set full capture of this command, committed; not re-measured in this run)"
+    peak_tf = pk["tf_burst"]                                      # the kernel is timed alone by its own event pair: burst peak
     roofline = {"bound": "tensor", "kernel": ("corr_tc_kernel pass 1 (tcgen05 fp16 hi*hi over every row; ambiguous rows are redone by the 3-pass split)" if cascade else "corr_tc_kernel (tcgen05 fp16, 3-pass split hi*lo + lo*hi + hi*hi over every row: small problem, ceiling = 1/3 of peak)") if tensor_mode else "corr_fp32_kernel (FFMA)",
-                "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": traffic, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "frac_of_sustained_peak": achieved / pk["tf_sustained"],
+                "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
                 "issued_passes": (1 if cascade else 3) if tensor_mode else 1,
-                "tensor_pipe_utilisation": (achieved * ((1 if cascade else 3) if tensor_mode else 1)) / pk["tf_sustained"],
-                "peak_source": pk["source"] + " bf16 dense, sustained",
+                "tensor_pipe_utilisation": (achieved * ((1 if cascade else 3) if tensor_mode else 1)) / peak_tf,
+                "peak_source": pk["source"] + " bf16 dense, burst (kernel timed alone by its own event pair)",
                 "note": "achieved = algorithmic FLOPs (2*N^2*C per image) / time of the timed correlation launch (event pair recorded by the library around it); tensor_pipe_utilisation counts the MMA passes actually issued (3 for the split over every row that small problems run, 1 for pass 1 of the cascade)"}
 
     # ---- workload diagnostics (one eager step): rows deferred to the exact path, attention entries that survive the
@@ -386,9 +386,12 @@ def run_ours(args):
     _, dsaved = shift_ops.shift_forward(sets[0][0], sets[0][1], mi, need_grad=True, diagnostics=True)
     torch.cuda.synchronize()
     rp = dsaved.route_ptr.long()
+    et = dsaved.exc_total
     diag = {"recheck_rows_per_image": float(dsaved.nrecheck.float().mean()),
-            "exceptions_per_image_mean": float(dsaved.exc_total.float().mean()) if dsaved.exc_total is not None else 0.0,
-            "exceptions_per_image_max": int(dsaved.exc_total.max()) if dsaved.exc_total is not None else 0,
+            "exceptions_per_image_mean": float(et.float().mean()) if et is not None else 0.0,
+            "exceptions_per_image_max": int(et.max()) if et is not None else 0,
+            "exception_pool_entries": int(dsaved.exc_cap),
+            "images_replaying": int((et >= shift_ops.EXC_REPLAY).sum()) if et is not None else 0,
             "three_pass_rows_per_image": float(dsaved.npass2.float().mean()),
             "exception_columns_per_image": float((dsaved.exc_cnt > 0).float().sum(1).mean()) if dsaved.exc_cnt is not None else 0.0,
             "max_routes_per_column": int((rp[:, 1:] - rp[:, :-1]).max())}
@@ -406,7 +409,6 @@ def run_ours(args):
         torch.cuda.synchronize()
         return a_.elapsed_time(b__) / reps
 
-    from deepinpainting_b200 import _lib as L
     st = torch.cuda.current_stream().cuda_stream
     f32 = dict(dtype=torch.float32, device=dev)
     k_inv, k_rn = torch.empty(B, N, **f32), torch.empty(B, N, **f32)
@@ -441,125 +443,177 @@ def run_ours(args):
     t_prep, t_paste, t_bwd = time_call(run_prep), time_call(run_paste), time_call(run_bwd)
     nc4 = B * N * C * 4
     kernels = []
-    for name, ms_, byts in (("prep_kernel (a)", t_prep, 2 * nc4 + nc4 + (2 * nc4 if tiles_ok else 0) + B * M * C * 4),
-                            ("paste_kernel (d)", t_paste, 2 * nc4),
-                            ("shift_bwd_kernel (e)", t_bwd, 2 * nc4)):
+    # algorithmic bytes per SURVEY 8(d): (a) reads x and ref (8NC) and writes their fp16 hi/lo operand images (8NC);
+    # (d), (e) read one map and write one
+    for name, ms_, byts, moved in (("prep_kernel (a)", t_prep, 4 * nc4, 2 * nc4 + nc4 + (2 * nc4 if tiles_ok else 0) + B * M * C * 4),
+                                   ("paste_kernel (d)", t_paste, 2 * nc4, 2 * nc4),
+                                   ("shift_bwd_kernel (e)", t_bwd, 2 * nc4, 2 * nc4)):
         gbs = byts / (ms_ * 1e-3) / 1e9
-        kernels.append({"kernel": name, "bound": "hbm", "ms": ms_, "algorithmic_bytes": byts, "achieved": gbs,
+        kernels.append({"kernel": name, "bound": "hbm", "ms": ms_, "algorithmic_bytes": byts, "bytes_moved": moved, "achieved": gbs,
                         "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                         "traffic": next((v for k, v in tj_all.items() if name.split("_kernel")[0] in k), None)})
 
-    # ---- e2e: reference-shaped module API, host pinned buffers, H2D + D2H inside the timed region ----
+    # ---- e2e: the module API with HOST (pinned) buffers, H2D + D2H inside the timed region ----
+    # Two pinned host buffer sets and two device buffer sets: copy-in of step i+1, compute of step i and copy-out of step
+    # i-1 overlap on three streams (H2D and D2H use separate copy engines).  Three legs over the same buffers:
+    #   graphed  IPSR_model forward + autograd backward captured once per buffer set (deepinpainting_b200.graphed) -- e2e.value
+    #   eager    the same through plain module calls (Python + ~12 launches per step)
+    #   copies   the H2D / D2H copies alone: the ceiling the link (and the host memory system) sets
     Ref = collections.namedtuple("Ref", ["relu4_3"])
-    layer = IPSR_model(5 / 16.0, 1, 1, 1, 1, 1)
     S = H * 8
     mg = torch.zeros(1, 1, S, S, dtype=torch.bool)
     mg[:, :, S // 4:3 * S // 4, S // 4:3 * S // 4] = True
+    layer = IPSR_model(5 / 16.0, 1, 1, 1, 1, 1)
     layer.set_mask(mg.to(dev), 3, 5 / 16.0)
-    # two pinned host buffer sets and two device buffer sets: copy-in of step i+1, compute of step i and
-    # copy-out of step i-1 overlap on three streams (H2D and D2H use separate copy engines)
     hin = [[torch.empty(B, C, H, H).pin_memory() for _ in range(3)] for _ in range(2)]
     hout = [[torch.empty(B, C, H, H).pin_memory() for _ in range(2)] for _ in range(2)]
-    din = [[torch.empty(B, C, H, H, device=dev) for _ in range(3)] for _ in range(2)]
     for k in range(2):
         for j in range(3):
             hin[k][j].copy_(sets[k % pool][j])
+    steppers = None
+    if args.graphs:
+        try:
+            steppers = [GraphedShiftStep(layer, B, C, H, H, dev) for _ in range(2)]
+        except Exception as exc:
+            sys.stderr.write("graphed module path unavailable (%s)\n" % exc)
+    din = [[torch.empty(B, C, H, H, device=dev) for _ in range(3)] for _ in range(2)]
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_cmp = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
     hold = [None, None]
 
-    def e2e_step(i):
+    def e2e_step(i, leg):
         k = i & 1
+        dst = (steppers[k].x, steppers[k].ref, steppers[k].g) if leg == "graphed" else din[k]
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_cmp[k])                      # device inputs of step i-2 are no longer read
             for j in range(3):
-                din[k][j].copy_(hin[k][j], non_blocking=True)
+                dst[j].copy_(hin[k][j], non_blocking=True)
             ev_in[k].record(s_in)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[k])
-            xin = din[k][0].detach().requires_grad_(True)
-            layer.set_ref(Ref(din[k][1]))
-            y = layer(xin)
-            y.backward(din[k][2])
+            if leg == "graphed":
+                s_cmp.wait_event(ev_out[k])                 # the static outputs of step i-2 have been copied out
+                yd, gd = steppers[k].replay()
+            elif leg == "eager":
+                xin = din[k][0].detach().requires_grad_(True)
+                layer.set_ref(Ref(din[k][1]))
+                y = layer(xin)
+                y.backward(din[k][2])
+                yd, gd = y.detach(), xin.grad
+                hold[k] = (y, xin)
+            else:
+                yd, gd = din[k][0], din[k][2]               # copies only
             ev_cmp[k].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[k])
             s_out.wait_event(ev_out[k])                     # host outputs of step i-2 have been written
-            yd, gd = y.detach(), xin.grad
-            yd.record_stream(s_out)
-            gd.record_stream(s_out)
+            if leg == "eager":
+                yd.record_stream(s_out)
+                gd.record_stream(s_out)
             hout[k][0].copy_(yd, non_blocking=True)
             hout[k][1].copy_(gd, non_blocking=True)
             ev_out[k].record(s_out)
-        hold[k] = (y, xin)
 
-    EK = args.e2e_steps or min(K, 200)
-    for i in range(4):
-        e2e_step(i)
-    sync_all()
-    t0 = time.perf_counter()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(s_in)                                         # first operation of the region: the first H2D copy
-    for i in range(EK):
-        e2e_step(i)
-    f1.record(s_out)                                        # last operation: the last D2H copy has landed
-    enqueue = time.perf_counter() - t0                      # host time to ENQUEUE the region (Python + launches)
-    sync_all()
-    wall = time.perf_counter() - t0
-    te = torch.tensor([f0.elapsed_time(f1) * 1e-3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * EK / float(te.item())
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * B * C * N * 4, "d2h_bytes_per_step": 2 * B * C * N * 4,
-           "steps": EK, "wall_s": wall, "host_enqueue_ms_per_step": enqueue / EK * 1e3, "timing": "CUDA events: first H2D copy -> last D2H copy of the region, max over ranks (3 streams overlap H2D / compute / D2H)",
-           "api": "IPSR_model.forward + autograd backward, pinned host buffers"}
+    def e2e_leg(leg, steps):
+        for i in range(4):
+            e2e_step(i, leg)
+        sync_all()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(s_in)                                     # first operation of the region: the first H2D copy
+        for i in range(steps):
+            e2e_step(i, leg)
+        f1.record(s_out)                                    # last operation: the last D2H copy has landed
+        enqueue = time.perf_counter() - t0                  # host time to ENQUEUE the region (Python + launches)
+        sync_all()
+        wall = time.perf_counter() - t0
+        secs = max_over_ranks(f0.elapsed_time(f1) * 1e-3)
+        return {"value": world * B * steps / secs, "steps": steps, "region_s": secs, "wall_s": wall,
+                "host_enqueue_ms_per_step": max_over_ranks(enqueue / steps * 1e3)}
+
+    main_leg = "graphed" if steppers is not None else "eager"
+    pilot = e2e_leg(main_leg, 8)
+    EK = args.e2e_steps or int(min(5000, max(20, math.ceil(e2e_seconds * 8 / max(pilot["region_s"], 1e-6)))))
+    legs = {main_leg: e2e_leg(main_leg, EK)}
+    other = "eager" if main_leg == "graphed" else None
+    if other:
+        legs[other] = e2e_leg(other, max(20, EK // 4))
+    legs["copies_only"] = e2e_leg("copies", max(20, EK // 4))
+    h2d, d2h = 3 * B * C * N * 4, 2 * B * C * N * 4
+    e2e = {"value": legs[main_leg]["value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": legs[main_leg]["steps"], "region_s": legs[main_leg]["region_s"], "wall_s": legs[main_leg]["wall_s"],
+           "host_enqueue_ms_per_step": legs[main_leg]["host_enqueue_ms_per_step"],
+           "api": ("deepinpainting_b200.graphed.GraphedShiftStep: IPSR_model.forward + autograd backward captured into a CUDA graph per buffer set"
+                   if main_leg == "graphed" else "IPSR_model.forward + autograd backward (eager)") + ", pinned host buffers",
+           "eager_module_api": legs.get("eager"),
+           "copies_only_ceiling": dict(legs["copies_only"], gbs_h2d=legs["copies_only"]["value"] / (world * B) * h2d / 1e9,
+                                       gbs_d2h=legs["copies_only"]["value"] / (world * B) * d2h / 1e9,
+                                       note="the same H2D / D2H copies on the same three streams with the layer left out: the ceiling set by the PCIe link and, with several ranks, by the host memory system they share"),
+           "timing": "CUDA events: first H2D copy -> last D2H copy of the region, max over ranks (3 streams overlap H2D / compute / D2H)"}
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_img = args.cpu_images or (1200 if H <= 32 else 40)        # ~10-20 s of CPU work
-        ips, threads, secs = cpu_path_images_per_sec(C, H, H, n_img)
-        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d images of the workload (B=1 each), fwd+bwd, fp32, %.1f s" % (n_img, secs)}
+    if with_cpu and rank == 0 and world == 1:
+        from oracle import ref_runner
+        real = ref_runner.available()
+        n_img = args.cpu_images or ((40 if real else 1200) if H <= 32 else (6 if real else 40))   # ~10-20 s of CPU work
+        ips, threads, secs, kind = cpu_path_images_per_sec(C, H, H, n_img)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "%d images of the workload (B=1 each: the reference loops over the batch), fwd+bwd, fp32, %.1f s" % (n_img, secs)}
 
-    # ---- the metric's second size (BASELINE.json: "at 256^2/512^2"): a short run of configs[2] in a fresh process,
-    # reported next to the headline line (N = 1 only; under torchrun pass --batch 64 --size 64 instead)
-    also = None
-    if (rank == 0 and world == 1 and not args.no_also and (B, C, H) == (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"])
-            and args.mode == "auto"):
-        try:
-            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--batch", "64", "--size", "64", "--steps", "50",
-                                  "--warmup", "5", "--no-cpu-baseline", "--e2e-steps", "20", "--no-also", "--seed", str(args.seed)],
-                                 capture_output=True, text=True, timeout=600)
-            sub = json.loads(res.stdout.strip().splitlines()[-1])
-            also = [{k: sub[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "roofline",
-                                         "e2e", "kernels", "diagnostics", "gpu_launches")}]
-        except Exception as exc:
-            sys.stderr.write("configs[2] leg failed: %s\n" % exc)
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD["name"] if (B, C, H) == (16, 256, 32) else
-                       "shift layer fwd+bwd, batch %d per GPU, %dx%dx%d features, centre mask" % (B, H, H, C),
-                       "batch_per_gpu": B, "global_batch": B * world, "C": C, "H": H, "W": H, "N": N, "M": M,
-                       "parallelism": "batch-sharded x%d, no data-path collective" % world,
-                       "mode": args.mode, "cuda_graphs": graphs is not None,
-                       "correlation": ("fp32 results; tcgen05 fp16 hi/lo split with fp32 accumulation ("
-                                       + ("precision cascade: 1 pass, 3-pass split on the ambiguous rows" if cascade
-                                          else "3-pass split over every row") + "), ties and ambiguous rows resolved in exact fp32")
-                                      if tensor_mode else "fp32 FFMA",
-                       "l2": "rotating pool of %d input sets (%d MB) > 126 MB L2" % (pool, pool * bytes_per_set >> 20)},
+    cfg = workload_config(B, C, H, world, args.mode)
+    cfg.update({"cuda_graphs": graphs is not None,
+                "correlation": ("fp32 results; tcgen05 fp16 hi/lo split with fp32 accumulation ("
+                                + ("precision cascade: 1 pass, 3-pass split on the ambiguous rows" if cascade
+                                   else "3-pass split over every row") + "), ties and ambiguous rows resolved in exact fp32")
+                               if tensor_mode else "fp32 FFMA",
+                "l2": "rotating pool of %d input sets (%d MB) > 126 MB L2" % (pool, pool * bytes_per_set >> 20)})
+    del sets, graphs, steppers, hin, hout, din
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms_max / K, "per_rank_ms_per_step": per_rank_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "diagnostics": diag, "kernels": kernels,
-            "gpu_launches": launches_per_step * K,
-        }
-        if also is not None:
-            line["also"] = also
+            "gpu_launches": launches_per_step * K}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from deepinpainting_b200 import shift_ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    shift_ops.config["correlation_mode"] = args.mode
+    pk = peaks()
+    B, C, H = args.batch, args.channels, args.size
+    line = measure(args, B, C, H, args.steps, max(3, args.warmup), world, rank, local, dev, dist, pk,
+                   with_cpu=not args.no_cpu_baseline, e2e_seconds=1.2)
+    # ---- the metric's second size (BASELINE.json: "at 256^2/512^2 ... 1/2/4/8 B200"): configs[2] (512^2: batch 64 per GPU,
+    # 64x64x256) runs on EVERY rank too, so that the scaling record carries both sizes; reported under "also"
+    if not args.no_also and (B, C, H) == (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"]) and args.mode == "auto":
+        try:
+            sub = measure(args, 64, 256, 64, min(args.steps, 60), 5, world, rank, local, dev, dist, pk, with_cpu=False,
+                          e2e_seconds=1.0)
+            if rank == 0:
+                line["also"] = [sub]
+        except Exception as exc:                                   # the headline line must survive a failure of the extra leg
+            sys.stderr.write("configs[2] leg failed on rank %d: %r\n" % (rank, exc))
+            if world > 1:
+                raise
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -182,14 +182,17 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
                                           grad ? a->route_ptr : nullptr, grad ? a->route_q : nullptr, stream, ms, mcount));
   if (M > 0) IPSR_FORWARD(blend_scan_ex(at<float>(a, w.staged), B, C, M, at<float>(a, w.y), a->wn, a->wo, stream, mcount));
   if (grad && M > 1) {
-    // the exception lists depend on wn / wo only: build them on the side stream while the paste streams x -> out
+    // the exception lists depend on wn / wo only: they are built on the side stream while the paste streams x -> out
+    auto bookkeeping = [&](void* s) -> int {
+      return build_exceptions_ex(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l, a->exc_w,
+                                 a->exc_total, a->exc_cap, s, ms, mcount);
+    };
     SideStream* ss = side_stream();
     cudaStream_t st = as_stream(stream);
     std::unique_lock<std::mutex> in_use;
     if (ss) in_use = std::unique_lock<std::mutex>(ss->use);
     if (ss && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
-      int rc = build_exceptions_ex(a->ind, a->mask_idx, a->wn, a->wo, B, N, M, a->exc_start, a->exc_cnt, a->exc_l, a->exc_w,
-                                   a->exc_total, a->exc_cap, ss->stream, ms, mcount);
+      int rc = bookkeeping(ss->stream);
       const int rc2 = paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms);
       // always join, even after an error, so that a capture in progress is not left forked
       const bool joined = cudaEventRecord(ss->join, ss->stream) == cudaSuccess && cudaStreamWaitEvent(st, ss->join, 0) == cudaSuccess;
@@ -199,9 +202,7 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
     }
     (void)cudaGetLastError();
     if (in_use.owns_lock()) in_use.unlock();
-    return paste_with_bookkeeping_ex(a->x, at<float>(a, w.y), a->ind, a->rank, a->flag, a->mask_idx, a->wn, a->wo, B, C,
-                                     N, M, a->out, nullptr, nullptr, a->exc_start, a->exc_cnt, a->exc_l,
-                                     a->exc_w, a->exc_total, a->exc_cap, stream, ms, mcount);
+    IPSR_FORWARD(bookkeeping(stream));
   }
   return paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms);
 }
@@ -256,6 +257,7 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
     e = cudaMemsetAsync(a->exc_total, 0, ((size_t)2 * B + 2) * sizeof(int32_t), st);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memset: %s", cudaGetErrorString(e));
   }
+
 
   const bool tensor = (mode == IPSR_MODE_TENSOR);
   auto record = [&](void* ev) -> int {

@@ -32,224 +32,220 @@ build_exceptions_kernel(const int* __restrict__ ind, const int* __restrict__ mas
 // ---------------------------------------------------------------------------------------------
 // backward proper
 // ---------------------------------------------------------------------------------------------
-// gin = g + triple_w * W^T g is a COPY of g plus corrections in the few hundred bank columns that receive anything
-// (a non-negative reference concentrates the matches on a few hundred patches).  The kernel therefore streams:
-//   * g is cut into tiles of CT channel rows (CT * N contiguous floats in NCHW; image-major, so the whole tensor is
-//     one sequence of tiles) and every persistent CTA owns a contiguous run of them;
-//   * a tile arrives by ONE bulk async copy (TMA engine) into a ring of shared-memory stages, is corrected IN PLACE
-//     and leaves by ONE bulk async store -- no thread ever copies a byte, loads and stores of neighbouring tiles
-//     overlap the corrections;
-//   * corrections: per image (once per CTA and image) the columns that receive something are listed with their CSR
-//     / exception ranges in shared memory; per tile, phase A sums the routed rows of every (column, channel) pair
-//     into a delta buffer -- one thread per pair for short columns, one warp per pair for hub columns (lane-strided
-//     partial sums in ascending q, then a fixed xor tree): deterministic -- and phase B adds the deltas into the tile
-//     (a column can also be a SOURCE of another column, hence two phases).
-// If the exception lists of an image are unusable (exc_state[b] >= kExcReplay: pool exhausted or non-finite weights,
-// chaotic inputs only) every column of that image replays the recurrence.
-constexpr int kBwdThreads = 512;
-constexpr int kBwdLight = 12;            // entries a single thread sums; heavier columns go to a warp
+// grid = (parts, B): a CTA owns a contiguous range of channel tiles (CT rows each, C % CT == 0) of ONE image and
+// streams them through a two-stage ring of bulk async copies (the CT rows of a tile are contiguous in NCHW), so
+// the copy of tile t+1 overlaps the work on tile t.  Most bank columns receive nothing (a non-negative reference
+// concentrates the matches on a few hundred patches), hence per tile:
+//   (1) copy-out   gin tile = g tile, 16-byte vector stores straight from shared memory;
+//   (2) correct    the columns that do receive something -- a compact list built ONCE per CTA from the CSR and
+//                  the exception directory, so every lane has work -- are recomputed as
+//                  g[:,p] + triple_w (sum of routed rows + weighted exception rows) by one thread each, hub
+//                  columns (hundreds of routes) by whole warps (lane-strided partial sums in ascending q, then a
+//                  fixed xor tree): deterministic.
+// If the exception lists of an image are unusable (exc_total[b] >= kExcReplay: the batch's pool is exhausted or a blend
+// weight is non-finite, chaotic inputs only) every column of that image replays the recurrence.
+constexpr int kBwdLight = 24;            // entries a single thread sums; heavier columns go to a warp
 constexpr int kBwdQueue = 512;
-constexpr int kBwdMaxStages = 8;
 
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int PENDING>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-struct BwdArgs {
-  const float* g; float* gin;
-  int B, C, N, M, CT, ntiles, stages, tiles_per_cta, vec;
-  const int* route_ptr; const int* route_q;
-  const int* exc_start; const int* exc_cnt; const int* exc_l; const float* exc_w; const int* exc_state;
-  const int* ind; const int* mask_idx; const float* wn; const float* wo;
-  float triple_w;
-  int ninfo, nexc_s, ms; const int* mcount;
-};
-
-__global__ void __launch_bounds__(kBwdThreads, 1) shift_bwd_kernel(const BwdArgs a) {
-  extern __shared__ __align__(128) float bwd_smem[];      // ring[stages][CT*N] | delta[CT*N] | spec[N] | rq[N] | info[ninfo] | el[E] | ew[E]
+template <int CT>
+__global__ void __launch_bounds__(CT >= 8 ? 512 : 1024, CT >= 8 ? 2 : 1)
+shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per_cta, const int* __restrict__ route_ptr,
+                 const int* __restrict__ route_q, const int* __restrict__ exc_start, const int* __restrict__ exc_cnt,
+                 const int* __restrict__ exc_l, const float* __restrict__ exc_w, const int* __restrict__ exc_total,
+                 int exc_cap, const int* __restrict__ ind, const int* __restrict__ mask_idx,
+                 const float* __restrict__ wn, const float* __restrict__ wo, float triple_w, float* __restrict__ gin,
+                 int ninfo, int nexc_s, int ms, const int* __restrict__ mcount) {
+  extern __shared__ __align__(128) float bwd_smem[];      // rows[2][CT*N] | spec[N] | info[N] int4 | rq[N] | el[E] | ew[E]
   __shared__ int heavy[kBwdQueue];
   __shared__ int4 heavy_info[kBwdQueue];
   __shared__ int nheavy, nspec_s;
-  __shared__ __align__(8) unsigned long long bars[kBwdMaxStages];
-  const int N = a.N, CT = a.CT, S = a.stages, B = a.B;
-  const int N4 = (N + 3) & ~3;
+  __shared__ __align__(8) unsigned long long bars[2];
+  const int b = blockIdx.y;
+  // per-image masks: mask_idx is [B][ms], mcount[b] steps; M stays the row stride of wn / wo
+  const int Mc = mcount ? mcount[b] : M;
+  if (mask_idx) mask_idx += (size_t)b * ms;
+  const int ntiles = C / CT;
+  const int t0 = blockIdx.x * tiles_per_cta;
+  const int t1 = min(ntiles, t0 + tiles_per_cta);
+  if (t0 >= t1) return;
   const int tile_elems = CT * N;
   const uint32_t tile_bytes = (uint32_t)tile_elems * 4u;
-  float* ring = bwd_smem;
-  float* delta = ring + (size_t)S * tile_elems;
-  int* spec = reinterpret_cast<int*>(delta + (((size_t)tile_elems + 3) & ~(size_t)3));
-  int* rq_s = spec + N4;
-  int4* info = reinterpret_cast<int4*>(rq_s + N4);       // per listed column: first route, routes, first exception, exceptions
-  int* el_s = reinterpret_cast<int*>(info + a.ninfo);
-  float* ew_s = reinterpret_cast<float*>(el_s + a.nexc_s);
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  float* rows0 = bwd_smem;
+  int* spec = reinterpret_cast<int*>(bwd_smem + 2 * (size_t)tile_elems);
+  int4* info = reinterpret_cast<int4*>(spec + ((N + 3) & ~3));      // per listed column: first route, routes, first exception, exceptions
+  int* rq_s = reinterpret_cast<int*>(info + ninfo);                 // the CSR's row list
+  int* el_s = rq_s + N;                                             // exception entries (when they fit)
+  float* ew_s = reinterpret_cast<float*>(el_s + nexc_s);
+  const int nthreads = blockDim.x;
+  const float* gimg = g + (size_t)b * C * N;
+  float* oimg = gin + (size_t)b * C * N;
+  const bool vec = ((N & 3) == 0) && ((reinterpret_cast<uintptr_t>(gimg) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(oimg) & 15) == 0);
 
-  const long long total_tiles = (long long)B * a.ntiles;
-  const long long g0 = (long long)blockIdx.x * a.tiles_per_cta;
-  const int n = (int)max(0ll, min(total_tiles, g0 + a.tiles_per_cta) - g0);
-  if (n <= 0) return;
-  const float* gsrc = a.g + (size_t)g0 * tile_elems;
-  float* gdst = a.gin + (size_t)g0 * tile_elems;
+  auto load_tile = [&](int t, int buf) {                  // executed by thread 0 (bulk) or by everybody (fallback)
+    const float* src = gimg + (size_t)t * tile_elems;
+    float* dst = rows0 + (size_t)buf * tile_elems;
+    if (vec) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(smem_u32(&bars[buf]), tile_bytes);
+        bulk_g2s(smem_u32(dst), src, tile_bytes, smem_u32(&bars[buf]));
+      }
+    } else {
+      for (int i = threadIdx.x; i < tile_elems; i += nthreads) dst[i] = __ldg(src + i);
+    }
+  };
 
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(smem_u32(&bars[s]), 1);
+  if (threadIdx.x == 0) {
+    nheavy = 0;
+    nspec_s = 0;
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
     mbar_fence_init();
   }
   __syncthreads();
-  auto issue_load = [&](int i) {                          // thread 0 only
-    const int s = i % S;
-    mbar_expect_tx(smem_u32(&bars[s]), tile_bytes);
-    bulk_g2s(smem_u32(ring + (size_t)s * tile_elems), gsrc + (size_t)i * tile_elems, tile_bytes, smem_u32(&bars[s]));
-  };
-  if (a.vec && tid == 0)
-    for (int i = 0; i < min(S - 1, n); ++i) issue_load(i);
+  load_tile(t0, 0);
+  if (t0 + 1 < t1) load_tile(t0 + 1, 1);
 
-  // per-image correction program
-  int cur_b = -1, nspec = 0, nh = 0, Mc = 0;
-  bool overflow = false, lists = false;
-  const int* gptr = nullptr; const int* estart = nullptr; const int* ecnt = nullptr;
-  const int* elx = nullptr; const float* ewx = nullptr; const int* mask_idx = nullptr;
-  auto setup = [&](int b) {
-    if (tid == 0) {
-      nheavy = 0;
-      nspec_s = 0;
-    }
-    __syncthreads();
-    Mc = a.mcount ? a.mcount[b] : a.M;
-    mask_idx = a.mask_idx ? a.mask_idx + (size_t)b * a.ms : nullptr;
-    const int ecount = (a.M > 1 && a.exc_state) ? a.exc_state[b] : 0;
-    overflow = ecount >= kExcReplay;
-    lists = ecount > 0 && !overflow;
-    gptr = a.route_ptr + (size_t)b * (N + 1);
-    const int* grq = a.route_q + (size_t)b * N;
-    ecnt = a.exc_cnt ? a.exc_cnt + (size_t)b * N : nullptr;
-    estart = a.exc_start ? a.exc_start + (size_t)b * N : nullptr;
-    const size_t ebase = lists ? (size_t)a.exc_state[B + b] : 0;
-    const int* el = a.exc_l ? a.exc_l + ebase : nullptr;
-    const float* ew = a.exc_w ? a.exc_w + ebase : nullptr;
-    const int etotal = lists ? ecount : 0;
-    const bool exc_in_smem = etotal <= a.nexc_s;
-    for (int p = tid; p < N; p += nthreads) {
-      const int r0 = __ldg(gptr + p), nr = __ldg(gptr + p + 1) - r0;
-      const int ne = lists ? __ldg(ecnt + p) : 0;
-      const int work = nr + ne;
-      if (overflow || work > 0) {
-        const int4 rec = make_int4(r0, nr, lists ? __ldg(estart + p) : 0, ne);
-        bool queued = false;
-        if (work > kBwdLight && !overflow) {
-          const int slot = atomicAdd(&nheavy, 1);
-          if (slot < kBwdQueue) {
-            heavy[slot] = p;
-            heavy_info[slot] = rec;
-            queued = true;
-          }
-        }
-        if (!queued) {
-          const int k = atomicAdd(&nspec_s, 1);
-          spec[k] = p;
-          if (k < a.ninfo) info[k] = rec;
+  // exc_total is the exception state of ipsr_build_exceptions: [b] entries of image b (>= kExcReplay: lists unusable,
+  // replay), [B + b] first entry of image b in the pool shared by the batch
+  const int ecount = ((M > 1) && exc_cnt && exc_total) ? exc_total[b] : 0;
+  const bool has_exc = ecount != 0;
+  const bool overflow = ecount >= kExcReplay;
+  const bool lists = has_exc && !overflow;
+  const size_t ebase = lists ? (size_t)exc_total[gridDim.y + b] : 0;
+  const int* gptr = route_ptr + (size_t)b * (N + 1);
+  const int* grq = route_q + (size_t)b * N;
+  const int* ecnt = exc_cnt + (size_t)b * N;
+  const int* estart = exc_start + (size_t)b * N;
+  const int* el = exc_l + ebase;
+  const float* ew = exc_w + ebase;
+  // the columns that receive something, once per CTA (list order does not affect any sum); their CSR entries and
+  // the image's route / exception lists are staged in shared memory, so that the per-tile work below never waits
+  // on global memory for an index
+  const int etotal = lists ? ecount : 0;
+  const bool exc_in_smem = etotal <= nexc_s;
+  for (int p = threadIdx.x; p < N; p += nthreads) {
+    const int r0 = __ldg(gptr + p), n = __ldg(gptr + p + 1) - r0;
+    const int ne = lists ? __ldg(ecnt + p) : 0;
+    const int work = n + ne;
+    if (overflow || work > 0) {
+      const int4 rec = make_int4(r0, n, lists ? __ldg(estart + p) : 0, ne);
+      bool queued = false;
+      if (work > kBwdLight && !overflow) {
+        const int slot = atomicAdd(&nheavy, 1);
+        if (slot < kBwdQueue) {
+          heavy[slot] = p;
+          heavy_info[slot] = rec;
+          queued = true;
         }
       }
-    }
-    for (int i = tid; i < N; i += nthreads) rq_s[i] = __ldg(grq + i);
-    if (exc_in_smem)
-      for (int i = tid; i < etotal; i += nthreads) {
-        el_s[i] = __ldg(el + i);
-        ew_s[i] = __ldg(ew + i);
+      if (!queued) {
+        const int k = atomicAdd(&nspec_s, 1);
+        spec[k] = p;
+        if (k < ninfo) info[k] = rec;
       }
-    __syncthreads();
-    elx = exc_in_smem ? el_s : el;
-    ewx = exc_in_smem ? ew_s : ew;
-    nspec = nspec_s;
-    nh = min(nheavy, kBwdQueue);
-    cur_b = b;
-  };
-
-  for (int i = 0; i < n; ++i) {
-    const long long gid = g0 + i;
-    const int b = (int)(gid / a.ntiles);
-    if (b != cur_b) setup(b);
-    const int s = a.vec ? i % S : 0;
-    float* grow = ring + (size_t)s * tile_elems;
-    if (a.vec) {
-      mbar_wait(smem_u32(&bars[s]), (uint32_t)(i / S) & 1u);
-    } else {                                               // unaligned tensors: plain loads, one stage
-      for (int e = tid; e < tile_elems; e += nthreads) grow[e] = __ldg(gsrc + (size_t)i * tile_elems + e);
-      __syncthreads();
-    }
-
-    // ---- phase A: deltas (reads the unmodified tile only) ----
-    const int nlight = nspec * CT;
-    for (int it = tid; it < nlight; it += nthreads) {
-      const int ch = it / nspec, k = it - ch * nspec;
-      const int p = spec[k];
-      int4 rec;
-      if (k < a.ninfo) rec = info[k];
-      else rec = make_int4(__ldg(gptr + p), __ldg(gptr + p + 1) - __ldg(gptr + p), lists ? __ldg(estart + p) : 0,
-                           lists ? __ldg(ecnt + p) : 0);
-      const float* row = grow + (size_t)ch * N;
-      float acc = 0.f;
-      for (int r = rec.x; r < rec.x + rec.y; ++r) acc += row[rq_s[r]];
-      for (int e = rec.z; e < rec.z + rec.w; ++e) acc = fmaf(ewx[e], row[elx[e]], acc);
-      if (overflow) {                                      // rare, slow, bit-faithful replay of the recurrence
-        float e = (a.ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
-        for (int l = 1; l < Mc; ++l) {
-          const int ql = mask_idx[l];
-          e = __fmul_rn(e, a.wn[(size_t)b * a.M + l]);
-          if (a.ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, a.wo[(size_t)b * a.M + l]);
-          if (!(fabsf(e) < 1.0f)) acc = fmaf(trunc_as_reference(e), row[ql], acc);
-        }
-      }
-      delta[it] = acc;
-    }
-    const int nhw = nh * CT;
-    for (int hw = warp; hw < nhw; hw += nwarps) {          // hub columns: one warp per (column, channel)
-      const int ch = hw / nh, h = hw - ch * nh;
-      const int4 rec = heavy_info[h];
-      const float* row = grow + (size_t)ch * N;
-      float acc = 0.f;
-      for (int r = rec.x + lane; r < rec.x + rec.y; r += 32) acc += row[rq_s[r]];
-      for (int e = rec.z + lane; e < rec.z + rec.w; e += 32) acc = fmaf(ewx[e], row[elx[e]], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) delta[nlight + hw] = acc;
-    }
-    __syncthreads();
-
-    // ---- phase B: g + weighted * triple_w in place                                               :173
-    for (int it = tid; it < nlight; it += nthreads) {
-      const int ch = it / nspec, k = it - ch * nspec;
-      float* cell = grow + (size_t)ch * N + spec[k];
-      *cell = __fadd_rn(*cell, __fmul_rn(delta[it], a.triple_w));
-    }
-    for (int hw = tid; hw < nhw; hw += nthreads) {
-      const int ch = hw / nh, h = hw - ch * nh;
-      float* cell = grow + (size_t)ch * N + heavy[h];
-      *cell = __fadd_rn(*cell, __fmul_rn(delta[nlight + hw], a.triple_w));
-    }
-    if (a.vec) {
-      fence_proxy_async();                                 // the in-place writes become visible to the bulk store
-      __syncthreads();
-      if (tid == 0) {
-        bulk_s2g(gdst + (size_t)i * tile_elems, smem_u32(grow), tile_bytes);
-        bulk_commit();
-        if (i + S - 1 < n) {
-          bulk_wait_read<1>();                             // the store of tile i-1 has left its stage
-          issue_load(i + S - 1);
-        }
-      }
-    } else {
-      __syncthreads();
-      for (int e = tid; e < tile_elems; e += nthreads) gdst[(size_t)i * tile_elems + e] = grow[e];
-      __syncthreads();
     }
   }
-  if (a.vec && tid == 0) bulk_wait_all();                  // shared memory must outlive the last stores
+  for (int i = threadIdx.x; i < N; i += nthreads) rq_s[i] = __ldg(grq + i);
+  if (exc_in_smem)
+    for (int i = threadIdx.x; i < etotal; i += nthreads) {
+      el_s[i] = __ldg(el + i);
+      ew_s[i] = __ldg(ew + i);
+    }
+  __syncthreads();
+  const int* elx = exc_in_smem ? el_s : el;
+  const float* ewx = exc_in_smem ? ew_s : ew;
+  const int nspec = nspec_s;
+  const int nh = min(nheavy, kBwdQueue);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+
+  for (int t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    const float* grow = rows0 + (size_t)buf * tile_elems;
+    float* ob = oimg + (size_t)t * tile_elems;
+    if (vec) mbar_wait(smem_u32(&bars[buf]), (uint32_t)((t - t0) >> 1) & 1u);
+    else __syncthreads();
+
+    // (1) copy-out: g + triple_w * 0
+    if (vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(grow);
+      float4* d4 = reinterpret_cast<float4*>(ob);
+      for (int i = threadIdx.x; i < tile_elems / 4; i += nthreads) d4[i] = s4[i];
+    } else {
+      for (int i = threadIdx.x; i < tile_elems; i += nthreads) ob[i] = grow[i];
+    }
+    __syncthreads();                                         // the corrections below overwrite some of these stores
+
+    // (2) corrections
+    for (int k = threadIdx.x; k < nspec; k += nthreads) {
+      const int p = spec[k];
+      int4 rec;
+      if (k < ninfo) rec = info[k];
+      else rec = make_int4(__ldg(gptr + p), __ldg(gptr + p + 1) - __ldg(gptr + p), lists ? __ldg(estart + p) : 0,
+                           lists ? __ldg(ecnt + p) : 0);
+      const int r0 = rec.x, r1 = rec.x + rec.y, es = rec.z, ne = rec.w;
+      float acc[CT];
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
+      for (int r = r0; r < r1; ++r) {
+        const int q = rq_s[r];
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
+      }
+      for (int e = 0; e < ne; ++e) {
+        const int q = elx[es + e];
+        const float w = ewx[es + e];
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+      }
+      if (overflow) {                                        // rare, slow, bit-faithful replay of the recurrence
+        float e = (ind[(size_t)b * N + mask_idx[0]] == p) ? 1.f : 0.f;
+        for (int l = 1; l < Mc; ++l) {
+          const int ql = mask_idx[l];
+          e = __fmul_rn(e, wn[(size_t)b * M + l]);
+          if (ind[(size_t)b * N + ql] == p) e = __fadd_rn(e, wo[(size_t)b * M + l]);
+          if (!(fabsf(e) < 1.0f)) {
+            const float w = trunc_as_reference(e);
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + ql], acc[ch]);
+          }
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch)                        // g + weighted * triple_w           :173
+        ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
+    }
+    for (int h = warp; h < nh; h += nwarps) {                // hub columns: one warp each
+      const int p = heavy[h];
+      const int4 rec = heavy_info[h];
+      const int r0 = rec.x, r1 = rec.x + rec.y;
+      float acc[CT];
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) acc[ch] = 0.f;
+      for (int r = r0 + lane; r < r1; r += 32) {
+        const int q = rq_s[r];
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) acc[ch] += grow[ch * N + q];
+      }
+      if (lists) {
+        const int ne = rec.w, es = rec.z;
+        for (int e = lane; e < ne; e += 32) {
+          const int q = elx[es + e];
+          const float w = ewx[es + e];
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) acc[ch] = fmaf(w, grow[ch * N + q], acc[ch]);
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) acc[ch] = warp_sum(acc[ch]);
+      if (lane == 0) {
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) ob[(size_t)ch * N + p] = __fadd_rn(grow[ch * N + p], __fmul_rn(acc[ch], triple_w));
+      }
+    }
+    __syncthreads();                                         // everybody is done reading this buffer
+    if (t + 2 < t1) load_tile(t + 2, buf);
+  }
 }
 
 }  // namespace ipsr
@@ -328,50 +324,44 @@ extern "C" int ipsr_shift_bwd_masks(const float* g, int B, int C, int N, int M,
   if (M > 1)
     IPSR_REQUIRE(exc_start && exc_cnt && exc_l && exc_w && exc_total && ind && mask_idx && wn && wo, IPSR_ERR_INVALID_ARG,
                  "ipsr_shift_bwd: exception lists / replay operands missing");
-  // channel rows per tile: a power of two <= 16 that keeps a tile near the target size (IPSR_BWD_TILE_KB, default
-  // 32 KiB); N % 4 != 0 needs CT % 4 == 0 so that every tile stays a whole number of 16-byte units for the bulk copies
-  static const int tile_kb = [] {
-    const char* e = getenv("IPSR_BWD_TILE_KB");
-    const int v = e ? atoi(e) : 32;
-    return v >= 4 && v <= 64 ? v : 32;
-  }();
-  int CT = 16;
-  while (CT > 1 && (C % CT != 0 || (size_t)CT * N * sizeof(float) > (size_t)tile_kb * 1024)) CT >>= 1;
-  if ((N & 3) != 0 && CT < 4 && C % 4 == 0) CT = 4;
-  const size_t tile_bytes = (size_t)CT * N * sizeof(float);
-  const bool vec = (tile_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(gin) & 15) == 0);
-  // shared memory: the ring, the delta buffer (one tile), the column list [N] + the CSR row list [N], then up to 1024
-  // per-column records (16 B each) and 2048 exception entries (8 B each): what does not fit is read from global memory
-  const size_t N4 = (size_t)((N + 3) & ~3);
-  int ninfo = N < 1024 ? N : 1024;
-  int nexc_s = (M > 1) ? 2048 : 0;
-  const size_t delta_bytes = (((size_t)CT * N + 3) & ~(size_t)3) * sizeof(float);
-  const size_t fixed = delta_bytes + 2 * N4 * sizeof(int) + (size_t)ninfo * 16 + (size_t)nexc_s * 8;
-  const size_t budget = 227 * 1024 - 12 * 1024;            // static: the hub queue and the barriers
-  IPSR_REQUIRE(fixed + (vec ? 2 : 1) * tile_bytes <= budget, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
-  int stages = vec ? (int)((budget - fixed) / tile_bytes) : 1;
-  if (stages > kBwdMaxStages) stages = kBwdMaxStages;
-  const size_t smem = fixed + (size_t)stages * tile_bytes;
-  // persistent CTAs, one per SM, each owning a contiguous run of tiles (image-major: a CTA sees 1-2 images)
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // channel rows per tile: the largest of 8, 4, 2, 1 that divides C and keeps a tile within 32 KiB (N > 2048: 64 KiB)
+  int CT = 8;
+  const size_t tile_cap = (N <= 2048 ? 32 : 64) * 1024;
+  while (CT > 1 && (C % CT != 0 || (size_t)CT * N * sizeof(float) > tile_cap)) CT >>= 1;
+  // shared memory: two tiles + the column list [N] + the CSR row list [N], then as much of the per-column records
+  // (16 B each) and of the exception entries (8 B each) as fits: what does not fit is read from global memory
+  const size_t base_smem = 2 * (size_t)CT * N * sizeof(float) + 2 * (size_t)((N + 3) & ~3) * sizeof(int);
+  IPSR_REQUIRE(base_smem <= 227 * 1024 - 12 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: N=%d too large", N);
+  const size_t room = (N <= 2048 ? 96 : 215) * 1024 - 12 * 1024 > base_smem ? (N <= 2048 ? 96 : 215) * 1024 - 12 * 1024 - base_smem : 0;
+  int ninfo = (int)((room / 2) / 16);
+  if (ninfo > N) ninfo = N;
+  int nexc_s = (int)((room - (size_t)ninfo * 16) / 8) & ~3;
+  if (nexc_s > exc_cap) nexc_s = (exc_cap + 3) & ~3;
+  if (M <= 1) nexc_s = 0;
+  const size_t smem = base_smem + (size_t)ninfo * 16 + (size_t)nexc_s * 8;
+  const int threads = N > 2048 ? 1024 : 512;
+  // Tiles per CTA: every CTA pays a fixed set-up (staging the image's index lists) and the per-image work is uneven
+  // (hub columns, long exception runs), so the grid is cut into about 1.75 CTAs per SM -- measured best on the B200 for
+  // 32x32 (B = 16) and 64x64 (B = 64) maps alike -- with at least two tiles per CTA to keep the two-stage ring busy.
   const int ntiles = C / CT;
-  const long long total_tiles = (long long)B * ntiles;
-  long long tpc = (total_tiles + sms - 1) / sms;
-  if (tpc < 1) tpc = 1;
-  const long long ctas = (total_tiles + tpc - 1) / tpc;
-  IPSR_REQUIRE(tpc <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_shift_bwd: too many tiles");
-  cudaError_t e = cudaFuncSetAttribute(shift_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "shift_bwd smem attribute: %s", cudaGetErrorString(e));
-  BwdArgs a;
-  a.g = g; a.gin = gin;
-  a.B = B; a.C = C; a.N = N; a.M = M; a.CT = CT; a.ntiles = ntiles; a.stages = stages; a.tiles_per_cta = (int)tpc; a.vec = vec ? 1 : 0;
-  a.route_ptr = route_ptr; a.route_q = route_q;
-  a.exc_start = exc_start; a.exc_cnt = exc_cnt; a.exc_l = exc_l; a.exc_w = exc_w; a.exc_state = exc_total;
-  a.ind = ind; a.mask_idx = mask_idx; a.wn = wn; a.wo = wo;
-  a.triple_w = triple_w;
-  a.ninfo = ninfo; a.nexc_s = nexc_s; a.ms = mask_stride; a.mcount = m_count;
-  shift_bwd_kernel<<<(unsigned)ctas, kBwdThreads, smem, as_stream(stream)>>>(a);
+  int tiles_per_cta = (int)(((long long)B * ntiles + 258) / 259);
+  if (tiles_per_cta < 2) tiles_per_cta = 2;
+  if (tiles_per_cta > ntiles) tiles_per_cta = ntiles;
+  const int parts = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
+  void (*kern)(const float*, int, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
+               const int*, int, const int*, const int*, const float*, const float*, float, float*, int, int, int, const int*) = nullptr;
+  switch (CT) {
+    case 8: kern = shift_bwd_kernel<8>; break;
+    case 4: kern = shift_bwd_kernel<4>; break;
+    case 2: kern = shift_bwd_kernel<2>; break;
+    default: kern = shift_bwd_kernel<1>; break;
+  }
+  if (smem + 12 * 1024 > 48 * 1024) {                       // static (queues) + dynamic shared memory above the default limit
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "shift_bwd smem attribute: %s", cudaGetErrorString(e));
+  }
+  kern<<<dim3(parts, B), threads, smem, as_stream(stream)>>>(g, C, N, M, tiles_per_cta, route_ptr, route_q, exc_start, exc_cnt,
+                                                            exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn, wo, triple_w,
+                                                            gin, ninfo, nexc_s, mask_stride, m_count);
   return check_launch("ipsr_shift_bwd");
 }

@@ -24,7 +24,7 @@ config = {
     "tol_rel": -1.0,              # < 0: library default (5e-5 * ||R[q]||)
     "tol_abs": -1.0,
     "psplit": 0,                  # <= 0: auto
-    "exc_cap_factor": 32,         # exception POOL of the batch = factor * N * B + M * min(M, N) entries (8 bytes each): signed
+    "exc_cap_factor": 8,          # exception POOL of the batch = factor * N * B + M * min(M, N) entries (8 bytes each): signed
                                   # inputs make a few images chaotic (tens of thousands of attention entries survive the int64
                                   # store); they borrow the room of the others, and one image can always be fully chaotic.
                                   # Only when the whole pool is exhausted does the backward of the images that found no room

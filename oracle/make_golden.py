@@ -118,6 +118,69 @@ def run_case(name, kind, B, C, H, mask_kind, triple_w=1.0, seed=0):
     print(f"{name}: M={int(m.flag.sum())} out|max|={np.abs(y.detach().numpy()).max():.3g} nnz(A_trunc)={len(vals)}")
 
 
+def channel_probe(C, seed=4242):
+    """Fixed fp64 weights over the channels: sum_c w[c] t[b,c,q] is a per-position fingerprint of ALL channels."""
+    return np.random.default_rng(seed).standard_normal(C)
+
+
+def run_case_compact(name, kind, B, C, H, mask_kind, triple_w=1.0, seed=0):
+    """Full-size cases (BASELINE.json configs[2]: 64 x 64 x 256; the model's own 32 x 32 x 512): the tensors are too large
+    to commit, so the fixture holds the seed (the test regenerates x / ref / g with make_inputs), every arg-max index and
+    row maximum, per-position channel fingerprints of out and gin in fp64, every 16th channel of out and gin, and the
+    reference's truncated attention (sparse)."""
+    IPSR_model, _, _, F, U = _import_reference()
+    S = H * 8
+    mg = centre_mask(S) if mask_kind == "centre" else irregular_mask(S, seed + 77)
+    x, r, g = make_inputs(kind, B, C, H, seed)
+    rec = {"ind": [], "vmax": []}
+    orig = F.MaxCoord.update_output
+
+    def spy(self, inp, sp_x, sp_y):
+        o = orig(self, inp, sp_x, sp_y)
+        rec["ind"].append(o[1].clone().numpy())
+        rec["vmax"].append(o[2].clone().numpy())
+        return o
+
+    F.MaxCoord.update_output = spy
+    try:
+        m = IPSR_model(5 / 16.0, 1, 1, 1, 1, triple_w)
+        fm = m.set_mask(torch.from_numpy(mg), 3, 5 / 16.0)
+        m.set_ref(collections.namedtuple("R", ["relu4_3"])(torch.from_numpy(r)))
+        xt = torch.from_numpy(x).clone().requires_grad_(True)
+        y = m(xt)
+        y.backward(torch.from_numpy(g))
+        attn_trunc = y.grad_fn.ind_lst.numpy()            # [B, N(p), H, W] int64
+    finally:
+        F.MaxCoord.update_output = orig
+    N = H * H
+    at = attn_trunc.reshape(B, N, N).transpose(0, 2, 1)   # -> [B, q, p]
+    nz = np.argwhere(at != 0)
+    vals = at[at != 0]
+    out, gin = y.detach().numpy(), xt.grad.numpy()
+    w = channel_probe(C)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        compact=True, kind=kind, B=B, C=C, H=H, seed=seed, mask_kind=mask_kind, triple_w=np.float32(triple_w),
+        mask_global=np.packbits(mg), mask_size=S, feat_mask=fm.numpy(), flag=m.flag.numpy(),
+        ind=np.stack(rec["ind"]).astype(np.int32), vmax=np.stack(rec["vmax"]),
+        out_probe=np.einsum("c,bcq->bq", w, out.reshape(B, C, N).astype(np.float64)),
+        gin_probe=np.einsum("c,bcq->bq", w, gin.reshape(B, C, N).astype(np.float64)),
+        out_abs=np.abs(out.reshape(B, C, N)).astype(np.float64).sum(1), gin_abs=np.abs(gin.reshape(B, C, N)).astype(np.float64).sum(1),
+        out_sub=out[:, ::16].copy(), gin_sub=gin[:, ::16].copy(),
+        attn_trunc_nz=nz.astype(np.int32), attn_trunc_val=vals,
+    )
+    print(f"{name}: M={int(m.flag.sum())} out|max|={np.abs(out).max():.3g} nnz(A_trunc)={len(vals)}")
+
+
+COMPACT_CASES = [
+    # name, kind, B, C, H, mask, triple_w, seed
+    ("p1_c256_h64_centre_b1_compact", "P1", 1, 256, 64, "centre", 1.0, 40),
+    ("p2_c256_h64_centre_b1_compact", "P2", 1, 256, 64, "centre", 1.0, 41),
+    ("p1_c512_h32_centre_b1_compact", "P1", 1, 512, 32, "centre", 1.0, 42),
+    ("p2_c512_h32_irr_b2_compact", "P2", 2, 512, 32, "irr", 1.0, 43),
+]
+
+
 class _AnyStore(dict):
     """Stands in for the reference's ``ind_lst`` LongTensor when shift_sz != 1."""
 
@@ -236,6 +299,10 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if "--compact-only" in sys.argv:
+        for case in COMPACT_CASES:
+            run_case_compact(*case)
+        sys.exit(0)
     for case in PATCH_CASES:
         run_patch_case(*case)
     if "--patches-only" in sys.argv:
@@ -250,3 +317,5 @@ if __name__ == "__main__":
     run_case("p3_c32_h8_centre_b1", "P3", 1, 32, 8, "centre", seed=15)
     run_case("p1_c512_h16_centre_b1", "P1", 1, 512, 16, "centre", seed=16)
     run_case("p1_c256_h32_centre_b1", "P1", 1, 256, 32, "centre", seed=17)
+    for case in COMPACT_CASES:
+        run_case_compact(*case)

@@ -37,3 +37,11 @@ PATCH_CASES = [
     "k4s2_c16_h12_irr_b1_t3",
     "k3_c64_h16_centre_b1",
 ]
+
+# full-size cases stored compactly (seed + fingerprints of the reference's outputs): oracle/make_golden.py run_case_compact
+COMPACT_CASES = [
+    "p1_c256_h64_centre_b1_compact",
+    "p2_c256_h64_centre_b1_compact",
+    "p1_c512_h32_centre_b1_compact",
+    "p2_c512_h32_irr_b2_compact",
+]
