@@ -35,6 +35,8 @@ class FwdArgs(C.Structure):
         ("nrecheck_out", _p), ("npass2_out", _p), ("ev_corr_begin", _p), ("ev_corr_end", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
         ("mask_stride", C.c_int32), ("m_count", _p),
+        ("cos_target", _p), ("cos_mask", _p), ("cos_strength", _f), ("cos_crit", C.c_int32),
+        ("cos_partials", _p), ("cos_ticket", _p), ("cos_loss", _p),
     ]
 
 
@@ -68,6 +70,7 @@ SIGNATURES = {
     "ipsr_blend_scan": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "ipsr_paste_with_bookkeeping": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "ipsr_paste": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "ipsr_paste_loss_partials": (_i, [_i, _i, _i]),
     "ipsr_build_routes": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "ipsr_build_exceptions": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "ipsr_shift_bwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _f, _p, _p]),

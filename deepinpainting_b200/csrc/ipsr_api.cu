@@ -177,6 +177,13 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
   // the route builders depend on ind only: they ride in the stage launch
   const int ms = a->mask_stride;                           // 0: one mask for the batch; N: per-image flag / mask_idx / rank rows
   const int32_t* mcount = ms ? a->m_count : nullptr;
+  PasteLoss cos_args;
+  const PasteLoss* cos = nullptr;
+  if (a->cos_target) {
+    cos_args.target = a->cos_target; cos_args.mask = a->cos_mask; cos_args.strength = a->cos_strength; cos_args.crit = a->cos_crit;
+    cos_args.partials = a->cos_partials; cos_args.ticket = a->cos_ticket; cos_args.loss = a->cos_loss;
+    cos = &cos_args;
+  }
   IPSR_FORWARD(blend_stage_with_routes_ex(at<float>(a, w.xt), at<float>(a, w.r_masked), at<float>(a, w.inv_norm), a->ind,
                                           a->mask_idx, a->flag, B, C, N, M, at<float>(a, w.staged), at<float>(a, w.vmask),
                                           grad ? a->route_ptr : nullptr, grad ? a->route_q : nullptr, stream, ms, mcount));
@@ -193,7 +200,7 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
     if (ss) in_use = std::unique_lock<std::mutex>(ss->use);
     if (ss && cudaEventRecord(ss->fork, st) == cudaSuccess && cudaStreamWaitEvent(ss->stream, ss->fork, 0) == cudaSuccess) {
       int rc = bookkeeping(ss->stream);
-      const int rc2 = paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms);
+      const int rc2 = paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms, cos);
       // always join, even after an error, so that a capture in progress is not left forked
       const bool joined = cudaEventRecord(ss->join, ss->stream) == cudaSuccess && cudaStreamWaitEvent(st, ss->join, 0) == cudaSuccess;
       if (rc == IPSR_OK) rc = rc2;
@@ -204,7 +211,7 @@ static int run_blend_and_paste(const ipsr_fwd_args* a, const Workspace& w, void*
     if (in_use.owns_lock()) in_use.unlock();
     IPSR_FORWARD(bookkeeping(stream));
   }
-  return paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms);
+  return paste_ex(a->x, at<float>(a, w.y), a->ind, a->rank, B, C, N, M, a->out, stream, ms, cos);
 }
 
 }  // namespace ipsr

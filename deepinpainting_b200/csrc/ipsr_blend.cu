@@ -381,13 +381,18 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int Mmax,
 __device__ __forceinline__ void
 paste_cta(int part, int b, int tiles_per_cta, float* psm, const float* __restrict__ x, const float* __restrict__ y,
           const int* __restrict__ ind, const int* __restrict__ rank, int C, int N, int M, int CT,
-          float* __restrict__ out, int ms = 0) {
+          float* __restrict__ out, int ms = 0, const PasteLoss* cos = nullptr, int cta_index = 0, int cta_count = 0,
+          long long loss_count = 0) {
   __shared__ __align__(8) unsigned long long paste_bars[2];
+  __shared__ float loss_wsum[32];
+  __shared__ bool loss_last;
+  float loss_acc = 0.f;
+  const float* tgt = cos ? cos->target + (size_t)b * C * N : nullptr;
   rank += (size_t)b * ms;                                      // per-image masks: rank is [B][ms]
   const int ntiles = (C + CT - 1) / CT;
   const int t0 = part * tiles_per_cta;
   const int t1 = min(ntiles, t0 + tiles_per_cta);
-  if (t0 >= t1) return;
+  if (t0 >= t1 && !cos) return;                                // (with the fused loss every CTA takes its ticket below)
   const int nthreads = blockDim.x;
   const int Mp = padded_steps(M);
   const int tile_x = CT * N, tile_y = CT * Mp, tile_elems = tile_x + tile_y;
@@ -423,7 +428,7 @@ paste_cta(int part, int b, int tiles_per_cta, float* psm, const float* __restric
     mbar_fence_init();
   }
   __syncthreads();
-  load_tile(t0, 0);
+  if (t0 < t1) load_tile(t0, 0);
   if (t0 + 1 < t1) load_tile(t0 + 1, 1);
   const int* indb = ind + (size_t)b * N;
   for (int q = threadIdx.x; q < N; q += nthreads) {
@@ -439,14 +444,52 @@ paste_cta(int part, int b, int tiles_per_cta, float* psm, const float* __restric
     float* ob = oimg + (size_t)t * tile_x;
     if (bulk) mbar_wait(smem_u32(&paste_bars[buf]), (uint32_t)((t - t0) >> 1) & 1u);
     else __syncthreads();
-    for (int q = threadIdx.x; q < N; q += nthreads) {
-      const int l = rank_s[q];
-      const float* srow = (l < 0) ? rows + ind_s[q] : yrows + l;
-      const int stride = (l < 0) ? N : Mp;
-      for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = srow[ch * stride];
+    if (!cos) {
+      for (int q = threadIdx.x; q < N; q += nthreads) {
+        const int l = rank_s[q];
+        const float* srow = (l < 0) ? rows + ind_s[q] : yrows + l;
+        const int stride = (l < 0) ? N : Mp;
+        for (int ch = 0; ch < ct; ++ch) ob[(size_t)ch * N + q] = srow[ch * stride];
+      }
+    } else {                                                   // the same, plus the side loss on the values just pasted
+      const float* tg = tgt + (size_t)t * tile_x;
+      for (int q = threadIdx.x; q < N; q += nthreads) {
+        const int l = rank_s[q];
+        const float* srow = (l < 0) ? rows + ind_s[q] : yrows + l;
+        const int stride = (l < 0) ? N : Mp;
+        const float mq = __ldg(cos->mask + q);
+        for (int ch = 0; ch < ct; ++ch) {
+          const float v = srow[ch * stride];
+          ob[(size_t)ch * N + q] = v;
+          // (in_data * mask) * strength - target, the reference's operation order     InnerCos.py:33-36
+          const float d = __fmul_rn(__fmul_rn(v, mq), cos->strength) - __ldg(tg + (size_t)ch * N + q);
+          loss_acc += cos->crit == 0 ? d * d : fabsf(d);
+        }
+      }
     }
     __syncthreads();                                           // everybody is done reading this buffer
     if (t + 2 < t1) load_tile(t + 2, buf);
+  }
+  if (cos) {
+    // deterministic two-level reduction: one partial per CTA, the ticket-elected last CTA adds them in index order
+    loss_acc = warp_sum(loss_acc);
+    if ((threadIdx.x & 31) == 0) loss_wsum[threadIdx.x >> 5] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tsum = 0.f;
+      for (int w = 0; w < (nthreads >> 5); ++w) tsum += loss_wsum[w];
+      cos->partials[cta_index] = tsum;
+      __threadfence();
+      loss_last = (atomicAdd(cos->ticket, 1u) == (unsigned)cta_count - 1u);
+    }
+    __syncthreads();
+    if (loss_last && threadIdx.x == 0) {
+      __threadfence();
+      double tsum = 0.0;
+      for (int i = 0; i < cta_count; ++i) tsum += (double)((volatile float*)cos->partials)[i];
+      *cos->loss = (float)(tsum / (double)loss_count);
+      *cos->ticket = 0u;
+    }
   }
 }
 
@@ -474,6 +517,16 @@ paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int
              const int* __restrict__ rank, int C, int N, int M, int CT, int tiles_per_cta, float* __restrict__ out, int ms) {
   extern __shared__ __align__(128) float rows[];         // [2][CT][N] + ind[N] + rank[N]
   paste_cta(blockIdx.x, blockIdx.y, tiles_per_cta, rows, x, y, ind, rank, C, N, M, CT, out, ms);
+}
+
+// the paste with the InnerCos side loss fused in (the loss arguments by value: no pointer chasing on the device)
+__global__ void __launch_bounds__(512)
+paste_loss_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ ind,
+                  const int* __restrict__ rank, int C, int N, int M, int CT, int tiles_per_cta, float* __restrict__ out, int ms,
+                  const PasteLoss cos, long long loss_count) {
+  extern __shared__ __align__(128) float rows[];
+  paste_cta(blockIdx.x, blockIdx.y, tiles_per_cta, rows, x, y, ind, rank, C, N, M, CT, out, ms, &cos,
+            (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(gridDim.x * gridDim.y), loss_count);
 }
 
 // The paste and the two bookkeeping builders of the backward are independent once the scan is done:
@@ -640,8 +693,14 @@ extern "C" int ipsr_paste(const float* x, const float* y, const int32_t* ind, co
   return ipsr::paste_ex(x, y, ind, rank, B, C, N, M, out, stream, 0);
 }
 
+extern "C" int ipsr_paste_loss_partials(int B, int C, int N) {
+  // one partial per paste CTA: at most one CTA per channel tile and image
+  (void)N;
+  return B * C;
+}
+
 int ipsr::paste_ex(const float* x, const float* y, const int32_t* ind, const int32_t* rank,
-                   int B, int C, int N, int M, float* out, void* stream, int ms) {
+                   int B, int C, int N, int M, float* out, void* stream, int ms, const PasteLoss* loss) {
   using namespace ipsr;
   IPSR_REQUIRE(x && ind && rank && out && (M == 0 || y), IPSR_ERR_INVALID_ARG, "ipsr_paste: null pointer");
   IPSR_REQUIRE(B > 0 && C > 0 && N > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_paste: bad dims");
@@ -655,6 +714,17 @@ int ipsr::paste_ex(const float* x, const float* y, const int32_t* ind, const int
   const int threads = paste_threads(N);
   const int ntiles = (C + CT - 1) / CT;
   const int tpc = tiles_per_cta_for(B, ntiles, paste_slots(smem, threads));
+  if (loss) {
+    IPSR_REQUIRE(loss->target && loss->mask && loss->partials && loss->ticket && loss->loss && (loss->crit == 0 || loss->crit == 1),
+                 IPSR_ERR_INVALID_ARG, "ipsr_paste: fused InnerCos loss needs target, mask, partials, ticket, loss");
+    if (smem + 2048 > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(paste_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste smem attribute: %s", cudaGetErrorString(e));
+    }
+    paste_loss_kernel<<<dim3((ntiles + tpc - 1) / tpc, B), threads, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, tpc, out, ms,
+                                                                                             *loss, (long long)B * C * N);
+    return check_launch("ipsr_paste");
+  }
   paste_kernel<<<dim3((ntiles + tpc - 1) / tpc, B), threads, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, tpc, out, ms);
   return check_launch("ipsr_paste");
 }

@@ -44,8 +44,19 @@ int blend_stage_with_routes_ex(const float* xt, const float* r_masked, const flo
                                float* vmask, int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount);
 int blend_scan_ex(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, void* stream,
                   const int32_t* mcount);
+// Optional InnerCos side loss computed while the pasted tiles are still in shared memory (models/networks.py:347:
+// `ipsr, innerCos, downnorm_3`; models/InnerCos.py:30-36): loss = mean(crit(out * mask * strength - target)).
+struct PasteLoss {
+  const float* target;     // [B,C,N]
+  const float* mask;       // [N] float, 1 = hole
+  float strength;
+  int crit;                // 0 = squared error, 1 = absolute error
+  float* partials;         // one float per paste CTA (ipsr_paste_loss_partials)
+  unsigned int* ticket;    // zeroed u32, left zeroed
+  float* loss;             // scalar out
+};
 int paste_ex(const float* x, const float* y, const int32_t* ind, const int32_t* rank, int B, int C, int N, int M,
-             float* out, void* stream, int ms);
+             float* out, void* stream, int ms, const PasteLoss* loss = nullptr);
 int paste_with_bookkeeping_ex(const float* x, const float* y, const int32_t* ind, const int32_t* rank, const int32_t* flag,
                               const int32_t* mask_idx, const float* wn, const float* wo, int B, int C, int N, int M,
                               float* out, int32_t* route_ptr, int32_t* route_q, int32_t* exc_start, int32_t* exc_cnt,

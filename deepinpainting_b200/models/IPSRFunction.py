@@ -26,6 +26,7 @@ class IPSRFunction(torch.autograd.Function):
         ctx.flatten_offsets = flatten_offsets
         ctx.bz, c_real, ctx.h, ctx.w = input.size()
         ctx.saved_shift = None
+        fused_cos = shift_ops.take_fused_request()          # set by IPSR_model.forward for this very call, or None
         # fp16 / bf16 activations (autocast around the host network's convolutions): the layer computes in fp32, as the
         # reference does, and hands back the input's dtype
         ctx.in_dtype = input.dtype
@@ -44,7 +45,9 @@ class IPSRFunction(torch.autograd.Function):
         # as in the reference; mask_point_idx is implied by flag.
         mi = shift_ops.lookup_mask_index(flag, input.device)
         need_grad = bool(ctx.needs_input_grad[0])
-        output, saved = shift_ops.shift_forward(input.detach(), ref_feat.detach(), mi, need_grad=need_grad)
+        output, saved = shift_ops.shift_forward(input.detach(), ref_feat.detach(), mi, need_grad=need_grad,
+                                                fused_cos=fused_cos if ctx.in_dtype == torch.float32 else None)
+        shift_ops.publish_fused_loss(saved.cos_loss)
         ctx.saved_shift = saved
         ctx.ind_lst = saved.ind          # [B, N] int32 arg-max indices (the reference keeps A as int64 [B,N,H,W])
         return output if ctx.in_dtype == torch.float32 else output.to(ctx.in_dtype)

@@ -2,6 +2,8 @@
 (models/IPSR_model.py:9-68): holds the feature mask, the reference features and the flag vectors
 and calls IPSRFunction.  It owns no parameters or buffers, so state_dicts are unaffected.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -10,9 +12,17 @@ from ..util import util
 from .IPSRFunction import IPSRFunction
 
 
+# the most recently constructed shift module that no InnerCos has claimed yet (the generator builds
+# `ipsr = IPSR_model(...)` and then `innerCos = InnerCos(...)` for the module right behind it, models/networks.py:307-314)
+_last_unlinked = None
+
+
 class IPSR_model(nn.Module):
     def __init__(self, threshold, fixed_mask, shift_sz=1, stride=1, mask_thred=1, triple_weight=1):
         super(IPSR_model, self).__init__()
+        global _last_unlinked
+        self._cos_ref = None
+        _last_unlinked = weakref.ref(self)
         self.threshold = threshold
         self.fixed_mask = fixed_mask
         self.shift_sz = shift_sz
@@ -46,6 +56,37 @@ class IPSR_model(nn.Module):
     def set_ref(self, latent_ref):
         self.ref = latent_ref
 
+    def link_innercos(self, innercos):
+        """Tell the layer which InnerCos module consumes its output (`ipsr, innerCos, downnorm_3`, models/networks.py:347):
+        the forward then computes that module's loss in its paste kernel, while the output tiles are still in shared
+        memory, and InnerCos.forward picks the value up instead of reading the output again.  Done automatically for an
+        InnerCos constructed right after the layer; results are identical either way."""
+        self._cos_ref = None if innercos is None else weakref.ref(innercos)
+
+    def _fused_cos_request(self, input):
+        cos = self._cos_ref() if self._cos_ref is not None else None
+        if cos is None or not shift_ops.config["fuse_innercos"] or cos.skip or self.shift_sz != 1 or self.stride != 1:
+            return None, None
+        t, m = cos.target, getattr(cos, "mask", None)
+        if not (torch.is_tensor(t) and torch.is_tensor(m) and input.dtype == torch.float32 and t.dtype == torch.float32
+                and t.is_cuda and t.shape == input.shape and m.numel() == input.size(2) * input.size(3)):
+            return None, None
+        m = m if (m.device == input.device and m.dtype == torch.float32) else m.to(input.device, torch.float32)
+        return shift_ops.FusedCos(target=t.detach(), mask=m, strength=float(cos.strength), crit=cos.crit), cos.fuse_key()
+
+    def _call_function(self, input, mask2d):
+        req, key = self._fused_cos_request(input)
+        shift_ops.request_fused_cos(req)
+        try:
+            out = IPSRFunction.apply(input, mask2d, self.ref, self.shift_sz, self.stride, self.triple_weight, self.flag,
+                                     self.nonmask_point_idx, self.mask_point_idx, self.flatten_offsets, self.sp_x, self.sp_y)
+        finally:
+            shift_ops.request_fused_cos(None)
+        loss = shift_ops.take_fused_loss()
+        if req is not None and loss is not None:
+            out._ipsr_fused_cos = (loss, key)               # read by the InnerCos that receives this very tensor
+        return out
+
     def _forward_per_sample(self, input):
         """One batched operator call with a flag row per sample (flag vectors cached per mask)."""
         if len(self.masks) != input.size(0):
@@ -70,8 +111,7 @@ class IPSR_model(nn.Module):
             shift_ops.register_mask_index(self.flag, shift_ops.stack_mask_indices(
                 shift_ops.lookup_mask_index(v[0], input.device) for v in per))
             self._flag_key = key
-        return IPSRFunction.apply(input, self.masks[0], self.ref, self.shift_sz, self.stride, self.triple_weight, self.flag,
-                                  self.nonmask_point_idx, self.mask_point_idx, self.flatten_offsets, self.sp_x, self.sp_y)
+        return self._call_function(input, self.masks[0])
 
     def forward(self, input):
         if getattr(self, "masks", None) is not None:
@@ -91,9 +131,7 @@ class IPSR_model(nn.Module):
             self._flag_key = key
         if not (torch.is_tensor(self.sp_x) or torch.is_tensor(self.sp_y)):
             self.sp_x, self.sp_y = util.cal_sps_for_Advanced_Indexing(self.h, self.w)
-        return IPSRFunction.apply(input, self.mask, self.ref, self.shift_sz, self.stride, self.triple_weight,
-                                  self.flag, self.nonmask_point_idx, self.mask_point_idx, self.flatten_offsets,
-                                  self.sp_x, self.sp_y)
+        return self._call_function(input, self.mask)
 
     def __repr__(self):
         return self.__class__.__name__ + '(' \

@@ -24,6 +24,7 @@ config = {
     "tol_rel": -1.0,              # < 0: library default (5e-5 * ||R[q]||)
     "tol_abs": -1.0,
     "psplit": 0,                  # <= 0: auto
+    "fuse_innercos": True,        # compute the InnerCos loss that follows the layer (networks.py:347) inside the paste kernel
     "exc_cap_factor": 8,          # exception POOL of the batch = factor * N * B + M * min(M, N) entries (8 bytes each): signed
                                   # inputs make a few images chaotic (tens of thousands of attention entries survive the int64
                                   # store); they borrow the room of the others, and one image can always be fully chaotic.
@@ -43,6 +44,30 @@ def exc_pool_entries(B: int, N: int, M: int) -> int:
     single = min(M * min(M, N), 1 << 26) if f >= 1 else 0      # (tests shrink the pool with factors < 1)
     return max(1, shared + single)
 
+
+
+_tls = threading.local()
+
+
+def request_fused_cos(req) -> None:
+    """IPSR_model.forward -> IPSRFunction.forward (whose 12-argument signature is the reference's and cannot carry it)."""
+    _tls.fused_request = req
+
+
+def take_fused_request():
+    req = getattr(_tls, "fused_request", None)
+    _tls.fused_request = None
+    return req
+
+
+def publish_fused_loss(loss) -> None:
+    _tls.fused_loss = loss
+
+
+def take_fused_loss():
+    loss = getattr(_tls, "fused_loss", None)
+    _tls.fused_loss = None
+    return loss
 
 
 def _stream_ptr(device) -> int:
@@ -167,6 +192,16 @@ def mask_index_from_flag(flag: torch.Tensor, device) -> MaskIndex:
 # shift operator
 # --------------------------------------------------------------------------------------
 @dataclass
+class FusedCos:
+    """Request for the InnerCos side loss of the module that follows the shift layer (models/networks.py:347), computed
+    in the paste kernel while the pasted tiles are still in shared memory instead of a second pass over the output."""
+    target: torch.Tensor      # [B,C,H,W] fp32
+    mask: torch.Tensor        # [H,W] or [N] fp32, 1 = hole
+    strength: float
+    crit: str                 # 'MSE' or anything else for L1, as the reference's constructor argument
+
+
+@dataclass
 class ShiftSaved:
     B: int
     C: int
@@ -189,6 +224,7 @@ class ShiftSaved:
     nrecheck: Optional[torch.Tensor] = None
     npass2: Optional[torch.Tensor] = None
     m_count: Optional[torch.Tensor] = None      # per-image masks: mask_idx is [B, N], m_count [B]
+    cos_loss: Optional[torch.Tensor] = None     # fused InnerCos side loss (scalar), when requested
 
     def exceptions_of(self, b: int):
         """(positions q_l, truncated weights) of the attention entries of image ``b`` that survive the reference's int64
@@ -267,6 +303,14 @@ class _Plan:
         a.workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace_bytes
         a.mask_stride, a.m_count = (N, mi.m_count.data_ptr()) if mi.batched else (0, None)
         self.args = a
+        self._cos_scratch = None
+
+    def cos_scratch(self, dev):
+        """Partials + the (zeroed, left zeroed) ticket of the fused InnerCos loss; stream-ordered reuse across calls."""
+        if self._cos_scratch is None:
+            n = _lib.load().ipsr_paste_loss_partials(self.B, self.C, self.N)
+            self._cos_scratch = (torch.empty(n, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._cos_scratch
 
 
 _plans = threading.local()
@@ -297,7 +341,7 @@ class _Call:
     """One forward call: the output, the blob with what the backward needs, and the plan's argument struct pointed at them."""
 
     def __init__(self, x, ref, mi: MaskIndex, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics,
-                 events=None):
+                 events=None, fused_cos: Optional[FusedCos] = None):
         plan = _plan_for(x, mi, need_grad, mode, col_begin, col_end, stop_after_corr, diagnostics)
         dev = x.device
         self.plan = plan
@@ -327,6 +371,20 @@ class _Call:
                                                                _ptr(s.exc_w), _ptr(s.exc_state))
         a.nrecheck_out = _ptr(s.nrecheck)
         a.npass2_out = _ptr(s.npass2)
+        if fused_cos is not None:
+            t = _require_cuda(fused_cos.target, "InnerCos target", torch.float32)
+            m = _require_cuda(fused_cos.mask, "InnerCos mask", torch.float32)
+            if tuple(t.shape) != tuple(x.shape) or m.numel() != plan.N:
+                raise ValueError("fused InnerCos: target %s / mask %s do not match the layer output %s"
+                                 % (tuple(t.shape), tuple(m.shape), tuple(x.shape)))
+            partials, ticket = plan.cos_scratch(dev)
+            s.cos_loss = torch.empty((), dtype=torch.float32, device=dev)
+            a.cos_target, a.cos_mask = t.data_ptr(), m.data_ptr()
+            a.cos_strength, a.cos_crit = float(fused_cos.strength), 0 if fused_cos.crit == "MSE" else 1
+            a.cos_partials, a.cos_ticket, a.cos_loss = partials.data_ptr(), ticket.data_ptr(), s.cos_loss.data_ptr()
+            self.keep_cos = (t, m)
+        else:
+            a.cos_target = a.cos_mask = a.cos_partials = a.cos_ticket = a.cos_loss = None
         if events is not None:                       # (begin, end) torch.cuda.Event pair, already materialised
             a.ev_corr_begin, a.ev_corr_end = events[0].cuda_event, events[1].cuda_event
         else:
@@ -346,15 +404,16 @@ class _Call:
 
 
 def shift_forward(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, need_grad: bool = True,
-                  mode: Optional[str] = None, diagnostics: bool = False, events=None):
-    """models/IPSRFunction.py:13-140 for shift_sz = stride = 1.  Returns (out, ShiftSaved)."""
+                  mode: Optional[str] = None, diagnostics: bool = False, events=None, fused_cos: Optional[FusedCos] = None):
+    """models/IPSRFunction.py:13-140 for shift_sz = stride = 1.  Returns (out, ShiftSaved).  ``fused_cos``: also compute
+    the InnerCos side loss of the output (``saved.cos_loss``) inside the paste kernel."""
     x = _require_cuda(x, "input", torch.float32)
     ref = _require_cuda(ref, "ref.relu4_3", torch.float32)
     if x.dim() != 4:
         raise AssertionError("Input Dim has to be 4")
     if ref.shape != x.shape:
         raise ValueError("ref.relu4_3 %s must have the shape of the input %s" % (tuple(ref.shape), tuple(x.shape)))
-    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], 0, -1, False, diagnostics, events)
+    call = _Call(x, ref, mi, need_grad, mode or config["correlation_mode"], 0, -1, False, diagnostics, events, fused_cos)
     _lib.call("ipsr_shift_forward", C.byref(call.args), _stream_ptr(x.device))
     return call.out, call.saved
 

@@ -219,6 +219,9 @@ int ipsr_padded_steps(int M);
 int ipsr_blend_scan(const float* staged, int B, int C, int M,
                     float* y, float* wn, float* wo, void* stream);
 
+/* floats of the partial-sum buffer of the fused InnerCos loss (ipsr_fwd_args.cos_partials) */
+int ipsr_paste_loss_partials(int B, int C, int N);
+
 /* out[b,:,q] = y[b,:,rank[q]] (y laid out [B][C][ipsr_padded_steps(M)]) for masked q,
  * x[b,:,ind[b,q]] otherwise (replaces the dense
  * conv_transpose of IPSRFunction.py:131). */
@@ -367,6 +370,16 @@ typedef struct ipsr_fwd_args {
    *   wn, wo and of the workspace's per-step buffers). */
   int32_t mask_stride;
   const int32_t* m_count;
+  /* Optional: the InnerCos side loss that follows the layer in the generator (models/networks.py:347 `ipsr, innerCos,
+   * downnorm_3`; models/InnerCos.py:30-36) computed in the paste while the pasted tiles are still in shared memory:
+   * *cos_loss = mean(crit(out * cos_mask * cos_strength - cos_target)).  cos_target NULL: not computed. */
+  const float* cos_target;   /* [B,C,H,W]                                                */
+  const float* cos_mask;     /* [H*W] float, 1 = hole                                    */
+  float cos_strength;
+  int32_t cos_crit;          /* 0 = squared error (MSELoss), 1 = absolute error (L1Loss) */
+  float* cos_partials;       /* ipsr_paste_loss_partials(B, C, N) floats                 */
+  uint32_t* cos_ticket;      /* one zeroed u32 (left zeroed)                             */
+  float* cos_loss;           /* scalar                                                   */
 } ipsr_fwd_args;
 
 size_t ipsr_workspace_bytes(int B, int C, int H, int W, int M, int mode);
