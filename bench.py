@@ -51,6 +51,14 @@ def parse_args():
     ap.add_argument("--cpu-images", type=int, default=0, help="images of the CPU-baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1234, help="synthetic data seed (rank r uses seed + r)")
+    ap.add_argument("--workload", default="shift", choices=["shift", "patch3x3"],
+                    help="shift: configs[1] / configs[2], fwd+bwd of the 1x1 layer (the default line); patch3x3: configs[3], the "
+                         "reference-guided forward with 3x3 patches on a 64x64x256 map (forward only: the reference has no backward "
+                         "for shift_sz != 1)")
+    ap.add_argument("--shard", default="batch", choices=["batch", "bank"],
+                    help="with several GPUs: split the batch (no data-path collective) or, for patch3x3, split the patch BANK "
+                         "across the ranks and merge the (max, idx) keys with one NCCL all-reduce MAX")
+    ap.add_argument("--patch-batch", type=int, default=2, help="images per step of the patch3x3 workload")
     ap.add_argument("--no-also", action="store_true",
                     help="skip the short configs[2] (512^2: batch 64, 64x64x256) run appended to the default line as 'also'")
     return ap.parse_args()
@@ -198,6 +206,19 @@ def run_reference(args):
         pool = threadpool_limits(limits=_host_threads())
     except Exception as exc:                                       # keep the launcher's setting
         sys.stderr.write("threadpoolctl unavailable (%s): BLAS threads as configured by the environment\n" % exc)
+    if args.workload == "patch3x3":
+        C, H = args.channels, 64 if args.size == WORKLOAD["H"] else args.size
+        steps = max(1, min(args.steps, 2))
+        cpu_patch_images_per_sec(C, H, 3, 1)
+        ips, threads, secs = cpu_patch_images_per_sec(C, H, 3, steps)
+        line = {"impl": "reference", "metric": PATCH_METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+                "ms_per_step": 1e3 * secs / steps * args.patch_batch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": patch_config(args.patch_batch, C, H, 3, 1, "batch"),
+                "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": "%d steps x 1 image, forward, fp32 (numpy port: the reference fails after computing the output for shift_sz = 3)" % steps},
+                "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
     C, H = args.channels, args.size
     per_step = max(1, min(args.batch, 2 if H <= 32 else 1))          # bounded sample of the batch per step
     steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 1))
@@ -581,6 +602,156 @@ def measure(args, B, C, H, K, W_, world, rank, local, dev, dist, pk, with_cpu, e
             "gpu_launches": launches_per_step * K}
 
 
+PATCH_METRIC = "patch3x3_forward_images_per_sec"
+
+
+def patch_config(B, C, H, k, world, shard):
+    nH = H - k + 1
+    return {"workload": "configs[3]: reference-guided shift layer forward, %dx%dx%d features, %dx%d patches (P = %d patch positions, "
+                        "rows of K = %d), centre hole, batch %d" % (H, H, C, k, k, nH * nH, C * k * k, B),
+            "batch": B, "C": C, "H": H, "W": H, "patch": k, "stride": 1, "P": nH * nH, "K": C * k * k,
+            "parallelism": ("bank-sharded x%d: every rank correlates P/%d bank columns, one NCCL all-reduce MAX of the (max, idx) keys"
+                            % (world, world)) if shard == "bank" and world > 1 else "batch-sharded x%d, no data-path collective" % world}
+
+
+def measure_patch(args, world, rank, local, dev, dist, pk):
+    """BASELINE.json configs[3]: forward of the layer with shift_sz = 3 on a 64 x 64 x 256 map (models/IPSRFunction.py:46-133
+    with 3 x 3 patches; the reference has no backward for it).  --shard bank: all ranks hold the same images, the patch bank
+    is split across them and the (max, idx) keys are merged by one all-reduce MAX."""
+    import torch
+    from deepinpainting_b200 import shift_ops
+    from deepinpainting_b200.sharding import shard_bank, allreduce_max_keys
+    B, C, H, k = args.patch_batch, args.channels, 64 if args.size == WORKLOAD["H"] else args.size, 3
+    nH = H - k + 1
+    P, K = nH * nH, C * k * k
+    bank = args.shard == "bank" and world > 1
+    feat = torch.zeros(H, H, dtype=torch.uint8, device=dev)
+    feat[H // 4:3 * H // 4, H // 4:3 * H // 4] = 1
+    mi = shift_ops.build_flags(feat, k, 1, 1)
+    gen = torch.Generator(device="cpu").manual_seed(args.seed + (0 if bank else rank))     # bank mode: the SAME images everywhere
+    pool = 4
+    sets = [(torch.randn(B, C, H, H, generator=gen).abs().to(dev), (torch.relu(torch.randn(B, C, H, H, generator=gen)) * 3).to(dev))
+            for _ in range(pool)]
+    Ppad = -(-P // 128) * 128
+    cb, ce = (0, -1)
+    if bank:
+        cb, ce = shard_bank(Ppad, world, rank)
+        ce = min(ce, P)
+        cb = min(cb, P)
+    ar_ms = []
+
+    def reduce_keys(keys):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        allreduce_max_keys(keys)
+        b_.record()
+        ar_ms.append((a, b_))
+
+    def step(i):
+        x, ref = sets[i % pool]
+        return shift_ops.shift_forward_patches(x, ref, mi, k, 1, mode=args.mode if args.mode != "auto" else None,
+                                               col_begin=cb, col_end=ce, reduce_max=reduce_keys if bank else None)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W_, Ks = max(3, args.warmup), min(args.steps, 100)
+    for i in range(W_):
+        step(i)
+    sync_all()
+    ar_ms.clear()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for i in range(Ks):
+        step(W_ + i)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms_max = max_over_ranks(e0.elapsed_time(e1))
+    images = B * Ks * (1 if bank else world)
+    value = images / (ms_max * 1e-3)
+    allreduce_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in ar_ms) if ar_ms else None
+    # the correlation alone (tcgen05 three-pass split over this rank's bank columns), by its C-ABI entry points
+    corr = shift_ops.time_wide_patch_correlation(sets[0][0], sets[0][1], k, 1, cb, ce if ce >= 0 else P, reps=10)
+    cols = (ce if ce >= 0 else P) - cb
+    flops = 2.0 * P * max(cols, 0) * K * B
+    achieved = flops / (corr["gemm_ms"] * 1e-3) / 1e12 if corr["gemm_ms"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "corr_tc_kernel<1,3,false> (tcgen05 fp16 three-pass split, both operands streamed: K = %d)" % K,
+                "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
+                "issued_passes": 3, "tensor_pipe_utilisation": 3 * achieved / pk["tf_burst"], "kernel_ms": corr["gemm_ms"],
+                "share_of_step": corr["gemm_ms"] / (ms_max / Ks), "traffic": None,
+                "peak_source": pk["source"] + " bf16 dense, burst (kernel timed alone)",
+                "note": "achieved = algorithmic FLOPs (2 * P * bank columns of this rank * K per image) / time of the GEMM launch"}
+    # e2e: host pinned buffers in, result out
+    hx = [t.cpu().pin_memory() for t in sets[0]]
+    hout = torch.empty(B, C, H, H).pin_memory()
+    dx = [torch.empty_like(t) for t in sets[0]]
+
+    def e2e_once():
+        dx[0].copy_(hx[0], non_blocking=True)
+        dx[1].copy_(hx[1], non_blocking=True)
+        out, _ = shift_ops.shift_forward_patches(dx[0], dx[1], mi, k, 1, col_begin=cb, col_end=ce, reduce_max=reduce_keys if bank else None)
+        hout.copy_(out, non_blocking=True)
+
+    for _ in range(2):
+        e2e_once()
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    EK = max(5, min(Ks, 40))
+    f0.record()
+    for _ in range(EK):
+        e2e_once()
+    f1.record()
+    sync_all()
+    e2e_s = max_over_ranks(f0.elapsed_time(f1) * 1e-3)
+    e2e = {"value": B * EK * (1 if bank else world) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * B * C * H * H * 4,
+           "d2h_bytes_per_step": B * C * H * H * 4, "steps": EK, "api": "shift_ops.shift_forward_patches (what IPSRFunction.apply calls for shift_sz = 3), pinned host buffers"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, threads, secs = cpu_patch_images_per_sec(C, H, k, 1)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "1 image, forward, fp32, %.1f s (numpy port: the reference itself fails after computing the output for shift_sz = 3, IPSRFunction.py:134)" % secs}
+    if rank != 0:
+        return None
+    return {"metric": PATCH_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ks, "warmup": W_, "ms_per_step": ms_max / Ks,
+            "higher_is_better": True, "scaling": "strong" if bank else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": patch_config(B, C, H, k, world, args.shard), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "allreduce_ms": allreduce_ms, "allreduce_bytes": 8 * B * P if bank else 0,
+            "stages_ms": corr, "gpu_launches": corr["launches_per_step"] * Ks}
+
+
+def cpu_patch_images_per_sec(C, H, k, n_images, seed=1234):
+    import numpy as np
+    from oracle import ipsr_oracle as O
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+    fm = np.zeros((H, H), np.uint8)
+    fm[H // 4:3 * H // 4, H // 4:3 * H // 4] = 1
+    total = 0.0
+    for _ in range(n_images):
+        x = np.abs(rng.standard_normal((1, C, H, H))).astype(np.float32)
+        ref = (np.maximum(rng.standard_normal((1, C, H, H)), 0) * 3).astype(np.float32)
+        t0 = time.perf_counter()
+        O.shift_forward_patches(x, ref, fm, k, 1, 1)
+        total += time.perf_counter() - t0
+    return n_images / total, threads, total
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -599,6 +770,13 @@ def run_ours(args):
     shift_ops.config["correlation_mode"] = args.mode
     pk = peaks()
     B, C, H = args.batch, args.channels, args.size
+    if args.workload == "patch3x3":
+        line = measure_patch(args, world, rank, local, dev, dist, pk)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     line = measure(args, B, C, H, args.steps, max(3, args.warmup), world, rank, local, dev, dist, pk,
                    with_cpu=not args.no_cpu_baseline, e2e_seconds=1.2)
     # ---- the metric's second size (BASELINE.json: "at 256^2/512^2 ... 1/2/4/8 B200"): configs[2] (512^2: batch 64 per GPU,

@@ -52,6 +52,14 @@ SIGNATURES = {
     "ipsr_extract_normalize": (_i, [_p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ipsr_compact_rows": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ipsr_correlate_argmax_tc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ipsr_correlate_argmax_tc_valid": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "ipsr_finalize_argmax_valid": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _i,
+                                        _p, _p, _p, _p, _p, _i, _p]),
+    "ipsr_patch_rows_stats": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ipsr_patch_tiles": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ipsr_patch_recheck": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ipsr_patch_resolve_pairs": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "ipsr_patch_winner_scores": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "ipsr_finalize_argmax": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _i,
                                   _p, _p, _p, _p, _p, _p]),
     "ipsr_resolve_rows": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),

@@ -46,6 +46,8 @@ struct TcParams {
   int* part_idx2;           // PASSES 3 only (optional): column of the runner-up and the third-best score, so that rows
   float* part_third;        // with exactly two candidates inside the error band need two exact dot products, not N
   float* s_dump;
+  int n_valid;              // bank columns >= n_valid are padding (patch maps whose position count is no multiple of 128):
+                            // they never win
 };
 
 // CL = 2: clusters of two CTAs (adjacent row-tile groups of the same image and column range) share every streamed
@@ -255,6 +257,11 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         const int c0 = colb + ch * 32;
+        if (c0 + 32 > prm.n_valid) {                       // (warp-uniform) padding columns: -inf
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c0 + e >= prm.n_valid) r[e] = 0xFF800000u;
+        }
         if (top3) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -323,10 +330,10 @@ __global__ void finalize_kernel(const float* __restrict__ part_best, const int* 
                                 int* __restrict__ nlist_out, long long* __restrict__ packed,
                                 const uint8_t* __restrict__ r_tiles, uint8_t* __restrict__ c_tiles, int KB,
                                 const int* __restrict__ part_idx2, const float* __restrict__ part_third,
-                                int* __restrict__ cand2, int* __restrict__ pair_list, int* __restrict__ npair) {
+                                int* __restrict__ cand2, int* __restrict__ pair_list, int* __restrict__ npair, int n_valid) {
   const int b = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = r < N;
+  bool live = r < n_valid;                                // rows >= n_valid are padding of the tile image
   int q = r;
   if (list_in) {
     live = live && r < min(nlist_in[b], N);
@@ -476,7 +483,16 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
                                         int col_begin, int col_end, int psplit, int passes, int r_parts,
                                         const int32_t* row_limit, float* part_best, int32_t* part_idx, float* part_second,
                                         int32_t* part_idx2, float* part_third, float* s_dump, void* stream) {
+  return ipsr_correlate_argmax_tc_valid(r_tiles, x_tiles, B, C, N, col_begin, col_end, psplit, passes, r_parts, row_limit, part_best,
+                                        part_idx, part_second, part_idx2, part_third, s_dump, N, stream);
+}
+
+extern "C" int ipsr_correlate_argmax_tc_valid(const void* r_tiles, const void* x_tiles, int B, int C, int N,
+                                              int col_begin, int col_end, int psplit, int passes, int r_parts,
+                                              const int32_t* row_limit, float* part_best, int32_t* part_idx, float* part_second,
+                                              int32_t* part_idx2, float* part_third, float* s_dump, int n_valid, void* stream) {
   using namespace ipsr;
+  IPSR_REQUIRE(n_valid > 0 && n_valid <= N, IPSR_ERR_INVALID_ARG, "ipsr_correlate_argmax_tc: n_valid=%d outside (0, %d]", n_valid, N);
   IPSR_REQUIRE(r_tiles && x_tiles && part_best && part_idx && part_second, IPSR_ERR_INVALID_ARG,
                "ipsr_correlate_argmax_tc: null pointer");
   IPSR_REQUIRE(ipsr_tensor_path_supported(C, N), IPSR_ERR_UNSUPPORTED,
@@ -501,6 +517,7 @@ extern "C" int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles
   prm.part_best = part_best; prm.part_idx = part_idx; prm.part_second = part_second; prm.s_dump = s_dump;
   prm.part_idx2 = (passes == 3 && part_third) ? part_idx2 : nullptr;
   prm.part_third = part_third;
+  prm.n_valid = n_valid;
   cudaStream_t st = as_stream(stream);
   const int AH = passes == 3 ? 2 : 1;
   const size_t a_one = (size_t)(C / kTileK) * AH * kTileBytes;           // resident bytes per 128-row tile
@@ -542,7 +559,22 @@ extern "C" int ipsr_finalize_argmax(const float* part_best, const int32_t* part_
                                     const void* r_tiles, void* c_tiles, int C,
                                     const int32_t* part_idx2, const float* part_third,
                                     int32_t* cand2, int32_t* pair_list, int32_t* npair, void* stream) {
+  return ipsr_finalize_argmax_valid(part_best, part_idx, part_second, psplit, rnorm, rscale, rerr, xerr_max, nonfinite, list_in,
+                                    nlist_in, B, N, tol_rel, tol_abs, ind, list_out, nlist_out, packed, r_tiles, c_tiles, C, part_idx2,
+                                    part_third, cand2, pair_list, npair, N, stream);
+}
+
+extern "C" int ipsr_finalize_argmax_valid(const float* part_best, const int32_t* part_idx, const float* part_second,
+                                          int psplit, const float* rnorm, const float* rscale, const float* rerr,
+                                          const float* xerr_max, const int32_t* nonfinite,
+                                          const int32_t* list_in, const int32_t* nlist_in,
+                                          int B, int N, float tol_rel, float tol_abs,
+                                          int32_t* ind, int32_t* list_out, int32_t* nlist_out, int64_t* packed,
+                                          const void* r_tiles, void* c_tiles, int C,
+                                          const int32_t* part_idx2, const float* part_third,
+                                          int32_t* cand2, int32_t* pair_list, int32_t* npair, int n_valid, void* stream) {
   using namespace ipsr;
+  IPSR_REQUIRE(n_valid > 0 && n_valid <= N, IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: n_valid=%d outside (0, %d]", n_valid, N);
   IPSR_REQUIRE(part_best && part_idx && part_second && rnorm && rscale && ind && list_out && nlist_out,
                IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: null pointer");
   IPSR_REQUIRE(!list_in || nlist_in, IPSR_ERR_INVALID_ARG, "ipsr_finalize_argmax: list_in needs nlist_in");
@@ -557,6 +589,6 @@ extern "C" int ipsr_finalize_argmax(const float* part_best, const int32_t* part_
   finalize_kernel<<<dim3((N + 255) / 256, B), 256, 0, as_stream(stream)>>>(
       part_best, part_idx, part_second, psplit, rnorm, rscale, rerr, xerr_max, nonfinite, list_in, nlist_in, B, N, tol_rel,
       tol_abs, ind, list_out, nlist_out, reinterpret_cast<long long*>(packed), reinterpret_cast<const uint8_t*>(r_tiles),
-      reinterpret_cast<uint8_t*>(c_tiles), c_tiles ? C / kTileK : 0, part_idx2, part_third, cand2, pair_list, npair);
+      reinterpret_cast<uint8_t*>(c_tiles), c_tiles ? C / kTileK : 0, part_idx2, part_third, cand2, pair_list, npair, n_valid);
   return check_launch("ipsr_finalize_argmax");
 }

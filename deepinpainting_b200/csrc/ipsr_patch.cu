@@ -66,27 +66,39 @@ __global__ void __launch_bounds__(256) fold_cols_kernel(const float* __restrict_
 // rows[b][q][kk] (position-major raw patches = decoder weights, NonparametricShift.py:54) and
 // inv_norm[b][q] = 1 / (||patch||_2 + 1e-8) (:40).  One CTA per patch position.
 __global__ void __launch_bounds__(256) patch_rows_kernel(const float* __restrict__ x, PatchGeom g, float* __restrict__ rows,
-                                                         float* __restrict__ inv_norm) {
-  __shared__ float part[8];
+                                                         float* __restrict__ inv_norm, float* __restrict__ norm_out,
+                                                         float* __restrict__ max_out) {
+  __shared__ float part[8], partm[8];
   const int q = blockIdx.x, b = blockIdx.y, P = g.nH * g.nW, kk2 = g.k * g.k;
   const int i = q / g.nW, j = q - i * g.nW;
   const float* xb = x + (size_t)b * g.C * g.H * g.W + (size_t)(i * g.s) * g.W + j * g.s;
   float* dst = rows + ((size_t)b * P + q) * g.K;
-  float ss = 0.f;
+  float ss = 0.f, mx = 0.f;
   for (int kk = threadIdx.x; kk < g.K; kk += blockDim.x) {
     const int c = kk / kk2, d = kk - c * kk2, dy = d / g.k, dx = d - dy * g.k;
     const float v = __ldg(xb + ((size_t)c * g.H + dy) * g.W + dx);
     dst[kk] = v;
     ss = fmaf(v, v, ss);
+    mx = fmaxf(mx, fabsf(v));
   }
-  if (!inv_norm) return;
+  if (!inv_norm && !norm_out && !max_out) return;
   ss = warp_sum(ss);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) {
+    part[threadIdx.x >> 5] = ss;
+    partm[threadIdx.x >> 5] = mx;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float tot = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
-    inv_norm[(size_t)b * P + q] = 1.0f / (sqrtf(tot) + 1e-8f);
+    float tot = 0.f, m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      tot += part[w];
+      m = fmaxf(m, partm[w]);
+    }
+    if (inv_norm) inv_norm[(size_t)b * P + q] = 1.0f / (sqrtf(tot) + 1e-8f);
+    if (norm_out) norm_out[(size_t)b * P + q] = sqrtf(tot);
+    if (max_out) max_out[(size_t)b * P + q] = m;
   }
 }
 
@@ -239,12 +251,17 @@ extern "C" int ipsr_fold_patches(const float* cols, int B, int C, int H, int W, 
 
 extern "C" int ipsr_patch_rows(const float* x, int B, int C, int H, int W, int patch, int stride,
                                float* rows, float* inv_norm, void* stream) {
+  return ipsr_patch_rows_stats(x, B, C, H, W, patch, stride, rows, inv_norm, nullptr, nullptr, stream);
+}
+
+extern "C" int ipsr_patch_rows_stats(const float* x, int B, int C, int H, int W, int patch, int stride,
+                                     float* rows, float* inv_norm, float* norm, float* maxabs, void* stream) {
   using namespace ipsr;
   IPSR_REQUIRE(x && rows, IPSR_ERR_INVALID_ARG, "ipsr_patch_rows: null pointer");
   PatchGeom g;
   IPSR_FORWARD(make_geom("ipsr_patch_rows", B, C, H, W, patch, stride, 0, &g));
   IPSR_REQUIRE(B <= 65535, IPSR_ERR_UNSUPPORTED, "ipsr_patch_rows: B=%d > 65535", B);
-  patch_rows_kernel<<<dim3(g.nH * g.nW, B), 256, 0, as_stream(stream)>>>(x, g, rows, inv_norm);
+  patch_rows_kernel<<<dim3(g.nH * g.nW, B), 256, 0, as_stream(stream)>>>(x, g, rows, inv_norm, norm, maxabs);
   return check_launch("ipsr_patch_rows");
 }
 

@@ -507,27 +507,32 @@ def shift_forward_patches(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, pat
             cols_o, saved = shift_forward(cols_x, cols_r, mi, need_grad=False, mode=mode)
         _lib.call("ipsr_fold_patches", cols_o.data_ptr(), B, Cc, H, W, k, s, Kpad, out.data_ptr(), st)
         return out, saved.ind
-    # wide rows: position-major patches + norms, exact fp32 correlation on the patch maps, register-resident blend
-    cols_x = torch.empty((B, K, P), dtype=torch.float32, device=dev)
-    cols_r = torch.empty((B, K, P), dtype=torch.float32, device=dev)
-    _lib.call("ipsr_unfold_patches", x.data_ptr(), B, Cc, H, W, k, s, K, cols_x.data_ptr(), st)
-    _lib.call("ipsr_unfold_patches", ref.data_ptr(), B, Cc, H, W, k, s, K, cols_r.data_ptr(), st)
+    # wide rows: position-major patches + norms; correlation on the tensor cores (or exact fp32 on the patch maps);
+    # register-resident blend
+    mode_eff = mode or config["correlation_mode"]
     rows = torch.empty((B, P, K), dtype=torch.float32, device=dev)
     inv = torch.empty((B, P), dtype=torch.float32, device=dev)
-    _lib.call("ipsr_patch_rows", x.data_ptr(), B, Cc, H, W, k, s, rows.data_ptr(), inv.data_ptr(), st)
-    packed = torch.empty((B, P), dtype=torch.int64, device=dev)
-    rlist = torch.empty((B, P), dtype=torch.int32, device=dev)
-    nrow = torch.empty((B,), dtype=torch.int32, device=dev)
-    _lib.call("ipsr_select_all_rows", B, P, rlist.data_ptr(), nrow.data_ptr(), packed.data_ptr(), st)
-    cb, ce = (int(col_begin), P if (col_end < 0 or (col_end == 0 and col_begin == 0)) else int(col_end)) if sharded else (0, P)
-    if cb < ce:                                   # an empty shard (more ranks than columns) contributes identity keys
-        _lib.call("ipsr_correlate_argmax_fp32", cols_x.data_ptr(), cols_r.data_ptr(), inv.data_ptr(), B, K, P, cb, ce,
-                  rlist.data_ptr(), nrow.data_ptr(), (P + 63) // 64, packed.data_ptr(), st)
-    if sharded:
-        reduce_max(packed)
     ind = torch.empty((B, P), dtype=torch.int32, device=dev)
     vmax = torch.empty((B, P), dtype=torch.float32, device=dev)
-    _lib.call("ipsr_unpack_maxidx", packed.data_ptr(), B * P, vmax.data_ptr(), ind.data_ptr(), st)
+    cb, ce = (int(col_begin), P if (col_end < 0 or (col_end == 0 and col_begin == 0)) else int(col_end)) if sharded else (0, P)
+    if mode_eff != "exact":
+        ind, vmax = _wide_patch_correlation_tc(x, ref, B, Cc, H, W, k, s, P, K, rows, inv, cb, ce, reduce_max if sharded else None, st)
+    else:
+        cols_x = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+        cols_r = torch.empty((B, K, P), dtype=torch.float32, device=dev)
+        _lib.call("ipsr_unfold_patches", x.data_ptr(), B, Cc, H, W, k, s, K, cols_x.data_ptr(), st)
+        _lib.call("ipsr_unfold_patches", ref.data_ptr(), B, Cc, H, W, k, s, K, cols_r.data_ptr(), st)
+        _lib.call("ipsr_patch_rows", x.data_ptr(), B, Cc, H, W, k, s, rows.data_ptr(), inv.data_ptr(), st)
+        packed = torch.empty((B, P), dtype=torch.int64, device=dev)
+        rlist = torch.empty((B, P), dtype=torch.int32, device=dev)
+        nrow = torch.empty((B,), dtype=torch.int32, device=dev)
+        _lib.call("ipsr_select_all_rows", B, P, rlist.data_ptr(), nrow.data_ptr(), packed.data_ptr(), st)
+        if cb < ce:                                   # an empty shard (more ranks than columns) contributes identity keys
+            _lib.call("ipsr_correlate_argmax_fp32", cols_x.data_ptr(), cols_r.data_ptr(), inv.data_ptr(), B, K, P, cb, ce,
+                      rlist.data_ptr(), nrow.data_ptr(), (P + 63) // 64, packed.data_ptr(), st)
+        if sharded:
+            reduce_max(packed)
+        _lib.call("ipsr_unpack_maxidx", packed.data_ptr(), B * P, vmax.data_ptr(), ind.data_ptr(), st)
     M = mi.M
     y = None
     if M > 0:
@@ -539,6 +544,107 @@ def shift_forward_patches(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, pat
     _lib.call("ipsr_fold_patch_rows", rows.data_ptr(), _ptr(y), ind.data_ptr(), mi.rank.data_ptr(), B, Cc, H, W, k, s, M,
               out.data_ptr(), st)
     return out, ind
+
+
+# error band of the three-pass fp16 split for LONG rows, relative to ||R[q]||: the operand rounding of the split (1.2e-6)
+# plus the fp32 accumulation of K * 3 products in tensor memory (8e-6 covers K <= 512; it grows linearly with K at worst).
+# Rows whose top-2 gap lies inside twice the band are recomputed in exact fp32.
+def _wide_tol_rel(K: int) -> float:
+    return 2.0 * (8e-6 * max(1.0, K / 512.0) + 1.2e-6)
+
+
+def time_wide_patch_correlation(x, ref, patch: int, stride: int, col_begin: int, col_end: int, reps: int = 10):
+    """Measurement helper (bench.py): the stages of the long-row tensor route timed alone with CUDA events on the current
+    stream -- patch rows + statistics, operand images, the tcgen05 GEMM, finalize + resolve + winner scores."""
+    B, Cc, H, W = x.shape
+    nH, nW = patch_grid(H, W, patch, stride)
+    P, K = nH * nW, Cc * patch * patch
+    dev = x.device
+    st = _stream_ptr(dev)
+    rows = torch.empty((B, P, K), dtype=torch.float32, device=dev)
+    inv = torch.empty((B, P), dtype=torch.float32, device=dev)
+    marks = {}
+    out = {"launches_per_step": 13}
+    for r in range(reps + 2):
+        marks.clear()
+        _wide_patch_correlation_tc(x, ref, B, Cc, H, W, patch, stride, P, K, rows, inv, col_begin, col_end, None, st, marks)
+        torch.cuda.synchronize(dev)
+        if r >= 2:
+            names = list(marks)
+            for a, b in zip(names[:-1], names[1:]):
+                out[b + "_ms"] = out.get(b + "_ms", 0.0) + marks[a].elapsed_time(marks[b]) / reps
+    return out
+
+
+def _wide_patch_correlation_tc(x, ref, B, Cc, H, W, k, s, P, K, rows, inv, cb, ce, reduce_max, st, marks=None):
+    """models/IPSRFunction.py:54-65 for long patch rows on the tcgen05 path (ipsr_patch_tc.cu).  Fills ``rows`` / ``inv``
+    (the patches of x) and returns (ind [B,P] int32, vmax [B,P])."""
+    dev = x.device
+
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks[name] = ev
+
+    Kpad, Ppad = -(-K // 64) * 64, -(-P // 128) * 128
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    rows_r = torch.empty((B, P, K), **f32)
+    mark("start")
+    rnorm, rmax = torch.empty((B, P), **f32), torch.empty((B, P), **f32)
+    _lib.call("ipsr_patch_rows_stats", x.data_ptr(), B, Cc, H, W, k, s, rows.data_ptr(), inv.data_ptr(), None, None, st)
+    _lib.call("ipsr_patch_rows_stats", ref.data_ptr(), B, Cc, H, W, k, s, rows_r.data_ptr(), None, rnorm.data_ptr(), rmax.data_ptr(), st)
+    mark("rows")
+    tile_bytes = B * (Kpad // 64) * 2 * (Ppad // 128) * 16384
+    x_tiles = torch.empty((tile_bytes,), dtype=torch.uint8, device=dev)
+    r_tiles = torch.empty((tile_bytes,), dtype=torch.uint8, device=dev)
+    rscale, rnorm_pad = torch.empty((B, Ppad), **f32), torch.empty((B, Ppad), **f32)
+    _lib.call("ipsr_patch_tiles", rows.data_ptr(), inv.data_ptr(), None, None, 0, B, K, P, x_tiles.data_ptr(), None, None, st)
+    _lib.call("ipsr_patch_tiles", rows_r.data_ptr(), None, rmax.data_ptr(), rnorm.data_ptr(), 1, B, K, P, r_tiles.data_ptr(),
+              rscale.data_ptr(), rnorm_pad.data_ptr(), st)
+    mark("tiles")
+    ind_pad = torch.empty((B, Ppad), **i32)
+    packed_pad = torch.empty((B, Ppad), dtype=torch.int64, device=dev)
+    rlist = torch.empty((B, Ppad), **i32)
+    nlist = torch.zeros((B,), **i32)
+    ind = torch.empty((B, P), **i32)
+    vmax = torch.empty((B, P), **f32)
+    keys = torch.empty((B, P), dtype=torch.int64, device=dev)
+    if cb < ce:
+        # this rank's bank columns, in whole 128-column tiles (the last tile may run into the padding, masked by n_valid)
+        if cb % 128 != 0 or (ce % 128 != 0 and ce != P):
+            raise ValueError("bank shards of the tensor path must be 128-column aligned, got [%d, %d)" % (cb, ce))
+        ce_pad = min(Ppad, -(-ce // 128) * 128)
+        tiles_rows = B * (Ppad // 128)
+        psplit = max(1, min(8, 148 // max(1, tiles_rows), (ce_pad - cb) // 128))
+        parts = [torch.empty((psplit, B, Ppad), **f32), torch.empty((psplit, B, Ppad), **i32), torch.empty((psplit, B, Ppad), **f32),
+                 torch.empty((psplit, B, Ppad), **i32), torch.empty((psplit, B, Ppad), **f32)]
+        cand2, pair_list, npair = torch.empty((B, Ppad), **i32), torch.empty((B, Ppad), **i32), torch.zeros((B,), **i32)
+        _lib.call("ipsr_correlate_argmax_tc_valid", r_tiles.data_ptr(), x_tiles.data_ptr(), B, Kpad, Ppad, cb, ce_pad, psplit, 3, 2,
+                  None, parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(), parts[3].data_ptr(), parts[4].data_ptr(),
+                  None, min(ce, P), st)
+        mark("gemm")
+        # rows inside the error band: exactly two candidates -> two exact dot products; three or more (ties, duplicates)
+        # -> the whole bank in fp32
+        _lib.call("ipsr_finalize_argmax_valid", parts[0].data_ptr(), parts[1].data_ptr(), parts[2].data_ptr(), psplit,
+                  rnorm_pad.data_ptr(), rscale.data_ptr(), None, None, None, None, None, B, Ppad, _wide_tol_rel(K), 1e-12,
+                  ind_pad.data_ptr(), rlist.data_ptr(), nlist.data_ptr(), packed_pad.data_ptr(), None, None, Kpad,
+                  parts[3].data_ptr(), parts[4].data_ptr(), cand2.data_ptr(), pair_list.data_ptr(), npair.data_ptr(), P, st)
+        _lib.call("ipsr_patch_recheck", rows.data_ptr(), rows_r.data_ptr(), inv.data_ptr(), B, K, P, cb, ce, rlist.data_ptr(),
+                  nlist.data_ptr(), packed_pad.data_ptr(), st)
+        _lib.call("ipsr_apply_recheck", packed_pad.data_ptr(), rlist.data_ptr(), nlist.data_ptr(), B, Ppad, ind_pad.data_ptr(), None, st)
+        _lib.call("ipsr_patch_resolve_pairs", rows.data_ptr(), rows_r.data_ptr(), inv.data_ptr(), B, K, P, pair_list.data_ptr(),
+                  npair.data_ptr(), cand2.data_ptr(), ind_pad.data_ptr(), packed_pad.data_ptr(), st)
+        _lib.call("ipsr_patch_winner_scores", rows.data_ptr(), rows_r.data_ptr(), inv.data_ptr(), ind_pad.data_ptr(),
+                  packed_pad.data_ptr(), B, K, P, ind.data_ptr(), vmax.data_ptr(), keys.data_ptr(), st)
+        mark("resolve")
+    else:
+        keys.fill_(-(1 << 63))                        # empty shard: identity keys
+    if reduce_max is not None:
+        reduce_max(keys)
+        _lib.call("ipsr_unpack_maxidx", keys.data_ptr(), B * P, vmax.data_ptr(), ind.data_ptr(), st)
+    return ind, vmax
 
 
 def patch_rows(img: torch.Tensor, patch: int, stride: int):

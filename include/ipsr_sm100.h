@@ -118,6 +118,13 @@ int ipsr_correlate_argmax_tc(const void* r_tiles, const void* x_tiles, int B, in
                              const int32_t* row_limit, float* part_best, int32_t* part_idx, float* part_second,
                              int32_t* part_idx2, float* part_third, float* s_dump, void* stream);
 
+/* ipsr_correlate_argmax_tc with padding: bank columns >= n_valid (<= N) never win (patch maps whose position count is
+ * not a multiple of 128 are padded with zero rows up to N). */
+int ipsr_correlate_argmax_tc_valid(const void* r_tiles, const void* x_tiles, int B, int C, int N,
+                                   int col_begin, int col_end, int psplit, int passes, int r_parts,
+                                   const int32_t* row_limit, float* part_best, int32_t* part_idx, float* part_second,
+                                   int32_t* part_idx2, float* part_third, float* s_dump, int n_valid, void* stream);
+
 /* Merge the `psplit` partial (best, idx, second) triples per row, then decide per row:
  *   gap = (best - second) * rscale[b,q] >= tol[q]  -> ind[b,q] = idx (trusted);
  *   otherwise (or when nonfinite[b] != 0) the row is appended to list_out[b] (ind[b,q] = idx provisionally).
@@ -139,6 +146,17 @@ int ipsr_finalize_argmax(const float* part_best, const int32_t* part_idx, const 
                          const void* r_tiles, void* c_tiles, int C,
                          const int32_t* part_idx2, const float* part_third,
                          int32_t* cand2, int32_t* pair_list, int32_t* npair, void* stream);
+
+/* ipsr_finalize_argmax over the first n_valid (<= N) rows only (the others are padding of the tile image). */
+int ipsr_finalize_argmax_valid(const float* part_best, const int32_t* part_idx, const float* part_second,
+                               int psplit, const float* rnorm, const float* rscale, const float* rerr,
+                               const float* xerr_max, const int32_t* nonfinite,
+                               const int32_t* list_in, const int32_t* nlist_in,
+                               int B, int N, float tol_rel, float tol_abs,
+                               int32_t* ind, int32_t* list_out, int32_t* nlist_out, int64_t* packed,
+                               const void* r_tiles, void* c_tiles, int C,
+                               const int32_t* part_idx2, const float* part_third,
+                               int32_t* cand2, int32_t* pair_list, int32_t* npair, int n_valid, void* stream);
 
 /* Select every row for the exact path (IPSR_MODE_EXACT): recheck_list[b] = 0..N-1,
  * nrecheck[b] = N, packed = identity. */
@@ -305,6 +323,34 @@ int ipsr_fold_patches(const float* cols, int B, int C, int H, int W, int patch, 
 /* rows [B][P][K] position-major raw patches and (optional) inv_norm [B][P] = 1/(||patch||_2 + 1e-8). */
 int ipsr_patch_rows(const float* x, int B, int C, int H, int W, int patch, int stride,
                     float* rows, float* inv_norm, void* stream);
+/* the same, plus (optional) norm [B][P] = ||patch||_2 and maxabs [B][P] = max |patch value|. */
+int ipsr_patch_rows_stats(const float* x, int B, int C, int H, int W, int patch, int stride,
+                          float* rows, float* inv_norm, float* norm, float* maxabs, void* stream);
+
+/* Long patch rows (K > 1024) on the tensor cores (BASELINE configs[3]; models/IPSRFunction.py:54-59 with shift_sz = 3).
+ * Kpad = K rounded up to 64, Ppad = P rounded up to 128; every [B][Ppad] array below has row stride Ppad.
+ * ipsr_patch_tiles: rows [B][P][K] -> fp16 hi/lo operand images [B][Kpad/64][2][Ppad/128][128 x 64] (zero padding) for
+ *   ipsr_correlate_argmax_tc_valid (passes = 3, n_valid = P).  is_ref = 0: values fl(fl(x * inv_norm) * 2^11);
+ *   is_ref = 1: values r * 2^s_q (max |.| in [2^13, 2^14)), rscale [B][Ppad] = 2^-(s_q + 11) and rnorm_pad [B][Ppad] =
+ *   norm (padding rows: 1 and 0) for ipsr_finalize_argmax_valid. */
+int ipsr_patch_tiles(const float* rows, const float* inv_norm, const float* maxabs, const float* norm, int is_ref,
+                     int B, int K, int P, void* tiles, float* rscale, float* rnorm_pad, void* stream);
+/* Rows list[b][0 .. nlist[b]) (row stride Ppad) recomputed in fp32 against bank columns [col_begin, col_end):
+ * packed[b][q] (stride Ppad) = max(packed, pack(score, column)) as ipsr_correlate_argmax_fp32 does. */
+int ipsr_patch_recheck(const float* rows_x, const float* rows_r, const float* inv_norm, int B, int K, int P,
+                       int col_begin, int col_end, const int32_t* list, const int32_t* nlist, int64_t* packed, void* stream);
+/* Rows of pair_list (exactly two candidates, ind_pad[b][q] and cand2[b][q], inside the error band: the pair output of
+ * ipsr_finalize_argmax_valid; strides Ppad): two exact fp32 dot products per row; the winner goes to ind_pad and, as an
+ * exact (score, column) key, to packed. */
+int ipsr_patch_resolve_pairs(const float* rows_x, const float* rows_r, const float* inv_norm, int B, int K, int P,
+                             const int32_t* pair_list, const int32_t* npair, const int32_t* cand2, int32_t* ind_pad,
+                             int64_t* packed, void* stream);
+/* Per row q < P: exact fp32 score of its winner ind_pad[b][q] (or the key the recheck left in packed_pad, both with
+ * stride Ppad; packed_pad may be NULL) -> ind [B][P], vmax [B][P] (IPSRFunction.py:70) and keys [B][P] for the
+ * bank-sharded exchange (each optional). */
+int ipsr_patch_winner_scores(const float* rows_x, const float* rows_r, const float* inv_norm, const int32_t* ind_pad,
+                             const int64_t* packed_pad, int B, int K, int P, int32_t* ind, float* vmax, int64_t* keys,
+                             void* stream);
 /* The blend recurrence (IPSRFunction.py:82-126) on rows of K <= 8192 values, one CTA per image:
  * y [B][M][K], wn / wo [B][M] (wn[b,0] = 0, wo[b,0] = 1).  vmax [B][P] = row maxima of the correlation. */
 int ipsr_blend_wide(const float* rows, const float* inv_norm, const float* vmax, const int32_t* ind,

@@ -73,6 +73,34 @@ def _worker(rank, world, port):
                                                            reduce_max=allreduce_max_keys)
             torch.cuda.synchronize()
             assert torch.equal(ind_k, full_ind) and torch.equal(out_k, full_out), (Cp, Hp)
+        # ---- more ranks than 128-column tiles: the surplus ranks own an EMPTY shard, contribute identity keys and must not
+        # fall out of the collective (16 x 16 map: 2 tiles) ----
+        Hs = 16
+        xs = torch.randn(2, 64, Hs, Hs, generator=gen).to(dev)
+        rs = (torch.relu(torch.randn(2, 64, Hs, Hs, generator=gen)) * 3).to(dev)
+        fs = torch.zeros(Hs, Hs, dtype=torch.int64)
+        fs[4:12, 3:11] = 1
+        mis = shift_ops.mask_index_from_flag(fs.view(-1), dev)
+        full_out, full_saved = shift_ops.shift_forward(xs, rs, mis, need_grad=False, mode="tensor")
+        cb, ce = shard_bank(Hs * Hs, world, rank)
+        out_k, saved_k = shift_ops.shift_forward_sharded(xs, rs, mis, cb, ce, allreduce_max_keys, need_grad=False, mode="tensor")
+        torch.cuda.synchronize()
+        assert torch.equal(saved_k.ind, full_saved.ind) and torch.equal(out_k, full_out), (rank, cb, ce)
+        # ---- long patch rows on the tensor route (K = 1152, P = 324 padded to 3 tiles of 128 columns) ----
+        Bp, Cp, Hp = 1, 128, 20
+        xp = torch.randn(Bp, Cp, Hp, Hp, generator=gen).abs().to(dev)
+        rp = (torch.relu(torch.randn(Bp, Cp, Hp, Hp, generator=gen)) * 3).to(dev)
+        feat = torch.zeros(Hp, Hp, dtype=torch.uint8, device=dev)
+        feat[5:12, 4:13] = 1
+        mip = shift_ops.build_flags(feat, 3, 1, 1)
+        P = mip.flag.numel()
+        full_out, full_ind = shift_ops.shift_forward_patches(xp, rp, mip, 3, 1, mode="tensor")
+        cb, ce = shard_bank(-(-P // 128) * 128, world, rank)
+        cb, ce = min(cb, P), min(ce, P)
+        out_k, ind_k = shift_ops.shift_forward_patches(xp, rp, mip, 3, 1, mode="tensor", col_begin=cb, col_end=ce,
+                                                       reduce_max=allreduce_max_keys)
+        torch.cuda.synchronize()
+        assert torch.equal(ind_k, full_ind) and torch.equal(out_k, full_out), (rank, cb, ce)
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -83,5 +111,5 @@ def test_batch_and_bank_sharding_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     mp.spawn(_worker, args=(world, _free_port()), nprocs=world, join=True)

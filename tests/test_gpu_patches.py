@@ -197,6 +197,60 @@ def test_bank_sharded_patches_single_process():
         assert torch.equal(out, full)
 
 
+def test_wide_patch_tensor_route_matches_exact_route_and_shards():
+    """Long patch rows (K = 1152 > 1024) on the tcgen05 path -- P = 324 positions padded to 384, the padding columns masked
+    in the GEMM epilogue -- against the exact fp32 route, unsharded and as three 128-column bank shards merged by MAX."""
+    from deepinpainting_b200 import shift_ops
+    rng = np.random.default_rng(21)
+    B, C, H, k = 2, 128, 20, 3
+    xs = torch.from_numpy(rng.standard_normal((B, C, H, H)).astype(np.float32)).to(DEV)
+    ref = torch.from_numpy(np.abs(rng.standard_normal((B, C, H, H))).astype(np.float32)).to(DEV)
+    feat = torch.zeros(H, H, dtype=torch.uint8, device=DEV)
+    feat[5:12, 4:13] = 1
+    mi = shift_ops.build_flags(feat, k, 1, 1)
+    P = mi.flag.numel()
+    assert P == 324 and C * k * k > shift_ops.PATCH_ROW_LIMIT
+    # signed input, NEGATED reference: every true score is negative, so an unmasked padding column (score 0) would win
+    # everywhere.  (The blend is chaotic on signed data: indices only.)
+    _, ind_e = shift_ops.shift_forward_patches(xs.abs(), -ref, mi, k, 1, mode="exact")
+    _, ind_t = shift_ops.shift_forward_patches(xs.abs(), -ref, mi, k, 1, mode="tensor")
+    gap = _gap64(xs.abs().cpu().numpy(), -ref.cpu().numpy(), k, 1)
+    safe = torch.from_numpy(gap > 1e-4)
+    assert safe.float().mean() > 0.9 and int(ind_t.max()) < P
+    assert torch.equal(ind_t.cpu()[safe], ind_e.cpu()[safe])
+    x = xs.abs()                                                                                # well conditioned from here on
+    out_e, ind_e = shift_ops.shift_forward_patches(x, ref, mi, k, 1, mode="exact")
+    out_t, ind_t = shift_ops.shift_forward_patches(x, ref, mi, k, 1, mode="tensor")
+    torch.cuda.synchronize()
+    gap = _gap64(x.cpu().numpy(), ref.cpu().numpy(), k, 1)
+    safe = torch.from_numpy(gap > 1e-4)
+    assert safe.float().mean() > 0.9
+    assert torch.equal(ind_t.cpu()[safe], ind_e.cpu()[safe])
+    if torch.equal(ind_t, ind_e):
+        assert float((out_t - out_e).abs().max()) <= 1e-4 * float(out_e.abs().max())
+    cuts = [0, 128, 256, P]
+    keys = []
+
+    def grab(t, keys=keys):
+        keys.append(t.clone())
+
+    for r in range(3):
+        shift_ops.shift_forward_patches(x, ref, mi, k, 1, mode="tensor", col_begin=cuts[r], col_end=cuts[r + 1], reduce_max=grab)
+    merged = torch.stack(keys).max(dim=0).values
+
+    def put(t, merged=merged):
+        t.copy_(merged)
+
+    out_s, ind_s = shift_ops.shift_forward_patches(x, ref, mi, k, 1, mode="tensor", col_begin=0, col_end=128, reduce_max=put)
+    torch.cuda.synchronize()
+    assert torch.equal(ind_s, ind_t)
+    assert torch.equal(out_s, out_t)
+    # an empty shard (more ranks than 128-column tiles) contributes identity keys
+    keys.clear()
+    shift_ops.shift_forward_patches(x, ref, mi, k, 1, mode="tensor", col_begin=P, col_end=P, reduce_max=grab)
+    assert bool((keys[0] == -(1 << 63)).all())
+
+
 def test_nonparametricshift_patches_k3():
     from deepinpainting_b200.util.NonparametricShift import NonparametricShift
     rng = np.random.default_rng(3)
