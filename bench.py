@@ -51,10 +51,12 @@ def parse_args():
     ap.add_argument("--cpu-images", type=int, default=0, help="images of the CPU-baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1234, help="synthetic data seed (rank r uses seed + r)")
-    ap.add_argument("--workload", default="shift", choices=["shift", "patch3x3"],
+    ap.add_argument("--workload", default="shift", choices=["shift", "patch3x3", "generator"],
                     help="shift: configs[1] / configs[2], fwd+bwd of the 1x1 layer (the default line); patch3x3: configs[3], the "
                          "reference-guided forward with 3x3 patches on a 64x64x256 map (forward only: the reference has no backward "
-                         "for shift_sz != 1)")
+                         "for shift_sz != 1); generator: configs[4], the full generator training step (rough + refinement U-Net in "
+                         "bf16 around the shift layer, per-sample free-form masks, Adam; DDP with several GPUs)")
+    ap.add_argument("--gen-batch", type=int, default=32, help="images per GPU and step of the generator workload")
     ap.add_argument("--shard", default="batch", choices=["batch", "bank"],
                     help="with several GPUs: split the batch (no data-path collective) or, for patch3x3, split the patch BANK "
                          "across the ranks and merge the (max, idx) keys with one NCCL all-reduce MAX")
@@ -206,6 +208,17 @@ def run_reference(args):
         pool = threadpool_limits(limits=_host_threads())
     except Exception as exc:                                       # keep the launcher's setting
         sys.stderr.write("threadpoolctl unavailable (%s): BLAS threads as configured by the environment\n" % exc)
+    if args.workload == "generator":
+        base = cpu_generator_baseline(max(1, min(args.steps, 3)))
+        if base is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not staged on this box (python oracle/build_ref.py)"}), flush=True)
+            return
+        line = {"impl": "reference", "metric": GEN_METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
+                "warmup": 1, "ms_per_step": 1e3 / base["value"] * args.gen_batch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": gen_config(args.gen_batch, 1, False), "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
     if args.workload == "patch3x3":
         C, H = args.channels, 64 if args.size == WORKLOAD["H"] else args.size
         steps = max(1, min(args.steps, 2))
@@ -378,6 +391,7 @@ def measure(args, B, C, H, K, W_, world, rank, local, dev, dist, pk, with_cpu, e
     corr_ms = statistics.mean(p[0].elapsed_time(p[1]) for p in pairs)
     tensor_mode = args.mode == "tensor" or (args.mode == "auto" and C % 64 == 0 and N % 128 == 0)
     cascade = tensor_mode and L.load().ipsr_tensor_cascade(B, C, N) == 1
+    full_passes = L.load().ipsr_tensor_full_passes(B, C, N) if tensor_mode else 1
     flops = 2.0 * N * N * C * B                                    # algorithmic: one N x N x C correlation per image
     achieved = flops / (corr_ms * 1e-3) / 1e12
     # DRAM bytes per launch: NOT measured in this run -- read from the committed ncu --set full capture of the same
@@ -393,12 +407,17 @@ def measure(args, B, C, H, K, W_, world, rank, local, dev, dist, pk, with_cpu, e
                 traffic = next((v for k, v in tj_all.items() if pick in k), None)
                 traffic_src = "profiles/" + fname + " (ncu --set full capture of this command, committed; not re-measured in this run)"
     peak_tf = pk["tf_burst"]                                      # the kernel is timed alone by its own event pair: burst peak
-    roofline = {"bound": "tensor", "kernel": ("corr_tc_kernel pass 1 (tcgen05 fp16 hi*hi over every row; ambiguous rows are redone by the 3-pass split)" if cascade else "corr_tc_kernel (tcgen05 fp16, 3-pass split hi*lo + lo*hi + hi*hi over every row: small problem, ceiling = 1/3 of peak)") if tensor_mode else "corr_fp32_kernel (FFMA)",
+    kname = "corr_fp32_kernel (FFMA)"
+    if tensor_mode:
+        kname = ("corr_tc_kernel pass 1 (tcgen05 fp16 hi*hi over every row; ambiguous rows are redone by the 3-pass split)" if cascade
+                 else "corr_tc_kernel, one tcgen05 fp16 hi*hi pass over every row with the per-row decision in its epilogue (rows inside the rigorous error band: two exact fp32 dot products, or the exact fp32 correlation)" if full_passes == 1
+                 else "corr_tc_kernel (tcgen05 fp16, 3-pass split hi*lo + lo*hi + hi*hi over every row: ceiling = 1/3 of peak)")
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "frac_of_sustained_peak": achieved / pk["tf_sustained"],
                 "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": corr_ms, "share_of_step": corr_ms / (ms_max / K),
-                "issued_passes": (1 if cascade else 3) if tensor_mode else 1,
-                "tensor_pipe_utilisation": (achieved * ((1 if cascade else 3) if tensor_mode else 1)) / peak_tf,
+                "issued_passes": full_passes,
+                "tensor_pipe_utilisation": (achieved * full_passes) / peak_tf,
                 "peak_source": pk["source"] + " bf16 dense, burst (kernel timed alone by its own event pair)",
                 "note": "achieved = algorithmic FLOPs (2*N^2*C per image) / time of the timed correlation launch (event pair recorded by the library around it); tensor_pipe_utilisation counts the MMA passes actually issued (3 for the split over every row that small problems run, 1 for pass 1 of the cascade)"}
 
@@ -588,6 +607,7 @@ def measure(args, B, C, H, K, W_, world, rank, local, dev, dist, pk, with_cpu, e
     cfg.update({"cuda_graphs": graphs is not None,
                 "correlation": ("fp32 results; tcgen05 fp16 hi/lo split with fp32 accumulation ("
                                 + ("precision cascade: 1 pass, 3-pass split on the ambiguous rows" if cascade
+                                   else "1 pass, rows inside the rigorous error band settled in exact fp32" if full_passes == 1
                                    else "3-pass split over every row") + "), ties and ambiguous rows resolved in exact fp32")
                                if tensor_mode else "fp32 FFMA",
                 "l2": "rotating pool of %d input sets (%d MB) > 126 MB L2" % (pool, pool * bytes_per_set >> 20)})
@@ -603,6 +623,165 @@ def measure(args, B, C, H, K, W_, world, rank, local, dev, dist, pk, with_cpu, e
 
 
 PATCH_METRIC = "patch3x3_forward_images_per_sec"
+GEN_METRIC = "generator_training_step_images_per_sec"
+
+
+def freeform_masks(B, S, seed):
+    """One free-form mask per sample: a few random rectangles (bool [B,1,S,S], True = hole)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    m = np.zeros((B, 1, S, S), bool)
+    for b in range(B):
+        for _ in range(4):
+            y, x = rng.integers(0, S - S // 4, 2)
+            h, w = rng.integers(S // 16, S // 3, 2)
+            m[b, 0, y:y + h, x:x + w] = True
+    return m
+
+
+def gen_config(B, world, bf16):
+    return {"workload": "configs[4]: full generator training step -- rough U-Net netP + refinement U-Net netG (shift layer, InnerCos, "
+                        "InnerCos2 at 32x32x512) + VGG-16 relu4_3 of reference and ground truth, 256^2 images, one free-form mask per "
+                        "sample, L1 losses, Adam; discriminators / GAN loss out of scope",
+            "batch_per_gpu": B, "global_batch": B * world, "image": 256, "convs": "cuDNN " + ("bf16 autocast, channels_last" if bf16 else "fp32"),
+            "shift_layer": "fp32 results (tcgen05 fp16 split + exact recheck), per-sample masks in one batched call",
+            "parallelism": "DDP x%d (NCCL gradient all-reduce overlapped with backward); the shift layer needs no collective" % world}
+
+
+def measure_generator(args, world, rank, local, dev, dist, pk):
+    import torch
+    from deepinpainting_b200 import generator as G
+    B, S = args.gen_batch, 256
+    step = G.GeneratorStep(dev, bf16=True, ddp=world > 1, seed=args.seed)
+    gen = torch.Generator(device="cpu").manual_seed(args.seed + rank)
+    pool = 3
+    batches = []
+    for i in range(pool):
+        img = torch.rand(B, 3, S, S, generator=gen) * 2 - 1
+        ref = torch.rand(B, 3, S, S, generator=gen) * 2 - 1
+        mask = torch.from_numpy(freeform_masks(B, S, args.seed + 100 * rank + i))
+        batches.append((img, mask, ref))
+    dbatches = [(a.to(dev), m.to(dev), r.to(dev)) for a, m, r in batches]
+    # time spent inside the shift layer (forward) per step, by events around the module
+    layer = step.shift_layers[0]
+    marks = []
+    layer.register_forward_pre_hook(lambda m, i: marks.append([torch.cuda.Event(enable_timing=True), None]) or marks[-1][0].record())
+
+    def post(m, i, o):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks[-1][1] = ev
+    layer.register_forward_hook(post)
+
+    def one(i, host=False):
+        if host:
+            a, m, r = (t.pin_memory() if not t.is_pinned() else t for t in batches[i % pool])
+            a, m, r = a.to(dev, non_blocking=True), m.to(dev, non_blocking=True), r.to(dev, non_blocking=True)
+        else:
+            a, m, r = dbatches[i % pool]
+        step.set_input(a, m, r)
+        return step.optimize_parameters()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W_, K = max(3, min(args.warmup, 5)), min(args.steps, 30)
+    for i in range(W_):
+        one(i)
+    sync_all()
+    marks.clear()
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        one(W_ + i)
+    e1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms_max = max_over_ranks(e0.elapsed_time(e1))
+    shift_fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in marks if b is not None) if marks else None
+    value = world * B * K / (ms_max * 1e-3)
+    # e2e: pinned host batches in, the loss value out, every step
+    pinned = [tuple(t.pin_memory() for t in b_) for b_ in batches]
+    batches[:] = pinned
+    for i in range(2):
+        float(one(i, host=True))
+    sync_all()
+    EK = max(5, K // 2)
+    t0 = time.perf_counter()
+    for i in range(EK):
+        float(one(i, host=True))                          # .item(): the D2H read of the step's result
+    sync_all()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * B * EK / wall, "unit": UNIT, "h2d_bytes_per_step": B * (2 * 3 * S * S * 4 + S * S), "d2h_bytes_per_step": 4,
+           "steps": EK, "api": "deepinpainting_b200.generator.GeneratorStep.set_input + optimize_parameters, pinned host batches, loss.item() per step",
+           "timing": "host wall clock around the region (every step ends in a device -> host read), max over ranks"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_generator_baseline()
+    if rank != 0:
+        return None
+    return {"metric": GEN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 convolutions, f32 shift layer", "data": "synthetic",
+            "config": gen_config(B, world, True), "shift_layer_forward_ms": shift_fwd_ms,
+            "shift_layer_forward_share": (shift_fwd_ms / (ms_max / K)) if shift_fwd_ms else None,
+            "roofline": None, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": 12 * K}
+
+
+def cpu_generator_baseline(steps=2):
+    """The reference's own generator (models/networks.py, unmodified, staged under oracle/_ref) with the reference's own
+    shift layer on the host CPU: forward + backward of netP and netG on ONE image per step (the reference's batch size)."""
+    import torch
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return None
+    threads = _host_threads()
+    torch.set_num_threads(threads)
+    ref_runner.modules()
+    root = ref_runner.reference_dir()
+    with ref_runner.cpu_shim():
+        sys.path.insert(0, root)
+        try:
+            import models.networks as ref_networks
+        finally:
+            sys.path.remove(root)
+
+        class Opt:
+            threshold, fixed_mask, shift_sz, stride, mask_thred, triple_weight, strength, skip = 5 / 16.0, 1, 1, 1, 1, 1, 1, 0
+        S = 256
+        mask = torch.zeros(1, 1, S, S, dtype=torch.bool)
+        mask[:, :, S // 4:3 * S // 4, S // 4:3 * S // 4] = True
+        netG, cos, cos2, shift = ref_networks.define_G(6, 3, 64, "unet_ipsr", Opt, mask, "instance", False, "normal", [], 0.02)
+        netP, _, _, _ = ref_networks.define_G(3, 3, 64, "unet_256", Opt, mask, "instance", False, "normal", [], 0.02)
+        import collections
+        R = collections.namedtuple("R", ["relu4_3"])
+        total = 0.0
+        for i in range(steps + 1):
+            img = torch.rand(1, 3, S, S) * 2 - 1
+            for m in shift:
+                m.set_mask(mask, 3, Opt.threshold)
+                m.set_ref(R(torch.relu(torch.randn(1, 512, 32, 32))))
+            for m in cos + cos2:
+                m.set_mask(mask, Opt)
+                m.set_target(torch.relu(torch.randn(1, 512, 32, 32)))
+            t0 = time.perf_counter()
+            p = netP(img)
+            out = netG(torch.cat([p, img], 1))
+            ((out - img).abs().mean() + (p - img).abs().mean()).backward()
+            if i > 0:
+                total += time.perf_counter() - t0
+    return {"value": steps / total, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": "%d steps x 1 image: forward + backward of the reference's netP and netG (VGG and optimiser left out), fp32, %.1f s" % (steps, total)}
 
 
 def patch_config(B, C, H, k, world, shard):
@@ -770,8 +949,8 @@ def run_ours(args):
     shift_ops.config["correlation_mode"] = args.mode
     pk = peaks()
     B, C, H = args.batch, args.channels, args.size
-    if args.workload == "patch3x3":
-        line = measure_patch(args, world, rank, local, dev, dist, pk)
+    if args.workload in ("patch3x3", "generator"):
+        line = (measure_patch if args.workload == "patch3x3" else measure_generator)(args, world, rank, local, dev, dist, pk)
         if rank == 0:
             print(json.dumps(line), flush=True)
         if world > 1:

@@ -47,8 +47,11 @@ SIGNATURES = {
     "ipsr_abi_fwd_args_bytes": (_i, []),
     "ipsr_tensor_path_supported": (_i, [_i, _i]),
     "ipsr_tensor_cascade": (_i, [_i, _i, _i]),
+    "ipsr_tensor_full_passes": (_i, [_i, _i, _i]),
     "ipsr_feat_mask": (_i, [_p, _i, _i, _i, _f, _p, _p, _p]),
     "ipsr_build_flags": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ipsr_feat_mask_batch": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p]),
+    "ipsr_build_flags_batch": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ipsr_extract_normalize": (_i, [_p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ipsr_compact_rows": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ipsr_correlate_argmax_tc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -87,6 +90,8 @@ SIGNATURES = {
     "ipsr_fold_patches": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "ipsr_patch_rows": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ipsr_blend_wide": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "ipsr_blend_wide_gram_floats": (_i, [_i, _i]),
+    "ipsr_blend_wide_blocked": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "ipsr_fold_patch_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "ipsr_shift_bwd_masks": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _f, _p, _i, _p, _p]),
     "innercos_loss_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p]),

@@ -231,6 +231,20 @@ extern "C" int ipsr_tensor_cascade(int B, int C, int N) {
   return ((long long)B * rb * rb * (C / ipsr::kTileK) >= min_work) ? 1 : 0;
 }
 
+// tensor passes over EVERY row that ipsr_shift_forward issues for a whole-bank call of this size: 1 = one hi*hi pass (the
+// cascade, or its "lite" form on small problems without a column split), 3 = the three-pass split over every row
+extern "C" int ipsr_tensor_full_passes(int B, int C, int N) {
+  if (!ipsr_tensor_path_supported(C, N)) return 0;
+  if (ipsr_tensor_cascade(B, C, N)) return 1;
+  const char* e = getenv("IPSR_DIRECT_PASSES");
+  if (!(e && atoi(e) == 1)) return 3;
+  long long tiles = (long long)B * (N / ipsr::kTileRows);
+  int ps = (int)(148 / (tiles > 0 ? tiles : 1));
+  if (ps > ipsr::kMaxPsplit) ps = ipsr::kMaxPsplit;
+  if (ps > N / 128) ps = N / 128;
+  return ps <= 1 ? 1 : 3;
+}
+
 extern "C" size_t ipsr_workspace_bytes(int B, int C, int H, int W, int M, int mode) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || M < 0) return 0;
   return ipsr::carve(B, C, H * W, M, mode).total;
@@ -303,16 +317,39 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
     if (direct) {
       const int ps = auto_split((long long)B * RB);
       IPSR_FORWARD(record(a->ev_corr_begin));
-      IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps, 3, 2, nullptr,
-                                            at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
-                                            at<float>(a, w.part_second), at<int32_t>(a, w.part_idx2),
-                                            at<float>(a, w.part_third), nullptr, stream));
-      IPSR_FORWARD(record(a->ev_corr_end));
-      IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
-                                        ps, at<float>(a, w.rnorm), at<float>(a, w.rscale), nullptr, nullptr, nonfinite,
-                                        nullptr, nullptr, B, N, tol_rel, tol_abs, a->ind, list, nrecheck, packed, nullptr,
-                                        nullptr, C, at<int32_t>(a, w.part_idx2), at<float>(a, w.part_third),
-                                        at<int32_t>(a, w.cand2), at<int32_t>(a, w.pair_list), npair, stream));
+      if (ps == 1 && cb == 0 && ce == N) {
+        // No column split: the epilogue decides per row itself (one launch less).  IPSR_DIRECT_PASSES=1 (A/B runs) replaces
+        // the three-pass split by ONE hi*hi pass ("cascade lite": rows inside the rigorous single-pass band are settled by
+        // two exact dot products or the exact fp32 correlation, no second tensor launch) -- measured SLOWER at configs[1]
+        // (166 us per step against 144 us): tracking the third-best score doubles the work of the epilogue, which already
+        // limits this kernel, and 3 rows per image reach the fp32 correlation.
+        static const int direct_passes = [] {
+          const char* e = getenv("IPSR_DIRECT_PASSES");
+          return (e && atoi(e) == 1) ? 1 : 3;
+        }();
+        TcFinalize fin;
+        fin.rnorm = at<float>(a, w.rnorm); fin.rscale = at<float>(a, w.rscale); fin.nonfinite = nonfinite;
+        fin.rerr = direct_passes == 1 ? at<float>(a, w.rerr) : nullptr;
+        fin.xerr_max = direct_passes == 1 ? xerr_max : nullptr;
+        fin.tol_rel = direct_passes == 1 ? kAccumAllowance : tol_rel; fin.tol_abs = tol_abs;
+        fin.ind = a->ind; fin.list = list; fin.nlist = nrecheck; fin.packed = packed;
+        fin.cand2 = at<int32_t>(a, w.cand2); fin.pair_list = at<int32_t>(a, w.pair_list); fin.npair = npair;
+        IPSR_FORWARD(correlate_argmax_tc_ex(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, 1, direct_passes, 2, nullptr,
+                                            at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
+                                            at<int32_t>(a, w.part_idx2), at<float>(a, w.part_third), nullptr, N, &fin, stream));
+        IPSR_FORWARD(record(a->ev_corr_end));
+      } else {
+        IPSR_FORWARD(ipsr_correlate_argmax_tc(at<void>(a, w.r_tiles), at<void>(a, w.x_tiles), B, C, N, cb, ce, ps, 3, 2, nullptr,
+                                              at<float>(a, w.part_best), at<int32_t>(a, w.part_idx),
+                                              at<float>(a, w.part_second), at<int32_t>(a, w.part_idx2),
+                                              at<float>(a, w.part_third), nullptr, stream));
+        IPSR_FORWARD(record(a->ev_corr_end));
+        IPSR_FORWARD(ipsr_finalize_argmax(at<float>(a, w.part_best), at<int32_t>(a, w.part_idx), at<float>(a, w.part_second),
+                                          ps, at<float>(a, w.rnorm), at<float>(a, w.rscale), nullptr, nullptr, nonfinite,
+                                          nullptr, nullptr, B, N, tol_rel, tol_abs, a->ind, list, nrecheck, packed, nullptr,
+                                          nullptr, C, at<int32_t>(a, w.part_idx2), at<float>(a, w.part_third),
+                                          at<int32_t>(a, w.cand2), at<int32_t>(a, w.pair_list), npair, stream));
+      }
     } else {
       // pass 1: hi * hi over every row.  Two row tiles per CTA halve the L2 -> SM traffic of the streamed bank tiles:
       // prefer them (with a column split that brings the CTA count back up) whenever that still occupies most SMs

@@ -62,6 +62,20 @@ int paste_with_bookkeeping_ex(const float* x, const float* y, const int32_t* ind
                               float* out, int32_t* route_ptr, int32_t* route_q, int32_t* exc_start, int32_t* exc_cnt,
                               int32_t* exc_l, float* exc_w, int32_t* exc_total, int exc_cap, void* stream, int ms,
                               const int32_t* mcount);
+// The decision of ipsr_finalize_argmax folded into the GEMM epilogue (launches without a column split: the epilogue
+// thread already holds the row's best / runner-up / third-best): trusted rows get ind, rows with exactly two
+// candidates inside the error band go to pair_list, the others to list; packed is reset.
+struct TcFinalize {
+  const float* rnorm; const float* rscale; const int32_t* nonfinite;
+  const float* rerr; const float* xerr_max;   // non-NULL: the rigorous bound of the SINGLE pass (ipsr_finalize_argmax), else the split's
+  float tol_rel, tol_abs;
+  int32_t* ind; int32_t* list; int32_t* nlist; int64_t* packed;
+  int32_t* cand2; int32_t* pair_list; int32_t* npair;
+};
+int correlate_argmax_tc_ex(const void* r_tiles, const void* x_tiles, int B, int C, int N, int col_begin, int col_end, int psplit,
+                           int passes, int r_parts, const int32_t* row_limit, float* part_best, int32_t* part_idx,
+                           float* part_second, int32_t* part_idx2, float* part_third, float* s_dump, int n_valid,
+                           const TcFinalize* fin, void* stream);
 bool tc_pass1_wide(int B, int C, int N, int col_begin, int col_end, int psplit);
 int build_routes_ex(const int32_t* ind, const int32_t* flag, const int32_t* mask_idx, int B, int N, int M,
                     int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount);

@@ -46,6 +46,7 @@ struct TcParams {
   int* part_idx2;           // PASSES 3 only (optional): column of the runner-up and the third-best score, so that rows
   float* part_third;        // with exactly two candidates inside the error band need two exact dot products, not N
   float* s_dump;
+  TcFinalize fin;           // fin.ind != NULL: decide per row right here (psplit == 1, PASSES == 3)
   int n_valid;              // bank columns >= n_valid are padding (patch maps whose position count is no multiple of 128):
                             // they never win
 };
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
     const int q = (rbg * ROWT + rt) * kTileRows + row;   // (compact) row index
     float best = -INFINITY, second = -INFINITY, third = -INFINITY;
     int bidx = prm.col_begin + blk0 * kBlockN, sidx = bidx;
-    const bool top3 = (PASSES == 3) && prm.part_idx2 != nullptr;
+    const bool top3 = prm.part_idx2 != nullptr;
     float* dump = prm.s_dump ? prm.s_dump + ((size_t)b * prm.N + q) * prm.N : nullptr;
     for (int j = 0; j < nblk; ++j) {
       const int as = j & 1;
@@ -294,13 +295,33 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
       }
 
     }
-    const size_t o = ((size_t)split * prm.B + b) * prm.N + q;
-    prm.part_best[o] = best;
-    prm.part_idx[o] = bidx;
-    prm.part_second[o] = second;
-    if (top3) {
-      prm.part_idx2[o] = sidx;
-      prm.part_third[o] = third;
+    if (prm.fin.ind != nullptr) {
+      // the finalize decision inline (same arithmetic as finalize_kernel)
+      const TcFinalize& f = prm.fin;
+      const size_t bq = (size_t)b * prm.N + q;
+      const float rn = f.rnorm[bq], rs = f.rscale[bq];
+      const float tol = f.rerr ? fmaf(2.0f, fmaf(rn, fmaf(1.001f, f.xerr_max[b], f.tol_rel), f.rerr[bq]), f.tol_abs)   // single pass
+                               : fmaf(f.tol_rel, rn, f.tol_abs);                                                      // three-pass split
+      const float gap = __fmul_rn(best - second, rs);
+      const bool bad = (f.nonfinite && f.nonfinite[b] != 0);
+      f.ind[bq] = bidx;                                      // provisional for untrusted rows
+      bool amb = bad || !(gap >= tol);                       // !(gap >= tol) also catches NaN and the all -inf row
+      if (amb && top3 && !bad && (__fmul_rn(best - third, rs) >= tol)) {
+        amb = false;                                         // exactly two candidates: two exact dot products settle the row
+        f.cand2[bq] = sidx;
+        f.pair_list[(size_t)b * prm.N + atomicAdd(f.npair + b, 1)] = q;
+      }
+      if (amb) f.list[(size_t)b * prm.N + atomicAdd(f.nlist + b, 1)] = q;
+      if (f.packed) f.packed[bq] = kPackedIdentity;
+    } else {
+      const size_t o = ((size_t)split * prm.B + b) * prm.N + q;
+      prm.part_best[o] = best;
+      prm.part_idx[o] = bidx;
+      prm.part_second[o] = second;
+      if (top3) {
+        prm.part_idx2[o] = sidx;
+        prm.part_third[o] = third;
+      }
     }
   }
 
@@ -491,7 +512,19 @@ extern "C" int ipsr_correlate_argmax_tc_valid(const void* r_tiles, const void* x
                                               int col_begin, int col_end, int psplit, int passes, int r_parts,
                                               const int32_t* row_limit, float* part_best, int32_t* part_idx, float* part_second,
                                               int32_t* part_idx2, float* part_third, float* s_dump, int n_valid, void* stream) {
+  return ipsr::correlate_argmax_tc_ex(r_tiles, x_tiles, B, C, N, col_begin, col_end, psplit, passes, r_parts, row_limit, part_best,
+                                      part_idx, part_second, part_idx2, part_third, s_dump, n_valid, nullptr, stream);
+}
+
+int ipsr::correlate_argmax_tc_ex(const void* r_tiles, const void* x_tiles, int B, int C, int N, int col_begin, int col_end, int psplit,
+                                 int passes, int r_parts, const int32_t* row_limit, float* part_best, int32_t* part_idx,
+                                 float* part_second, int32_t* part_idx2, float* part_third, float* s_dump, int n_valid,
+                                 const TcFinalize* fin, void* stream) {
   using namespace ipsr;
+  IPSR_REQUIRE(!fin || (psplit == 1 && n_valid == N && !row_limit && fin->ind && fin->rnorm && fin->rscale && fin->list &&
+                        fin->nlist && (!part_third || (fin->cand2 && fin->pair_list && fin->npair)) &&
+                        (passes == 3 || (fin->rerr && fin->xerr_max))),
+               IPSR_ERR_INVALID_ARG, "ipsr_correlate_argmax_tc: the fused finalize needs psplit = 1 and the whole operand");
   IPSR_REQUIRE(n_valid > 0 && n_valid <= N, IPSR_ERR_INVALID_ARG, "ipsr_correlate_argmax_tc: n_valid=%d outside (0, %d]", n_valid, N);
   IPSR_REQUIRE(r_tiles && x_tiles && part_best && part_idx && part_second, IPSR_ERR_INVALID_ARG,
                "ipsr_correlate_argmax_tc: null pointer");
@@ -515,9 +548,11 @@ extern "C" int ipsr_correlate_argmax_tc_valid(const void* r_tiles, const void* x
   prm.psplit = psplit;
   prm.stages = 0;
   prm.part_best = part_best; prm.part_idx = part_idx; prm.part_second = part_second; prm.s_dump = s_dump;
-  prm.part_idx2 = (passes == 3 && part_third) ? part_idx2 : nullptr;
+  prm.part_idx2 = part_third ? part_idx2 : nullptr;       // runner-up column + third-best score (pair resolve)
   prm.part_third = part_third;
   prm.n_valid = n_valid;
+  if (fin) prm.fin = *fin;
+  else memset(&prm.fin, 0, sizeof(prm.fin));
   cudaStream_t st = as_stream(stream);
   const int AH = passes == 3 ? 2 : 1;
   const size_t a_one = (size_t)(C / kTileK) * AH * kTileBytes;           // resident bytes per 128-row tile

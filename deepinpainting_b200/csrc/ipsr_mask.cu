@@ -10,6 +10,8 @@ namespace ipsr {
 // integer count / 16^L is the same number.
 template <typename TIn>
 __global__ void box4s2_kernel(const TIn* __restrict__ in, int Hi, int Wi, int* __restrict__ out, int Ho, int Wo) {
+  in += (size_t)blockIdx.y * Hi * Wi;                      // blockIdx.y: image of the batch
+  out += (size_t)blockIdx.y * Ho * Wo;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ho * Wo) return;
   const int oy = i / Wo, ox = i % Wo;
@@ -30,12 +32,16 @@ __global__ void box4s2_kernel(const TIn* __restrict__ in, int Hi, int Wi, int* _
 
 __global__ void threshold_kernel(const int* __restrict__ in, int n, float scale, float threshold,
                                  uint8_t* __restrict__ out) {
+  in += (size_t)blockIdx.y * n;
+  out += (size_t)blockIdx.y * n;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = (__fmul_rn((float)in[i], scale) > threshold) ? 1 : 0;   // `> threshold` util/util.py:82
 }
 
 __global__ void threshold_u8_kernel(const uint8_t* __restrict__ in, int n, float threshold, uint8_t* __restrict__ out) {
+  in += (size_t)blockIdx.y * n;
+  out += (size_t)blockIdx.y * n;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = ((float)in[i] > threshold) ? 1 : 0;
@@ -48,6 +54,11 @@ build_flags_kernel(const uint8_t* __restrict__ feat, int H, int W, int k, int st
   __shared__ int warp_tot[32];
   __shared__ int carry;
   const int P = nH * nW;
+  feat += (size_t)blockIdx.x * H * W;                      // blockIdx.x: image of the batch (rows of P entries each)
+  flag += (size_t)blockIdx.x * P;
+  mask_idx += (size_t)blockIdx.x * P;
+  rank += (size_t)blockIdx.x * P;
+  count += blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
@@ -91,8 +102,14 @@ build_flags_kernel(const uint8_t* __restrict__ feat, int H, int W, int k, int st
 
 extern "C" int ipsr_feat_mask(const uint8_t* mask_u8, int S_h, int S_w, int conv_layers, float threshold,
                               uint8_t* feat_u8, int32_t* scratch_i32, void* stream) {
+  return ipsr_feat_mask_batch(mask_u8, 1, S_h, S_w, conv_layers, threshold, feat_u8, scratch_i32, stream);
+}
+
+extern "C" int ipsr_feat_mask_batch(const uint8_t* mask_u8, int B, int S_h, int S_w, int conv_layers, float threshold,
+                                    uint8_t* feat_u8, int32_t* scratch_i32, void* stream) {
   using namespace ipsr;
   IPSR_REQUIRE(mask_u8 && feat_u8, IPSR_ERR_INVALID_ARG, "ipsr_feat_mask: null pointer");
+  IPSR_REQUIRE(B > 0 && B <= 65535, IPSR_ERR_INVALID_ARG, "ipsr_feat_mask: bad batch %d", B);
   IPSR_REQUIRE(S_h > 0 && S_w > 0 && conv_layers >= 0 && conv_layers <= 5, IPSR_ERR_INVALID_ARG,
                "ipsr_feat_mask: bad arguments S=%dx%d layers=%d", S_h, S_w, conv_layers);
   IPSR_REQUIRE((S_h % (1 << conv_layers)) == 0 && (S_w % (1 << conv_layers)) == 0, IPSR_ERR_UNSUPPORTED,
@@ -100,40 +117,47 @@ extern "C" int ipsr_feat_mask(const uint8_t* mask_u8, int S_h, int S_w, int conv
   cudaStream_t st = as_stream(stream);
   if (conv_layers == 0) {
     const int n = S_h * S_w;
-    threshold_u8_kernel<<<(n + 255) / 256, 256, 0, st>>>(mask_u8, n, threshold, feat_u8);
+    threshold_u8_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(mask_u8, n, threshold, feat_u8);
     return check_launch("ipsr_feat_mask");
   }
   IPSR_REQUIRE(scratch_i32, IPSR_ERR_INVALID_ARG, "ipsr_feat_mask: scratch is null");
   int Hi = S_h, Wi = S_w;
-  int* buf[2] = {scratch_i32, scratch_i32 + (size_t)(S_h / 2) * (S_w / 2)};
+  int* buf[2] = {scratch_i32, scratch_i32 + (size_t)B * (S_h / 2) * (S_w / 2)};
   const int* cur = nullptr;
   for (int l = 0; l < conv_layers; ++l) {
     const int Ho = Hi / 2, Wo = Wi / 2;
     int* dst = buf[l & 1];
     const int n = Ho * Wo;
-    if (l == 0) box4s2_kernel<uint8_t><<<(n + 255) / 256, 256, 0, st>>>(mask_u8, Hi, Wi, dst, Ho, Wo);
-    else box4s2_kernel<int><<<(n + 255) / 256, 256, 0, st>>>(cur, Hi, Wi, dst, Ho, Wo);
+    if (l == 0) box4s2_kernel<uint8_t><<<dim3((n + 255) / 256, B), 256, 0, st>>>(mask_u8, Hi, Wi, dst, Ho, Wo);
+    else box4s2_kernel<int><<<dim3((n + 255) / 256, B), 256, 0, st>>>(cur, Hi, Wi, dst, Ho, Wo);
     cur = dst;
     Hi = Ho;
     Wi = Wo;
   }
   const int n = Hi * Wi;
   const float scale = ldexpf(1.0f, -4 * conv_layers);
-  threshold_kernel<<<(n + 255) / 256, 256, 0, st>>>(cur, n, scale, threshold, feat_u8);
+  threshold_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(cur, n, scale, threshold, feat_u8);
   return check_launch("ipsr_feat_mask");
 }
 
 extern "C" int ipsr_build_flags(const uint8_t* feat_u8, int H, int W, int patch, int stride, int mask_thred,
                                 int32_t* flag_i32, int32_t* mask_idx_i32, int32_t* rank_i32, int32_t* count_i32,
                                 void* stream) {
+  return ipsr_build_flags_batch(feat_u8, 1, H, W, patch, stride, mask_thred, flag_i32, mask_idx_i32, rank_i32, count_i32, stream);
+}
+
+extern "C" int ipsr_build_flags_batch(const uint8_t* feat_u8, int B, int H, int W, int patch, int stride, int mask_thred,
+                                      int32_t* flag_i32, int32_t* mask_idx_i32, int32_t* rank_i32, int32_t* count_i32,
+                                      void* stream) {
   using namespace ipsr;
+  IPSR_REQUIRE(B > 0, IPSR_ERR_INVALID_ARG, "ipsr_build_flags: bad batch %d", B);
   IPSR_REQUIRE(feat_u8 && flag_i32 && mask_idx_i32 && rank_i32 && count_i32, IPSR_ERR_INVALID_ARG,
                "ipsr_build_flags: null pointer");
   IPSR_REQUIRE(H > 0 && W > 0 && patch > 0 && stride > 0 && patch <= H && patch <= W, IPSR_ERR_INVALID_ARG,
                "ipsr_build_flags: bad geometry H=%d W=%d k=%d s=%d", H, W, patch, stride);
   const int nH = (H - patch) / stride + 1, nW = (W - patch) / stride + 1;
   IPSR_REQUIRE((long long)nH * nW <= 65536, IPSR_ERR_UNSUPPORTED, "ipsr_build_flags: %d positions > 65536", nH * nW);
-  build_flags_kernel<<<1, 1024, 0, as_stream(stream)>>>(feat_u8, H, W, patch, stride, mask_thred, nH, nW,
+  build_flags_kernel<<<B, 1024, 0, as_stream(stream)>>>(feat_u8, H, W, patch, stride, mask_thred, nH, nW,
                                                          flag_i32, mask_idx_i32, rank_i32, count_i32);
   return check_launch("ipsr_build_flags");
 }

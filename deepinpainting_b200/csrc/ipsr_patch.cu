@@ -173,6 +173,225 @@ __global__ void __launch_bounds__(kWideThreads) blend_wide_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Blocked version of the recurrence (the scheme of ipsr_blend.cu's scan, for rows too long for its shared-memory
+// tiles): only ONE scalar per step is sequential.  By linearity z_i = <u_i, y_cur> for the steps i still ahead obeys
+// z_i <- wn_l z_i + wo_l <u_i, X[p_l]>, so inside a block of T = 32 steps the chain runs on scalars and the in-block
+// Gram matrix Gt[j][i] = <u_i, X[p_j]>, which wide_gram_kernel computes for all blocks in parallel.  Per block the scan
+// CTA then needs one real reduction (z_i = <u_i, y_prev> for the block's T rows: re-anchors z on the real y, so that
+// rounding differences to the reference's dot product cannot accumulate beyond T steps) and one channel-parallel update
+// of y.  The rows of u and X[p] are read in place from `rows` (position-major): nothing is staged.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWideT = 32;
+constexpr int kWideKS = 8;               // K ranges of the Gram kernel (partial matrices, summed in fixed order by the scan)
+constexpr int kWideCluster = 8;          // CTAs per image of the scan: each owns K / 8 of every row
+constexpr int kWideScanThreads = 256;
+
+// grid = (blocks of T steps, kWideKS, B), 256 threads: thread (ti, tj) owns the 2 x 2 outputs (ti, ti+16) x (tj, tj+16) of
+// the partial Gram matrix over its K range: gram[b][block][ks][j][i] = sum over that range of u_i[k] X[p_j][k]
+__global__ void __launch_bounds__(256) wide_gram_kernel(const float* __restrict__ rows, const float* __restrict__ inv_norm,
+                                                        const int32_t* __restrict__ ind, const int32_t* __restrict__ mask_idx,
+                                                        int K, int P, int M, float* __restrict__ gram) {
+  constexpr int T = kWideT, KC = 64;
+  __shared__ float Us[T][KC + 4], Ks[T][KC + 4];
+  __shared__ int qs[T], ps[T];
+  __shared__ float invs[T];
+  const int kb = blockIdx.x, ks = blockIdx.y, b = blockIdx.z, nblk = gridDim.x;
+  const int l0 = kb * T;
+  const float* R = rows + (size_t)b * P * K;
+  if (threadIdx.x < T) {
+    const int l = l0 + threadIdx.x;
+    const int q = l < M ? mask_idx[l] : -1;
+    qs[threadIdx.x] = q;
+    ps[threadIdx.x] = q >= 0 ? ind[(size_t)b * P + q] : -1;
+    invs[threadIdx.x] = q >= 0 ? inv_norm[(size_t)b * P + q] : 0.f;
+  }
+  __syncthreads();
+  const int kper = ((K + kWideKS - 1) / kWideKS + KC - 1) / KC * KC;      // whole chunks per range
+  const int kbeg = ks * kper, kend = min(K, kbeg + kper);
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += KC) {
+    for (int it = threadIdx.x; it < T * KC; it += 256) {        // coalesced 256-byte row segments
+      const int r = it / KC, c = it - r * KC;
+      const bool ok = qs[r] >= 0 && k0 + c < kend;
+      Us[r][c] = ok ? __fmul_rn(__ldg(R + (size_t)qs[r] * K + k0 + c), invs[r]) : 0.f;   // u = little * (1/(norm+1e-8))  :109
+      Ks[r][c] = ok ? __ldg(R + (size_t)ps[r] * K + k0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < KC; ++c) {
+      const float u0 = Us[ti][c], u1 = Us[ti + 16][c], x0 = Ks[tj][c], x1 = Ks[tj + 16][c];
+      g00 = fmaf(u0, x0, g00);
+      g01 = fmaf(u0, x1, g01);
+      g10 = fmaf(u1, x0, g10);
+      g11 = fmaf(u1, x1, g11);
+    }
+    __syncthreads();
+  }
+  float* G = gram + (((size_t)b * nblk + kb) * kWideKS + ks) * T * T;          // Gt[j][i] = <u_i, X[p_j]> over this range
+  G[tj * T + ti] = g00;
+  G[(tj + 16) * T + ti] = g01;
+  G[tj * T + ti + 16] = g10;
+  G[(tj + 16) * T + ti + 16] = g11;
+}
+
+__device__ __forceinline__ float wide_rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t wide_map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void wide_st_cluster(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// One CLUSTER of kWideCluster CTAs per image: a single SM cannot pull the 2 * M * K * 4 bytes of u / X[p] rows (21 MB at
+// configs[3]) fast enough -- the one-CTA version of this kernel was bound by exactly that, at 1.1 us per step -- so every
+// CTA owns 1/8 of the columns of every row.  Per block of T steps: (B) each CTA reduces its part of z_i = <u_i, y_prev>,
+// writes the T partial sums into the shared memory of ALL CTAs of the cluster (distributed shared memory) and, after ONE
+// cluster barrier, adds the eight partials in rank order; (C) every CTA runs the same T scalar steps on warp 0 (bit-identical
+// in all of them); (D) each CTA updates its columns of y.  y lives in registers (E values per thread).
+template <int E>
+__global__ void __launch_bounds__(kWideScanThreads)
+wide_scan_kernel(const float* __restrict__ rows, const float* __restrict__ inv_norm, const float* __restrict__ vmax,
+                 const int32_t* __restrict__ ind, const int32_t* __restrict__ mask_idx, const float* __restrict__ gram,
+                 int K, int P, int M, int kper, float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out) {
+  constexpr int T = kWideT, NW = kWideScanThreads / 32;
+  __shared__ float red[NW][T + 1];
+  __shared__ float zpart[2][kWideCluster][T];              // [parity][source CTA][row]: written by every CTA of the cluster
+  __shared__ float zs[T], wn_s[T], wo_s[T], vs[T], invs[T];
+  __shared__ int qs[T], ps[T];
+  const uint32_t crank = cluster_ctarank();
+  const int b = blockIdx.x / kWideCluster, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* R = rows + (size_t)b * P * K;
+  const int32_t* indb = ind + (size_t)b * P;
+  float* yb = y + (size_t)b * M * K;
+  const int nblk = (M + T - 1) / T;
+  const int kbeg = (int)crank * kper, kend = min(K, kbeg + kper);      // this CTA's columns
+  float yv[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) yv[e] = 0.f;
+  cluster_sync_all();                                      // every CTA of the cluster runs before anybody writes into it
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int l0 = kb * T;
+    const int nvalid = min(T, M - l0);
+    __syncthreads();                                       // the previous block's lists are no longer read
+    if (tid < T) {
+      const int l = l0 + tid;
+      const int q = l < M ? mask_idx[l] : -1;
+      qs[tid] = q;
+      ps[tid] = q >= 0 ? indb[q] : -1;
+      invs[tid] = q >= 0 ? inv_norm[(size_t)b * P + q] : 0.f;
+      vs[tid] = q >= 0 ? vmax[(size_t)b * P + q] : 1.f;
+    }
+    __syncthreads();
+    // ---- B: this CTA's part of z_i = <u_i, y_prev> for the block's rows, eight rows at a time ----
+    for (int i0 = 0; i0 < T; i0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        acc[r] = 0.f;
+        const int q = qs[i0 + r];
+        if (q >= 0) {
+          const float inv = invs[i0 + r];
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int kk = kbeg + tid + e * kWideScanThreads;
+            if (kk < kend) acc[r] = fmaf(__fmul_rn(__ldg(R + (size_t)q * K + kk), inv), yv[e], acc[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = warp_sum(acc[r]);
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) red[warp][i0 + r] = acc[r];
+      }
+    }
+    __syncthreads();
+    if (tid < T) {
+      float t = 0.f;
+      for (int w = 0; w < NW; ++w) t += red[w][tid];        // fixed order
+      const uint32_t mine = smem_u32(&zpart[kb & 1][crank][tid]);
+#pragma unroll
+      for (uint32_t dst = 0; dst < (uint32_t)kWideCluster; ++dst) wide_st_cluster(wide_map_to_cta(mine, dst), t);
+    }
+    cluster_sync_all();                                    // release / acquire: all partials of this block have landed
+    // ---- C: T scalar steps on warp 0 (the same arithmetic in every CTA of the cluster) ----
+    if (warp == 0) {
+      float z = 0.f;
+#pragma unroll
+      for (int c = 0; c < kWideCluster; ++c) z += zpart[kb & 1][c][lane];      // rank order
+      const float* Gt = gram + ((size_t)b * nblk + kb) * kWideKS * T * T;
+      const float v = vs[lane];
+      float my_wn = 0.f, my_wo = 1.f;
+      float g[T], vj[T];
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        float gs = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < kWideKS; ++s2) gs += __ldg(Gt + (size_t)s2 * T * T + j * T + lane);   // range order
+        g[j] = gs;
+        vj[j] = __shfl_sync(0xffffffffu, v, j);
+      }
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        const float zj = __shfl_sync(0xffffffffu, z, j);
+        const float r = wide_rcp_approx(__fadd_rn(zj, vj[j]));   // no clamp: inf / nan propagate      :120
+        float wn = __fmul_rn(zj, r);
+        float wo = __fmul_rn(vj[j], r);                          //                                     :121
+        if (kb == 0 && j == 0) {                                 // first masked patch: plain copy      :98-101
+          wn = 0.f;
+          wo = 1.f;
+        }
+        z = fmaf(wn, z, __fmul_rn(wo, g[j]));
+        if (lane == j) {
+          my_wn = wn;
+          my_wo = wo;
+        }
+      }
+      wn_s[lane] = my_wn;
+      wo_s[lane] = my_wo;
+      if (crank == 0 && l0 + lane < M) {
+        wn_out[(size_t)b * M + l0 + lane] = my_wn;
+        wo_out[(size_t)b * M + l0 + lane] = my_wo;
+      }
+    }
+    __syncthreads();
+    // ---- D: this CTA's columns of the block's y rows ----
+    for (int j0 = 0; j0 < nvalid; j0 += 8) {
+      float kv[8][E];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int p = j0 + r < nvalid ? ps[j0 + r] : -1;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int kk = kbeg + tid + e * kWideScanThreads;
+          kv[r][e] = (p >= 0 && kk < kend) ? __ldg(R + (size_t)p * K + kk) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (j0 + r < nvalid) {
+          const float wn = wn_s[j0 + r], wo = wo_s[j0 + r];
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int kk = kbeg + tid + e * kWideScanThreads;
+            yv[e] = __fadd_rn(__fmul_rn(wn, yv[e]), __fmul_rn(wo, kv[r][e]));          // :122
+            if (kk < kend) yb[(size_t)(l0 + j0 + r) * K + kk] = yv[e];
+          }
+        }
+      }
+    }
+  }
+  cluster_sync_all();                                      // nobody leaves while a peer may still write into it
+}
+
 // out[b][c][Y][X] = sum over the patches q covering (Y, X) of src(q)[(c, dy, dx)], src(q) = y[rank[q]] for masked
 // patch positions, rows[ind[q]] otherwise (IPSRFunction.py:129-131)
 __global__ void __launch_bounds__(256) fold_rows_kernel(const float* __restrict__ rows, const float* __restrict__ y,
@@ -279,6 +498,54 @@ extern "C" int ipsr_blend_wide(const float* rows, const float* inv_norm, const f
   else if (E <= 4) blend_wide_kernel<4><<<B, kWideThreads, 0, st>>>(rows, inv_norm, vmax, ind, mask_idx, K, P, M, y, wn, wo);
   else blend_wide_kernel<8><<<B, kWideThreads, 0, st>>>(rows, inv_norm, vmax, ind, mask_idx, K, P, M, y, wn, wo);
   return check_launch("ipsr_blend_wide");
+}
+
+extern "C" int ipsr_blend_wide_gram_floats(int B, int M) {
+  if (B <= 0 || M <= 0) return 0;
+  return B * ((M + ipsr::kWideT - 1) / ipsr::kWideT) * ipsr::kWideKS * ipsr::kWideT * ipsr::kWideT;
+}
+
+namespace ipsr {
+template <int E>
+static int launch_wide_scan(const float* rows, const float* inv_norm, const float* vmax, const int32_t* ind, const int32_t* mask_idx,
+                            const float* gram, int B, int K, int P, int M, int kper, float* y, float* wn, float* wo, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)B * kWideCluster);
+  cfg.blockDim = dim3(kWideScanThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kWideCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wide_scan_kernel<E>, rows, inv_norm, vmax, ind, mask_idx, gram, K, P, M, kper, y, wn, wo);
+  IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_blend_wide_blocked: launch failed: %s", cudaGetErrorString(e));
+  return check_launch("ipsr_blend_wide_blocked");
+}
+}  // namespace ipsr
+
+extern "C" int ipsr_blend_wide_blocked(const float* rows, const float* inv_norm, const float* vmax, const int32_t* ind,
+                                       const int32_t* mask_idx, int B, int K, int P, int M, float* gram,
+                                       float* y, float* wn, float* wo, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(rows && inv_norm && vmax && ind && mask_idx && gram && y && wn && wo, IPSR_ERR_INVALID_ARG,
+               "ipsr_blend_wide_blocked: null pointer");
+  IPSR_REQUIRE(B > 0 && B <= 8000 && K > 0 && P > 0 && M > 0 && M <= P, IPSR_ERR_INVALID_ARG, "ipsr_blend_wide_blocked: bad dims");
+  // columns per CTA of the cluster, E values per thread
+  const int kper = (K + kWideCluster - 1) / kWideCluster;
+  const int E = (kper + kWideScanThreads - 1) / kWideScanThreads;
+  IPSR_REQUIRE(E <= 8, IPSR_ERR_UNSUPPORTED, "ipsr_blend_wide_blocked: K=%d > %d", K, 8 * kWideScanThreads * kWideCluster);
+  cudaStream_t st = as_stream(stream);
+  const int nblk = (M + kWideT - 1) / kWideT;
+  wide_gram_kernel<<<dim3(nblk, kWideKS, B), 256, 0, st>>>(rows, inv_norm, ind, mask_idx, K, P, M, gram);
+  IPSR_FORWARD(check_launch("ipsr_blend_wide_blocked (gram)"));
+  if (E <= 1) return launch_wide_scan<1>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
+  if (E <= 2) return launch_wide_scan<2>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
+  if (E <= 4) return launch_wide_scan<4>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
+  return launch_wide_scan<8>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
 }
 
 extern "C" int ipsr_fold_patch_rows(const float* rows, const float* y, const int32_t* ind, const int32_t* rank,

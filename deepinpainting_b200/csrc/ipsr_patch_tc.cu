@@ -95,7 +95,7 @@ __device__ __forceinline__ float patch_dot(const float* __restrict__ r, const fl
   return warp_sum(acc);
 }
 
-// grid = (column chunks of 64, B), 256 threads = 8 warps; every warp takes 8 columns of the chunk per listed row.
+// grid = (column chunks of 64, B, row groups), 256 threads = 8 warps; every warp takes 8 columns of the chunk per listed row.
 __global__ void __launch_bounds__(256)
 patch_recheck_kernel(const float* __restrict__ rows_x, const float* __restrict__ rows_r, const float* __restrict__ inv_norm,
                      int K, int P, int Ppad, int col_begin, int col_end, const int* __restrict__ list,
@@ -105,7 +105,7 @@ patch_recheck_kernel(const float* __restrict__ rows_x, const float* __restrict__
   if (n == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int p0 = col_begin + blockIdx.x * 64;
-  for (int i = 0; i < n; ++i) {
+  for (int i = blockIdx.z; i < n; i += gridDim.z) {        // listed rows are dealt to blockIdx.z
     const int q = list[(size_t)b * Ppad + i];
     const float* rq = rows_r + ((size_t)b * P + q) * K;
     long long best = kPackedIdentity;
@@ -193,7 +193,7 @@ extern "C" int ipsr_patch_recheck(const float* rows_x, const float* rows_r, cons
   IPSR_REQUIRE(B > 0 && B <= 65535 && K > 0 && P > 0 && col_begin >= 0 && col_begin < col_end && col_end <= P, IPSR_ERR_INVALID_ARG,
                "ipsr_patch_recheck: bad dims / column range [%d,%d)", col_begin, col_end);
   const int Ppad = (P + kTileRows - 1) / kTileRows * kTileRows;
-  patch_recheck_kernel<<<dim3((col_end - col_begin + 63) / 64, B), 256, 0, as_stream(stream)>>>(
+  patch_recheck_kernel<<<dim3((col_end - col_begin + 63) / 64, B, 16), 256, 0, as_stream(stream)>>>(
       rows_x, rows_r, inv_norm, K, P, Ppad, col_begin, col_end, list, nlist, reinterpret_cast<long long*>(packed));
   return check_launch("ipsr_patch_recheck");
 }

@@ -41,12 +41,14 @@ class IPSR_model(nn.Module):
         operator call -- every kernel indexes its image's own flag / index rows (images are independent,
         models/IPSRFunction.py:46)."""
         if mask_global.dim() == 4 and mask_global.size(0) > 1:
-            per = [util.cal_feat_mask(mask_global[i:i + 1], layer_to_last, threshold).squeeze() for i in range(mask_global.size(0))]
-            self.masks = per
-            self.mask = per[0]
-            self._per_sample = [None] * len(per)
+            dev = mask_global.device if mask_global.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            util._require_binary(mask_global, "mask_global")
+            feats = shift_ops.feat_mask_batched(mask_global.to(dev)[:, 0], layer_to_last, threshold)      # one launch per layer
+            self.masks = list(feats.unbind(0))
+            self._feats = feats
+            self.mask = self.masks[0]
             self._flag_key = None
-            return torch.stack(per)
+            return feats
         self.masks = None
         mask = util.cal_feat_mask(mask_global, layer_to_last, threshold)
         self.mask = mask.squeeze()
@@ -94,22 +96,22 @@ class IPSR_model(nn.Module):
         _, self.c, self.h, self.w = input.size()
         if not (torch.is_tensor(self.sp_x) or torch.is_tensor(self.sp_y)):
             self.sp_x, self.sp_y = util.cal_sps_for_Advanced_Indexing(self.h, self.w)
-        key = tuple((id(m), m._version) for m in self.masks) + (self.h, self.w, self.shift_sz, self.stride, self.mask_thred,
-                                                                 input.device)
+        key = (id(self._feats), self._feats._version, self.h, self.w, self.shift_sz, self.stride, self.mask_thred, input.device)
         if key != self._flag_key:
-            per = []
-            for i, m in enumerate(self.masks):
-                m_dev = m.to(input.device) if m.device != input.device else m
-                per.append(util.cal_mask_given_mask_thred(input.narrow(0, i, 1).data.squeeze(0), m_dev, self.shift_sz, self.stride,
-                                                          self.mask_thred))
-            self._per_sample = per
+            feats = self._feats if self._feats.device == input.device else self._feats.to(input.device)
+            if tuple(feats.shape[1:]) != (self.h, self.w):
+                raise ValueError("mask %s does not match the feature map %dx%d" % (tuple(feats.shape[1:]), self.h, self.w))
+            # flag / index vectors of every sample in ONE launch and one host synchronisation
+            import math
+            mi = shift_ops.build_flags_batched(feats, self.shift_sz, self.stride, int(math.ceil(self.mask_thred)))
+            counts = mi.m_count.tolist()
             # the reference's vectors, one row per sample; mask_point_idx rows are ragged, so it stays a list
-            self.flag = torch.stack([v[0] for v in per])
-            self.nonmask_point_idx = per[0][1]
-            self.flatten_offsets = torch.stack([v[2] for v in per])
-            self.mask_point_idx = [v[3] for v in per]
-            shift_ops.register_mask_index(self.flag, shift_ops.stack_mask_indices(
-                shift_ops.lookup_mask_index(v[0], input.device) for v in per))
+            self.flag = mi.flag.long()
+            P = self.flag.size(1)
+            self.nonmask_point_idx = torch.arange(P, dtype=torch.int64, device=input.device)
+            self.mask_point_idx = [mi.mask_idx[b, :c].long() for b, c in enumerate(counts)]
+            self.flatten_offsets = None                       # unused by the operator (models/IPSRFunction.py:88-89); per-sample: not built
+            shift_ops.register_mask_index(self.flag, mi)
             self._flag_key = key
         return self._call_function(input, self.masks[0])
 

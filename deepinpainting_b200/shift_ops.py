@@ -24,6 +24,7 @@ config = {
     "tol_rel": -1.0,              # < 0: library default (5e-5 * ||R[q]||)
     "tol_abs": -1.0,
     "psplit": 0,                  # <= 0: auto
+    "wide_blend": "blocked",      # long patch rows: "blocked" (one sequential scalar per step) | "stepwise" (one reduction per step)
     "fuse_innercos": True,        # compute the InnerCos loss that follows the layer (networks.py:347) inside the paste kernel
     "exc_cap_factor": 8,          # exception POOL of the batch = factor * N * B + M * min(M, N) entries (8 bytes each): signed
                                   # inputs make a few images chaotic (tens of thousands of attention entries survive the int64
@@ -105,6 +106,20 @@ def feat_mask(mask_2d: torch.Tensor, conv_layers: int, threshold: float) -> torc
     return out
 
 
+def feat_mask_batched(masks: torch.Tensor, conv_layers: int, threshold: float) -> torch.Tensor:
+    """util/util.py:68-84 for a batch of masks [B, S_h, S_w] in one launch per layer -> uint8 [B, S_h>>L, S_w>>L]."""
+    m = _require_cuda(masks, "mask")
+    if m.dim() != 3:
+        raise ValueError("feat_mask_batched expects [B, S_h, S_w]")
+    m8 = (m != 0).to(torch.uint8).contiguous()
+    B, sh, sw = m8.shape
+    out = torch.empty((B, sh >> conv_layers, sw >> conv_layers), dtype=torch.uint8, device=m.device)
+    scratch = torch.empty((2 * B * max(1, (sh // 2) * (sw // 2)),), dtype=torch.int32, device=m.device)
+    _lib.call("ipsr_feat_mask_batch", m8.data_ptr(), B, sh, sw, int(conv_layers), float(threshold), out.data_ptr(),
+              scratch.data_ptr(), _stream_ptr(m.device))
+    return out
+
+
 @dataclass
 class MaskIndex:
     """Device-side flag / index vectors of one mask (util/util.py:88-147)."""
@@ -139,6 +154,26 @@ def build_flags(feat: torch.Tensor, patch: int, stride: int, mask_thred: int) ->
               midx.data_ptr(), rank.data_ptr(), count.data_ptr(), _stream_ptr(dev))
     M = int(count.item())            # one host sync per NEW mask, never per forward
     return MaskIndex(flag=flag, mask_idx=midx[:M].contiguous(), rank=rank, M=M, nH=nH, nW=nW)
+
+
+def build_flags_batched(feats: torch.Tensor, patch: int, stride: int, mask_thred: int) -> MaskIndex:
+    """One MaskIndex for a batch whose images have their OWN masks (feats uint8 [B, H, W]) in ONE launch and ONE host
+    synchronisation (the largest count sizes the per-step buffers) -- not one of each per sample."""
+    f = _require_cuda(feats, "masks", torch.uint8)
+    if f.dim() != 3:
+        raise ValueError("build_flags_batched expects [B, H, W]")
+    B, H, W = f.shape
+    nH, nW = (H - patch) // stride + 1, (W - patch) // stride + 1
+    P = nH * nW
+    dev = f.device
+    flag = torch.empty((B, P), dtype=torch.int32, device=dev)
+    midx = torch.zeros((B, P), dtype=torch.int32, device=dev)
+    rank = torch.empty((B, P), dtype=torch.int32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    _lib.call("ipsr_build_flags_batch", f.data_ptr(), B, H, W, int(patch), int(stride), int(mask_thred), flag.data_ptr(),
+              midx.data_ptr(), rank.data_ptr(), count.data_ptr(), _stream_ptr(dev))
+    M = int(count.max().item())
+    return MaskIndex(flag=flag, mask_idx=midx, rank=rank, M=M, nH=nH, nW=nW, m_count=count)
 
 
 def stack_mask_indices(items) -> MaskIndex:
@@ -426,7 +461,13 @@ def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Opti
     tensor = mode == "tensor" or (mode == "auto" and _lib.load().ipsr_tensor_path_supported(C, N) == 1)
     n = 1                                   # extract_normalize
     cascade = tensor and _lib.load().ipsr_tensor_cascade(B, C, N) == 1
-    n += (4 if cascade else 2) if tensor else 1   # correlate_tc + finalize [x2 with the cascade] | select_all_rows
+    if tensor and not cascade:
+        # small problems: without a column split the epilogue of the (single) pass makes the finalize decision itself
+        tiles = B * (N // 128)
+        ps = config["psplit"] if config["psplit"] > 0 else max(1, min(8, 148 // max(1, tiles), N // 128))
+        n += 1 if ps == 1 else 2
+    else:
+        n += 4 if tensor else 1               # (correlate_tc + finalize) x 2 with the cascade | select_all_rows
     n += 2                                  # correlate_fp32 + resolve_rows
     if M > 0:
         n += 2                              # blend_stage (+ routes builders in the same launch) + blend_scan
@@ -539,8 +580,13 @@ def shift_forward_patches(x: torch.Tensor, ref: torch.Tensor, mi: MaskIndex, pat
         y = torch.empty((B, M, K), dtype=torch.float32, device=dev)
         wn = torch.empty((B, M), dtype=torch.float32, device=dev)
         wo = torch.empty((B, M), dtype=torch.float32, device=dev)
-        _lib.call("ipsr_blend_wide", rows.data_ptr(), inv.data_ptr(), vmax.data_ptr(), ind.data_ptr(), mi.mask_idx.data_ptr(),
-                  B, K, P, M, y.data_ptr(), wn.data_ptr(), wo.data_ptr(), st)
+        if config["wide_blend"] == "blocked":
+            gram = torch.empty((_lib.load().ipsr_blend_wide_gram_floats(B, M),), dtype=torch.float32, device=dev)
+            _lib.call("ipsr_blend_wide_blocked", rows.data_ptr(), inv.data_ptr(), vmax.data_ptr(), ind.data_ptr(),
+                      mi.mask_idx.data_ptr(), B, K, P, M, gram.data_ptr(), y.data_ptr(), wn.data_ptr(), wo.data_ptr(), st)
+        else:
+            _lib.call("ipsr_blend_wide", rows.data_ptr(), inv.data_ptr(), vmax.data_ptr(), ind.data_ptr(), mi.mask_idx.data_ptr(),
+                      B, K, P, M, y.data_ptr(), wn.data_ptr(), wo.data_ptr(), st)
     _lib.call("ipsr_fold_patch_rows", rows.data_ptr(), _ptr(y), ind.data_ptr(), mi.rank.data_ptr(), B, Cc, H, W, k, s, M,
               out.data_ptr(), st)
     return out, ind

@@ -46,6 +46,9 @@ int ipsr_tensor_path_supported(int C, int N);
  * ambiguous rows) for this problem size, 0 when it runs the three-pass split over every row (small problems, where
  * the cascade's extra launches cost more than the tensor time they save). */
 int ipsr_tensor_cascade(int B, int C, int N);
+/* Tensor passes that ipsr_shift_forward issues over EVERY row for a whole-bank call of this size: 1 (one hi*hi pass: the
+ * cascade) or 3 (the three-pass split over every row: small problems); 0: no tensor path. */
+int ipsr_tensor_full_passes(int B, int C, int N);
 
 /* ---------------------------------------------------------------------------------------------
  * Mask helpers
@@ -58,12 +61,23 @@ int ipsr_tensor_cascade(int B, int C, int N);
 int ipsr_feat_mask(const uint8_t* mask_u8, int S_h, int S_w, int conv_layers, float threshold,
                    uint8_t* feat_u8, int32_t* scratch_i32, void* stream);
 
+/* The same for a batch of B masks [B][S_h][S_w] -> [B][S_h>>L][S_w>>L] (one free-form mask per sample, BASELINE.json
+ * configs[4]); scratch_i32 must hold 2 * B * (S_h/2)*(S_w/2) ints. */
+int ipsr_feat_mask_batch(const uint8_t* mask_u8, int B, int S_h, int S_w, int conv_layers, float threshold,
+                         uint8_t* feat_u8, int32_t* scratch_i32, void* stream);
+
 /* util/util.py:88-147 cal_mask_given_mask_thred: flag[P] = (sum of mask over the k x k window
  * >= mask_thred); mask_idx = ascending positions with flag==1; rank[q] = position of q inside
  * mask_idx or -1; *count = M.  P = nH*nW patch positions.  One CTA; P <= 65536. */
 int ipsr_build_flags(const uint8_t* feat_u8, int H, int W, int patch, int stride, int mask_thred,
                      int32_t* flag_i32, int32_t* mask_idx_i32, int32_t* rank_i32, int32_t* count_i32,
                      void* stream);
+
+/* The same for B feature masks [B][H][W]: flag / mask_idx / rank rows of P entries per image (mask_idx row b holds
+ * count[b] valid entries) -- exactly the per-image layout of ipsr_fwd_args.mask_stride = P. */
+int ipsr_build_flags_batch(const uint8_t* feat_u8, int B, int H, int W, int patch, int stride, int mask_thred,
+                           int32_t* flag_i32, int32_t* mask_idx_i32, int32_t* rank_i32, int32_t* count_i32,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a) patch extraction + L2 normalisation   (util/NonparametricShift.py:36-40,59-73)
@@ -356,6 +370,16 @@ int ipsr_patch_winner_scores(const float* rows_x, const float* rows_r, const flo
 int ipsr_blend_wide(const float* rows, const float* inv_norm, const float* vmax, const int32_t* ind,
                     const int32_t* mask_idx, int B, int K, int P, int M,
                     float* y, float* wn, float* wo, void* stream);
+/* The same recurrence in blocks of 32 steps: by linearity only one scalar per step is sequential (the scheme of
+ * ipsr_blend_scan for rows too long for its shared-memory tiles); the in-block Gram matrices <u_i, X[p_j]> are computed
+ * for all blocks in parallel first (partial matrices per K range, added in fixed order).  The recurrence runs on a
+ * CLUSTER of 8 CTAs per image, each owning 1/8 of the columns of every row (a single SM cannot stream the rows fast
+ * enough); the per-block partial dot products meet in distributed shared memory.
+ * gram: ipsr_blend_wide_gram_floats(B, M) floats of scratch. */
+int ipsr_blend_wide_gram_floats(int B, int M);
+int ipsr_blend_wide_blocked(const float* rows, const float* inv_norm, const float* vmax, const int32_t* ind,
+                            const int32_t* mask_idx, int B, int K, int P, int M, float* gram,
+                            float* y, float* wn, float* wo, void* stream);
 /* Gather + fold in one pass: the patch pasted at position q is y[b][rank[q]] when rank[q] >= 0, else
  * rows[b][ind[b][q]]. */
 int ipsr_fold_patch_rows(const float* rows, const float* y, const int32_t* ind, const int32_t* rank,

@@ -1,3 +1,6 @@
-python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2_tm.log 2>&1; echo "pytest rc=$?"; tail -n 15 gpurun_out/r2_tm.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 200 --warmup 5 > gpurun_out/r2_bench_g2.json 2> gpurun_out/r2_bench_g2.err; echo "bench rc=$?"; tail -n 4 gpurun_out/r2_bench_g2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload patch3x3 --shard bank --steps 30 > gpurun_out/r2_patch_g2.json 2> gpurun_out/r2_patch_g2.err; echo "patch rc=$?"; tail -n 4 gpurun_out/r2_patch_g2.err
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_t12.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/r2_t12.log
+python scripts/patch_config4.py --iters 5 > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_cfg4.csv python scripts/patch_config4.py --iters 1 > gpurun_out/ncu_cfg4.log 2>&1
+tail -n 2 gpurun_out/plain.log
+python bench.py --steps 500 --no-also > gpurun_out/r2_bench3.json 2> gpurun_out/r2_bench3.err; echo "bench rc=$?"; tail -n 3 gpurun_out/r2_bench3.err
+python bench.py --workload generator --steps 10 > gpurun_out/r2_gen2.json 2> gpurun_out/r2_gen2.err; echo "gen rc=$?"; tail -n 5 gpurun_out/r2_gen2.err
