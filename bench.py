@@ -694,7 +694,7 @@ def measure_generator(args, world, rank, local, dev, dist, pk):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    W_, K = max(3, min(args.warmup, 5)), min(args.steps, 30)
+    W_, K = 6, max(10, min(args.steps, 30))               # the first steps pay cuDNN's algorithm selection and the allocator's growth
     for i in range(W_):
         one(i)
     sync_all()

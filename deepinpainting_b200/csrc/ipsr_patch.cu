@@ -10,6 +10,8 @@
 //     fit; patch_rows_kernel writes position-major rows + norms, the exact fp32 correlation runs on the patch maps,
 //     blend_wide_kernel runs the recurrence with y in registers (one CTA per image) and fold_rows_kernel gathers
 //     and sums.
+#include <stdlib.h>
+
 #include "ipsr_common.cuh"
 
 namespace ipsr {
@@ -392,6 +394,208 @@ wide_scan_kernel(const float* __restrict__ rows, const float* __restrict__ inv_n
   cluster_sync_all();                                      // nobody leaves while a peer may still write into it
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same cluster scan with everything a block needs ALREADY IN SHARED MEMORY when the block starts: the version above
+// pays eight dependent round trips to L2 per block (index lists, u rows, Gram entries, X[p] rows: ~15 us per block of 32
+// steps, latency not bandwidth).  Here the warps that idle during the scalar steps of block k fetch block k+1 with
+// cp.async (this CTA's column slice of the 2 T rows, the index lists of block k+2, the Gram matrix of block k+1, summed
+// over its K ranges), so that a block costs its own arithmetic, one cluster barrier and T scalar steps.
+// Needs 4 * T * kper floats of shared memory (K <= ~3000 with 8 CTAs); longer rows take the kernel above.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int E>
+__global__ void __launch_bounds__(kWideScanThreads)
+wide_scan_smem_kernel(const float* __restrict__ rows, const float* __restrict__ inv_norm, const float* __restrict__ vmax,
+                      const int32_t* __restrict__ ind, const int32_t* __restrict__ mask_idx, const float* __restrict__ gram,
+                      int K, int P, int M, int kper, float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out) {
+  constexpr int T = kWideT, NW = kWideScanThreads / 32;
+  extern __shared__ __align__(16) float wsm[];              // U[2][T][kper] | X[2][T][kper] | G[2][T][T]
+  float* Ubuf = wsm;
+  float* Xbuf = Ubuf + 2 * (size_t)T * kper;
+  float* Gbuf = Xbuf + 2 * (size_t)T * kper;
+  __shared__ float red[NW][T + 1];
+  __shared__ float zpart[2][kWideCluster][T];
+  __shared__ float wn_s[T], wo_s[T];
+  __shared__ float vs[3][T], invs[3][T];                    // index lists of three consecutive blocks
+  __shared__ int qs[3][T], ps[3][T];
+  const uint32_t crank = cluster_ctarank();
+  const int b = blockIdx.x / kWideCluster, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* R = rows + (size_t)b * P * K;
+  const int32_t* indb = ind + (size_t)b * P;
+  float* yb = y + (size_t)b * M * K;
+  const int nblk = (M + T - 1) / T;
+  const int kbeg = (int)crank * kper, kend = min(K, kbeg + kper);
+  const int klen = max(0, kend - kbeg);
+  const bool vec16 = ((K & 3) == 0) && ((kper & 3) == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0);
+
+  auto fetch_lists = [&](int kb) {                          // by one warp: T lanes, three dependent loads
+    const int s = kb % 3, l = kb * T + lane;
+    const int q = (kb < nblk && l < M) ? mask_idx[l] : -1;
+    qs[s][lane] = q;
+    ps[s][lane] = q >= 0 ? indb[q] : -1;
+    invs[s][lane] = q >= 0 ? inv_norm[(size_t)b * P + q] : 0.f;
+    vs[s][lane] = q >= 0 ? vmax[(size_t)b * P + q] : 1.f;
+  };
+  auto fetch_rows = [&](int kb, int t0, int nt) {           // threads t0 .. t0+nt-1: this CTA's slice of the block's 2 T rows
+    if (kb >= nblk) return;
+    const int s = kb % 3, buf = kb & 1;
+    float* U = Ubuf + (size_t)buf * T * kper;
+    float* X = Xbuf + (size_t)buf * T * kper;
+    const int t = tid - t0;
+    if (vec16) {
+      const int per_row = klen >> 2;                        // 16-byte pieces per row slice
+      for (int it = t; it < 2 * T * per_row; it += nt) {
+        const int r = it / per_row, c = (it - r * per_row) << 2;
+        const int rr = r < T ? r : r - T;
+        const int src = r < T ? qs[s][rr] : ps[s][rr];
+        float* dst = (r < T ? U : X) + (size_t)rr * kper + c;
+        if (src >= 0) cp_async16(dst, R + (size_t)src * K + kbeg + c);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int it = t; it < 2 * T * klen; it += nt) {
+        const int r = it / klen, c = it - r * klen;
+        const int rr = r < T ? r : r - T;
+        const int src = r < T ? qs[s][rr] : ps[s][rr];
+        float* dst = (r < T ? U : X) + (size_t)rr * kper + c;
+        if (src >= 0) cp_async4(dst, R + (size_t)src * K + kbeg + c);
+        else *dst = 0.f;
+      }
+    }
+  };
+  auto fetch_gram = [&](int kb, int t0, int nt) {           // Gram of block kb, its K ranges added in range order
+    if (kb >= nblk) return;
+    const float* Gt = gram + ((size_t)b * nblk + kb) * kWideKS * T * T;
+    float* G = Gbuf + (size_t)(kb & 1) * T * T;
+    for (int e = tid - t0; e < T * T; e += nt) {
+      float gs = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < kWideKS; ++s2) gs += __ldg(Gt + (size_t)s2 * T * T + e);
+      G[e] = gs;
+    }
+  };
+
+  float yv[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) yv[e] = 0.f;
+  // prologue: lists of blocks 0 and 1, rows and Gram of block 0
+  if (warp == 0) fetch_lists(0);
+  if (warp == 1) fetch_lists(1);
+  __syncthreads();
+  fetch_rows(0, 0, kWideScanThreads);
+  fetch_gram(0, 0, kWideScanThreads);
+  cp_async_wait_all();
+  cluster_sync_all();                                      // (also a CTA barrier) every CTA of the cluster runs before anybody writes into it
+
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int l0 = kb * T, s = kb % 3, buf = kb & 1;
+    const int nvalid = min(T, M - l0);
+    const float* U = Ubuf + (size_t)buf * T * kper;
+    const float* X = Xbuf + (size_t)buf * T * kper;
+    // ---- B: this CTA's part of z_i = <u_i, y_prev> for the block's T rows; 31-shuffle transpose-reduce per warp ----
+    {
+      float acc[T];
+#pragma unroll
+      for (int i = 0; i < T; ++i) {
+        const float inv = invs[s][i];
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int c = tid + e * kWideScanThreads;
+          if (c < klen) a = fmaf(__fmul_rn(U[(size_t)i * kper + c], inv), yv[e], a);     // u = little * (1/(norm+1e-8))  :109
+        }
+        acc[i] = a;
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+          const float send = up ? acc[j] : acc[j + o];
+          const float keep = up ? acc[j + o] : acc[j];
+          acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      red[warp][lane] = acc[0];                            // lane L holds the warp's sum of row L
+    }
+    __syncthreads();
+    if (tid < T) {
+      float t = 0.f;
+      for (int w = 0; w < NW; ++w) t += red[w][tid];        // fixed order
+      const uint32_t mine = smem_u32(&zpart[buf][crank][tid]);
+#pragma unroll
+      for (uint32_t dst = 0; dst < (uint32_t)kWideCluster; ++dst) wide_st_cluster(wide_map_to_cta(mine, dst), t);
+    }
+    cluster_sync_all();                                    // all partials of this block have landed everywhere
+    if (warp == 0) {
+      // ---- C: T scalar steps (the same arithmetic in every CTA of the cluster) ----
+      float z = 0.f;
+#pragma unroll
+      for (int c = 0; c < kWideCluster; ++c) z += zpart[buf][c][lane];         // rank order
+      const float* G = Gbuf + (size_t)buf * T * T;
+      const float v = vs[s][lane];
+      float my_wn = 0.f, my_wo = 1.f;
+      float g[T], vj[T];
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        g[j] = G[j * T + lane];
+        vj[j] = __shfl_sync(0xffffffffu, v, j);
+      }
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        const float zj = __shfl_sync(0xffffffffu, z, j);
+        const float r = wide_rcp_approx(__fadd_rn(zj, vj[j]));   // no clamp: inf / nan propagate      :120
+        float wn = __fmul_rn(zj, r);
+        float wo = __fmul_rn(vj[j], r);                          //                                     :121
+        if (kb == 0 && j == 0) {                                 // first masked patch: plain copy      :98-101
+          wn = 0.f;
+          wo = 1.f;
+        }
+        z = fmaf(wn, z, __fmul_rn(wo, g[j]));
+        if (lane == j) {
+          my_wn = wn;
+          my_wo = wo;
+        }
+      }
+      wn_s[lane] = my_wn;
+      wo_s[lane] = my_wo;
+      if (crank == 0 && l0 + lane < M) {
+        wn_out[(size_t)b * M + l0 + lane] = my_wn;
+        wo_out[(size_t)b * M + l0 + lane] = my_wo;
+      }
+    } else {
+      // ---- meanwhile: everything block kb+1 needs (its lists arrived one block ago), and the lists of block kb+2 ----
+      if (warp == 1) fetch_lists(kb + 2);
+      fetch_rows(kb + 1, 32, kWideScanThreads - 32);
+      fetch_gram(kb + 1, 32, kWideScanThreads - 32);
+      cp_async_wait_all();
+    }
+    __syncthreads();
+    // ---- D: this CTA's columns of the block's y rows ----
+#pragma unroll 4
+    for (int j = 0; j < nvalid; ++j) {
+      const float wn = wn_s[j], wo = wo_s[j];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int c = tid + e * kWideScanThreads;
+        if (c < klen) {
+          yv[e] = __fadd_rn(__fmul_rn(wn, yv[e]), __fmul_rn(wo, X[(size_t)j * kper + c]));          // :122
+          yb[(size_t)(l0 + j) * K + kbeg + c] = yv[e];
+        }
+      }
+    }
+    __syncthreads();                                       // this block's buffers may be refilled (two blocks from now)
+  }
+  cluster_sync_all();                                      // nobody leaves while a peer may still write into it
+}
+
 // out[b][c][Y][X] = sum over the patches q covering (Y, X) of src(q)[(c, dy, dx)], src(q) = y[rank[q]] for masked
 // patch positions, rows[ind[q]] otherwise (IPSRFunction.py:129-131)
 __global__ void __launch_bounds__(256) fold_rows_kernel(const float* __restrict__ rows, const float* __restrict__ y,
@@ -508,11 +712,12 @@ extern "C" int ipsr_blend_wide_gram_floats(int B, int M) {
 namespace ipsr {
 template <int E>
 static int launch_wide_scan(const float* rows, const float* inv_norm, const float* vmax, const int32_t* ind, const int32_t* mask_idx,
-                            const float* gram, int B, int K, int P, int M, int kper, float* y, float* wn, float* wo, cudaStream_t st) {
+                            const float* gram, int B, int K, int P, int M, int kper, size_t smem, float* y, float* wn, float* wo,
+                            cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)B * kWideCluster);
   cfg.blockDim = dim3(kWideScanThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -521,7 +726,14 @@ static int launch_wide_scan(const float* rows, const float* inv_norm, const floa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, wide_scan_kernel<E>, rows, inv_norm, vmax, ind, mask_idx, gram, K, P, M, kper, y, wn, wo);
+  cudaError_t e;
+  if (smem > 0) {
+    e = cudaFuncSetAttribute(wide_scan_smem_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_blend_wide_blocked smem attribute: %s", cudaGetErrorString(e));
+    e = cudaLaunchKernelEx(&cfg, wide_scan_smem_kernel<E>, rows, inv_norm, vmax, ind, mask_idx, gram, K, P, M, kper, y, wn, wo);
+  } else {
+    e = cudaLaunchKernelEx(&cfg, wide_scan_kernel<E>, rows, inv_norm, vmax, ind, mask_idx, gram, K, P, M, kper, y, wn, wo);
+  }
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_blend_wide_blocked: launch failed: %s", cudaGetErrorString(e));
   return check_launch("ipsr_blend_wide_blocked");
 }
@@ -534,18 +746,25 @@ extern "C" int ipsr_blend_wide_blocked(const float* rows, const float* inv_norm,
   IPSR_REQUIRE(rows && inv_norm && vmax && ind && mask_idx && gram && y && wn && wo, IPSR_ERR_INVALID_ARG,
                "ipsr_blend_wide_blocked: null pointer");
   IPSR_REQUIRE(B > 0 && B <= 8000 && K > 0 && P > 0 && M > 0 && M <= P, IPSR_ERR_INVALID_ARG, "ipsr_blend_wide_blocked: bad dims");
-  // columns per CTA of the cluster, E values per thread
-  const int kper = (K + kWideCluster - 1) / kWideCluster;
+  // columns per CTA of the cluster (a multiple of 4: 16-byte cp.async pieces), E values per thread
+  const int kper = ((K + kWideCluster - 1) / kWideCluster + 3) & ~3;
   const int E = (kper + kWideScanThreads - 1) / kWideScanThreads;
+  // the prefetching kernel when its buffers (two blocks of 2 T row slices + two Gram matrices) fit
+  size_t smem = (4 * (size_t)kWideT * kper + 2 * (size_t)kWideT * kWideT) * sizeof(float);
+  static const bool no_prefetch = [] {
+    const char* e = getenv("IPSR_WIDE_NO_PREFETCH");
+    return e && atoi(e) != 0;
+  }();
+  if (smem > 200 * 1024 || no_prefetch) smem = 0;
   IPSR_REQUIRE(E <= 8, IPSR_ERR_UNSUPPORTED, "ipsr_blend_wide_blocked: K=%d > %d", K, 8 * kWideScanThreads * kWideCluster);
   cudaStream_t st = as_stream(stream);
   const int nblk = (M + kWideT - 1) / kWideT;
   wide_gram_kernel<<<dim3(nblk, kWideKS, B), 256, 0, st>>>(rows, inv_norm, ind, mask_idx, K, P, M, gram);
   IPSR_FORWARD(check_launch("ipsr_blend_wide_blocked (gram)"));
-  if (E <= 1) return launch_wide_scan<1>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
-  if (E <= 2) return launch_wide_scan<2>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
-  if (E <= 4) return launch_wide_scan<4>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
-  return launch_wide_scan<8>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, y, wn, wo, st);
+  if (E <= 1) return launch_wide_scan<1>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, smem, y, wn, wo, st);
+  if (E <= 2) return launch_wide_scan<2>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, smem, y, wn, wo, st);
+  if (E <= 4) return launch_wide_scan<4>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, smem, y, wn, wo, st);
+  return launch_wide_scan<8>(rows, inv_norm, vmax, ind, mask_idx, gram, B, K, P, M, kper, smem, y, wn, wo, st);
 }
 
 extern "C" int ipsr_fold_patch_rows(const float* rows, const float* y, const int32_t* ind, const int32_t* rank,

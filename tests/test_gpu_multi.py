@@ -33,7 +33,7 @@ def _worker(rank, world, port):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         gen = torch.Generator().manual_seed(11)                    # same data on every rank
-        B, C, H = 4, 256, 32
+        B, C, H = max(4, world), 256, 32                        # at least one image per rank
         N = H * H
         x = torch.randn(B, C, H, H, generator=gen).to(dev)
         ref = (torch.relu(torch.randn(B, C, H, H, generator=gen)) * 3).to(dev)
