@@ -251,6 +251,77 @@ def test_wide_patch_tensor_route_matches_exact_route_and_shards():
     assert bool((keys[0] == -(1 << 63)).all())
 
 
+def test_wide_kernels_stay_inside_their_buffers():
+    """compute-sanitizer is not available on the GPU pool: every output buffer of the long-row kernels sits between two
+    guard bands here, which must come back untouched (K = 1155: not a multiple of 4 -> the 4-byte cp.async path and the
+    scalar tile loads; P = 100: padded to 128 rows; M = 21: a partial block of the scan)."""
+    from deepinpainting_b200 import _lib
+    L = _lib.load()
+    dev = DEV
+    gen = torch.Generator().manual_seed(2)
+    B, K, P, M = 2, 1155, 100, 21
+    GUARD = 4096
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * GUARD,), fill, dtype=dtype, device=dev)
+        return buf, buf[GUARD:GUARD + n]
+
+    def intact(buf, n, fill):
+        lo, hi = buf[:GUARD], buf[GUARD + n:]
+        if buf.dtype.is_floating_point:
+            return bool((lo == fill).all() and (hi == fill).all())
+        return bool((lo == fill).all() and (hi == fill).all())
+
+    rows = torch.randn(B, P, K, generator=gen).abs().to(dev)
+    inv = (1.0 / (rows.norm(dim=2) + 1e-8)).contiguous()
+    rmax = rows.abs().amax(dim=2).contiguous()
+    rnorm = rows.norm(dim=2).contiguous()
+    Kpad, Ppad = -(-K // 64) * 64, -(-P // 128) * 128
+    nt = B * (Kpad // 64) * 2 * (Ppad // 128) * 16384
+    tb, tiles = guarded(nt, torch.uint8, 0x5A)
+    rb, rscale = guarded(B * Ppad, torch.float32, -7.0)
+    nb, rnorm_pad = guarded(B * Ppad, torch.float32, -7.0)
+    _lib.call("ipsr_patch_tiles", rows.data_ptr(), None, rmax.data_ptr(), rnorm.data_ptr(), 1, B, K, P, tiles.data_ptr(),
+              rscale.data_ptr(), rnorm_pad.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert intact(tb, nt, 0x5A) and intact(rb, B * Ppad, -7.0) and intact(nb, B * Ppad, -7.0)
+    assert bool((rscale.view(B, Ppad)[:, P:] == 1.0).all()) and bool((rnorm_pad.view(B, Ppad)[:, P:] == 0.0).all())
+    # the blocked blend: y, wn, wo, gram between guards
+    ind = torch.randint(0, P, (B, P), generator=gen, dtype=torch.int32).to(dev)
+    vmax = (torch.rand(B, P, generator=gen) + 0.5).to(dev)
+    midx = torch.arange(10, 10 + M, dtype=torch.int32, device=dev)
+    ng = L.ipsr_blend_wide_gram_floats(B, M)
+    gb, gram = guarded(ng, torch.float32, -3.0)
+    yb, y = guarded(B * M * K, torch.float32, -3.0)
+    wb, wn = guarded(B * M, torch.float32, -3.0)
+    ob, wo = guarded(B * M, torch.float32, -3.0)
+    _lib.call("ipsr_blend_wide_blocked", rows.data_ptr(), inv.data_ptr(), vmax.data_ptr(), ind.data_ptr(), midx.data_ptr(), B, K, P, M,
+              gram.data_ptr(), y.data_ptr(), wn.data_ptr(), wo.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert intact(gb, ng, -3.0) and intact(yb, B * M * K, -3.0) and intact(wb, B * M, -3.0) and intact(ob, B * M, -3.0)
+    assert bool(torch.isfinite(y).all()) and bool((y != -3.0).any())
+    # ... and it agrees with the one-reduction-per-step kernel
+    y2, wn2, wo2 = torch.empty_like(y), torch.empty_like(wn), torch.empty_like(wo)
+    _lib.call("ipsr_blend_wide", rows.data_ptr(), inv.data_ptr(), vmax.data_ptr(), ind.data_ptr(), midx.data_ptr(), B, K, P, M,
+              y2.data_ptr(), wn2.data_ptr(), wo2.data_ptr(), st)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(wn, wn2, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(y, y2, rtol=2e-4, atol=1e-5)
+    # winner scores: ind / vmax / keys between guards
+    ind_pad = torch.zeros(B, Ppad, dtype=torch.int32, device=dev)
+    ind_pad[:, :P] = ind
+    ib, ind_o = guarded(B * P, torch.int32, -5)
+    vb, vm_o = guarded(B * P, torch.float32, -5.0)
+    kb_, keys = guarded(B * P, torch.int64, -5)
+    _lib.call("ipsr_patch_winner_scores", rows.data_ptr(), rows.data_ptr(), inv.data_ptr(), ind_pad.data_ptr(), None, B, K, P,
+              ind_o.data_ptr(), vm_o.data_ptr(), keys.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert intact(ib, B * P, -5) and intact(vb, B * P, -5.0) and intact(kb_, B * P, -5)
+    want = torch.einsum("bpk,bpk->bp", rows, rows[torch.arange(B)[:, None], ind.long()] * inv[torch.arange(B)[:, None], ind.long()][..., None])
+    torch.testing.assert_close(vm_o.view(B, P), want, rtol=2e-5, atol=1e-5)
+
+
 def test_nonparametricshift_patches_k3():
     from deepinpainting_b200.util.NonparametricShift import NonparametricShift
     rng = np.random.default_rng(3)
