@@ -1,1 +1,2 @@
-python -m pytest tests/test_gpu_patches.py -x -q > gpurun_out/r2_t14.log 2>&1; echo "pytest rc=$?"; tail -n 25 gpurun_out/r2_t14.log
+timeout 700 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t18.log 2>&1; echo "pytest rc=$?"; tail -n 4 gpurun_out/r2_t18.log
+python bench.py --steps 500 > gpurun_out/r2_bench4.json 2> gpurun_out/r2_bench4.err; echo "bench rc=$?"
