@@ -8,6 +8,8 @@
 // over "unit routes" plus a short exception list; no N x N object exists anywhere.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ipsr_bookkeeping.cuh"
 
 namespace ipsr {
@@ -72,7 +74,7 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
                  const int* __restrict__ exc_l, const float* __restrict__ exc_w, const int* __restrict__ exc_total,
                  int exc_cap, const int* __restrict__ ind, const int* __restrict__ mask_idx,
                  const float* __restrict__ wn, const float* __restrict__ wo, float triple_w, float* __restrict__ gin,
-                 int ninfo, int nexc_s, int ms, const int* __restrict__ mcount, int S, int light) {
+                 int ninfo, int nexc_s, int ms, const int* __restrict__ mcount, int S, int light, int qcap) {
   extern __shared__ __align__(128) float bwd_smem[];      // rows[S][CT*N] | spec[N] | info[N] int4 | rq[N] | el[E] | ew[E]
   __shared__ int heavy[kBwdQueue];
   __shared__ int4 heavy_info[kBwdQueue];
@@ -113,6 +115,12 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
     }
     mbar_fence_init();
   }
+  // A column whose pieces do not fit the queue any more goes to the light list, but it has already advanced the queue
+  // cursor: the slots it leaves behind must read as "later piece, nothing to sum".
+  for (int i = threadIdx.x; i < kBwdQueue; i += blockDim.x) {
+    heavy[i] = -1;
+    heavy_info[i] = make_int4(0, 0, 0, 0);
+  }
   __syncthreads();
   auto issue_load = [&](int t) {                          // DMA thread
     const int s2 = (t - t0) % S;
@@ -152,7 +160,7 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
         // for the first piece (with the piece count in the high bits) and -1 for the others
         const int np = (work + kBwdPiece - 1) / kBwdPiece;
         const int slot = atomicAdd(&nheavy, np);
-        if (slot + np <= kBwdQueue) {
+        if (slot + np <= qcap) {
           for (int j = 0; j < np; ++j) {
             const int lo = j * kBwdPiece, hi = min(work, lo + kBwdPiece);
             const int ra = min(lo, n), rb = min(hi, n);                    // routes [ra, rb)
@@ -180,7 +188,7 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
   const int* elx = exc_in_smem ? el_s : el;
   const float* ewx = exc_in_smem ? ew_s : ew;
   const int nspec = nspec_s;
-  const int nh = min(nheavy, kBwdQueue);                     // (a column whose pieces did not fit the queue went to the light list)
+  const int nh = min(nheavy, qcap);                     // (a column whose pieces did not fit the queue went to the light list)
   // in place (DMA warp stores the finished tile) when every listed column has its own compute thread, so that the sums of
   // phase A can wait in registers for phase B
   const bool inplace = vec && !overflow && nspec <= ncompute && nspec <= ninfo && nh <= kBwdHubInplace;
@@ -486,7 +494,7 @@ extern "C" int ipsr_shift_bwd_masks(const float* g, int B, int C, int N, int M,
   if (tiles_per_cta > ntiles) tiles_per_cta = ntiles;
   const int parts = (ntiles + tiles_per_cta - 1) / tiles_per_cta;
   void (*kern)(const float*, int, int, int, int, const int*, const int*, const int*, const int*, const int*, const float*,
-               const int*, int, const int*, const int*, const float*, const float*, float, float*, int, int, int, const int*, int, int) = nullptr;
+               const int*, int, const int*, const int*, const float*, const float*, float, float*, int, int, int, const int*, int, int, int) = nullptr;
   switch (CT) {
     case 8: kern = shift_bwd_kernel<8>; break;
     case 4: kern = shift_bwd_kernel<4>; break;
@@ -497,9 +505,13 @@ extern "C" int ipsr_shift_bwd_masks(const float* g, int B, int C, int N, int M,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "shift_bwd smem attribute: %s", cudaGetErrorString(e));
   }
+  // IPSR_BWD_QUEUE (tests; read per call): a smaller hub queue, so that a modest case exercises its overflow
+  int qcap = kBwdQueue;
+  if (const char* e = getenv("IPSR_BWD_QUEUE")) qcap = std::max(1, std::min(kBwdQueue, atoi(e)));
   kern<<<dim3(parts, B), threads, smem, as_stream(stream)>>>(g, C, N, M, tiles_per_cta, route_ptr, route_q, exc_start, exc_cnt,
                                                             exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn, wo, triple_w,
                                                             gin, ninfo, nexc_s, mask_stride, m_count, S,
-                                                            []{ const char* e = getenv("IPSR_BWD_LIGHT"); return e ? atoi(e) : kBwdLight; }());
+                                                            []{ const char* e = getenv("IPSR_BWD_LIGHT"); return e ? atoi(e) : kBwdLight; }(),
+                                                            qcap);
   return check_launch("ipsr_shift_bwd");
 }

@@ -13,8 +13,8 @@
 //                        (ipsr_correlate_argmax_fp32).
 //
 // One CTA = ROWT x 128 query rows (one TMEM lane each) x a range of bank columns, walked in blocks of 128
-// columns.  Warp roles (64 + 128*ROWT threads):
-//   warp 0       producer: bulk async copies (UBLKCP) of pre-swizzled 16 KiB tile images -> smem ring
+// columns.  Warp roles (96 + 128*ROWT threads):
+//   warp 0, last producers (alternate stages): bulk async copies (UBLKCP) of pre-swizzled 16 KiB tile images -> smem ring
 //   warp 1       TMEM allocation + single-thread tcgen05.mma issue, commits free the ring slots
 //   warps 2..    epilogue, 4 warps per row tile: tcgen05.ld of the finished accumulator (double-buffered in
 //                TMEM) and the running (best, idx, second) per row in registers -- thread == row, no shuffles.
@@ -40,6 +40,8 @@ struct TcParams {
   int blocks_total;         // number of 128-column blocks in [col_begin, col_end)
   int psplit;
   int stages;
+  int nprod;                // producer warps in use (1 or 2): issuing one bulk copy costs its thread ~650 cycles, two
+                            // warps issue alternate stages
   float* part_best;
   int* part_idx;
   float* part_second;
@@ -58,7 +60,7 @@ struct TcParams {
 // BN: bank columns per accumulator block = N of the tcgen05.mma instruction (128, or 256 with ROWT = 1 and one pass: two
 // adjacent bank tiles per stage, one 128 x 256 x 16 instruction instead of two 128 x 128 x 16 ones).
 template <int ROWT, int PASSES, bool A_RESIDENT, int CL, int BN = 128>
-__global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcParams prm) {
+__global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcParams prm) {
   static_assert(BN == 128 || (BN == 256 && ROWT == 1 && PASSES == 1), "256-column blocks: one row tile, one pass");
   constexpr int kBlockN = BN;                                  // shadows the namespace constant inside this kernel
   constexpr int kBT = BN / 128;                                // bank tiles per block
@@ -130,21 +132,30 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (CL == 2) cluster_sync_all();             // the peer's barriers exist before anything is sent to them
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ producer
-    if (lane == 0 && nblk > 0) {
+  constexpr int kProducer2 = 2 + 4 * ROWT;                    // the second producer warp sits behind the epilogue warps
+  if (warp == 0 || warp == kProducer2) {
+    // ------------------------------------------------------------------ producers
+    // Measured (scripts/micro/bulk_bw.cu): a thread gets ONE bulk copy out per ~650 cycles whatever its size -- about the
+    // time the tensor core needs for a whole stage -- while copies of different warps proceed side by side.  So the
+    // stages alternate between two issuing warps.
+    const int pid = warp == 0 ? 0 : 1;
+    const int nprod = prm.nprod;
+    if (lane == 0 && nblk > 0 && pid < nprod) {
       if (A_RESIDENT) {
-        mbar_expect_tx(a_full_bar, a_bytes);
+        if (pid == 0) mbar_expect_tx(a_full_bar, a_bytes);
+        int idx = 0;
         for (int rt = 0; rt < ROWT; ++rt)
           for (int kb = 0; kb < KB; ++kb)
-            for (int hl = 0; hl < AH; ++hl)
-              bulk_g2s(a_base + (uint32_t)((rt * KB + kb) * AH + hl) * kTileBytes,
-                       prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg * ROWT + rt, KB, RB, prm.a_parts), kTileBytes, a_full_bar);
+            for (int hl = 0; hl < AH; ++hl, ++idx)
+              if (idx % nprod == pid)
+                bulk_g2s(a_base + (uint32_t)((rt * KB + kb) * AH + hl) * kTileBytes,
+                         prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg * ROWT + rt, KB, RB, prm.a_parts), kTileBytes, a_full_bar);
       }
       int it = 0;
       for (int blk = blk0; blk < blk1; ++blk) {
         const int cb = (prm.col_begin >> 7) + blk * kBT;          // first 128-row bank tile of the block
         for (int kb = 0; kb < KB; ++kb, ++it) {
+          if (it % nprod != pid) continue;
           const int s = it % prm.stages;
           const uint32_t ph = (uint32_t)(it / prm.stages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(64 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
         umma_commit(tfull_bar(as));           // accumulators complete -> epilogue
       }
     }
-  } else {
+  } else if (warp < kProducer2) {
     // ------------------------------------------------------------------ epilogue (thread == row)
     const int rt = (warp - 2) >> 2;
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
@@ -454,13 +465,18 @@ static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
   const size_t stage = (A_RES ? 0 : (size_t)AH * kTileBytes) + (size_t)AH * kTileBytes * (BN / 128);
   size_t smem = 0;
   prm.stages = tc_stage_count(a_bytes, stage, &smem);
+  static const int producers = [] {                        // IPSR_TC_PRODUCERS=1 (A/B runs): one issuing warp
+    const char* e = getenv("IPSR_TC_PRODUCERS");
+    return (e && atoi(e) == 1) ? 1 : 2;
+  }();
+  prm.nprod = producers;
   IPSR_REQUIRE(prm.stages >= 2, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: C=%d leaves %d pipeline stages", C, prm.stages);
   auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL, BN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)ctas);
-  cfg.blockDim = dim3(64 + 128 * ROWT);
+  cfg.blockDim = dim3(96 + 128 * ROWT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

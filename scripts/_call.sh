@@ -1,2 +1,1 @@
-timeout 700 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t18.log 2>&1; echo "pytest rc=$?"; tail -n 4 gpurun_out/r2_t18.log
-python bench.py --steps 500 > gpurun_out/r2_bench4.json 2> gpurun_out/r2_bench4.err; echo "bench rc=$?"
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "hub_pieces" > gpurun_out/r2_t19.log 2>&1; echo "pytest rc=$?"; tail -n 12 gpurun_out/r2_t19.log
