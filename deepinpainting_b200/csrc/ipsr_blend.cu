@@ -22,12 +22,11 @@ namespace ipsr {
 //   U  [T][C]  u_l = X[q_l] * inv_norm[q_l]                       (IPSRFunction.py:109)
 //   K  [T][C]  X[p_l], the matched bank patch                     (:95)
 //   Gt [T][T]  Gt[j][i] = <u_{l0+i}, X[p_{l0+j}>                  (in-block Gram matrix, transposed)
-//   G2 [T][T]  G2[j][i] = <u_{l0+T+i}, X[p_{l0+j}>                (the NEXT block's u rows against this block's matches)
 //   v  [T]     v_l = <R[q_l], Xn[p_l]>  exact fp32                (vmax at masked positions, :70)
 __host__ __device__ inline int scan_block_steps(int C) { return C <= 256 ? 32 : (C <= 512 ? 16 : 8); }
 __host__ __device__ inline int staged_block_floats(int C) {
   const int T = scan_block_steps(C);
-  return 2 * T * C + 2 * T * T + T;
+  return 2 * T * C + T * T + T;
 }
 // rows of y per image: M rounded up to a multiple of 8
 __host__ __device__ inline int padded_steps(int M) { return (M + 7) & ~7; }
@@ -60,26 +59,15 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
   const int ld = C + 4;                                  // padded row: conflict-free float4 reads across rows
   float* Us = stage_smem;                                // [T][ld]
   float* Ks = Us + (size_t)T * ld;                       // [T][ld]
-  float* U2s = Ks + (size_t)T * ld;                      // [T][ld] u rows of the next block
-  float* red = U2s + (size_t)T * ld;                     // [kSplit][T*T] (kSplit > 1 only)
+  float* red = Ks + (size_t)T * ld;                      // [kSplit][T*T] (kSplit > 1 only)
   const int l0 = kblk * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* blk = staged + ((size_t)b * nblocks + kblk) * staged_block_floats(C);
   float* gU = blk;
   float* gK = blk + (size_t)T * C;
-  float* gG1 = gK + (size_t)T * C;
-  float* gG2 = gG1 + T * T;
-  float* gV = gG2 + T * T;
+  float* gG = gK + (size_t)T * C;
+  float* gV = gG + T * T;
 
-  // index chains of the next block's rows first: they are in flight while this block's rows are gathered
-  int q2[(T + 7) / 8];
-  float inv2[(T + 7) / 8];
-#pragma unroll
-  for (int rr_ = 0; rr_ < (T + 7) / 8; ++rr_) {
-    const int l = l0 + T + warp + 8 * rr_;
-    q2[rr_] = (warp + 8 * rr_ < T && l < Mc) ? mask_idx[l] : -1;
-    inv2[rr_] = q2[rr_] >= 0 ? inv_norm[(size_t)b * N + q2[rr_]] : 0.f;
-  }
 #pragma unroll
   for (int rr_ = 0; rr_ < (T + 7) / 8; ++rr_) {           // unrolled: the index chains of the warp's rows overlap
     const int r = warp + 8 * rr_;
@@ -128,25 +116,6 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
       if (vmask) vmask[(size_t)b * M + l] = acc;
     }
   }
-  // u rows of the next block (zero beyond the image's last step)
-#pragma unroll
-  for (int rr_ = 0; rr_ < (T + 7) / 8; ++rr_) {
-    const int r = warp + 8 * rr_;
-    if (r >= T) break;
-    float* su = U2s + (size_t)r * ld;
-    const int q = q2[rr_];
-    if (q < 0) {
-      for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<float4*>(su + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
-    const float inv_q = inv2[rr_];
-    const float* xq = xt + ((size_t)b * N + q) * C;
-    for (int c = lane * 4; c < C; c += 128) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(xq + c));
-      *reinterpret_cast<float4*>(su + c) =
-          make_float4(__fmul_rn(a.x, inv_q), __fmul_rn(a.y, inv_q), __fmul_rn(a.z, inv_q), __fmul_rn(a.w, inv_q));
-    }
-  }
   __syncthreads();
 
   // Gram: tile (ti, tj) -> rows i = ti, ti + T/2 of U against rows j = tj, tj + T/2 of K
@@ -159,11 +128,8 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
   const float* k0 = Ks + (size_t)tj * ld;
   const float* k1 = k0 + (size_t)(T / 2) * ld;
   const int i0 = ti, i1 = ti + T / 2, j0 = tj, j1 = tj + T / 2;
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {                // in-block Gram, then the next block's rows against these matches
-  const float* u0 = (which ? U2s : Us) + (size_t)ti * ld;
+  const float* u0 = Us + (size_t)ti * ld;
   const float* u1 = u0 + (size_t)(T / 2) * ld;
-  float* gG = which ? gG2 : gG1;
   float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
 #pragma unroll 4
   for (int c = cbeg; c < cend; c += 4) {
@@ -193,8 +159,6 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
       for (int k2 = 1; k2 < kSplit; ++k2) s += red[(size_t)k2 * T * T + e];
       gG[e] = s;
     }
-    __syncthreads();                                       // red is reused by the second Gram
-  }
   }
 }
 
@@ -215,6 +179,29 @@ __global__ void __launch_bounds__(256) blend_stage_kernel(const StageArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // scan
+//
+// The recurrence of IPSRFunction.py:104-122,
+//     a_l = <u_l, y_{l-1}>,  wn_l = a_l/(a_l+v_l),  wo_l = v_l/(a_l+v_l),  y_l = wn_l y_{l-1} + wo_l X[p_l],
+// is sequential in l, but only through ONE scalar per step.  By linearity the scalars
+//     z_i = <u_i, y_cur>   (i = the steps still ahead inside the block of T steps)
+// follow y:  z_i <- wn_l z_i + wo_l <u_i, X[p_l]> = wn_l z_i + wo_l Gt[l][i],  so that a_l is simply z_l by the time step
+// l is reached.  One CTA per image, per block of T steps:
+//   B  warps 1..7: z_i = <u_i, y_prev> for the T rows of the block (re-anchors z on the real y every T steps, so
+//                  rounding differences to the reference's dot product cannot accumulate); warp 0 meanwhile loads the
+//                  chain's operands
+//   C  warp 0    : the T dependent steps on scalars only; warps 1..7 meanwhile store the previous block's y rows
+//   D  warps 0..7: y_l = wn_l y_{l-1} + wo_l X[p_l] channel-parallel, exactly the reference's two rounded products and
+//                  one sum (:122), left as 16-byte vectors in a [C][T+4] tile that the store reads row-wise
+//   warp 8       : the bulk async copies of the two-stage ring (issuing one costs its thread ~650 cycles:
+//                  scripts/micro/bulk_bw.cu)
+// The chain step: every lane carries the DIAGONAL element zd = z_j (the one step j divides by) itself -- lane j+1's state
+// before step j is broadcast by a shuffle issued at the START of step j, and every lane applies step j's update to it with
+// the formula lane j+1 uses for its own state (same bits) -- so the shuffle runs next to the reciprocal instead of in
+// front of it: one add, one reciprocal, one product and one fma on the dependent path (~47 cycles; with the shuffle in
+// the path it was ~165).  An alternative that takes B and D off the chain's path as well (z across a block boundary from a
+// second Gram matrix <u_{next block}, X[p_l]>) was built and measured: 20.6 us against 21 us here at 32x32 (the workers
+// become the limit), and the second Gram costs the stage kernel 60 us at 64x64x256 -- not kept.
+// wn, wo use a * rcp(a+v): <= 2 ulp from the reference's IEEE divisions.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -222,295 +209,216 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-// ---------------------------------------------------------------------------------------------
-// scan
-//
-// The recurrence of IPSRFunction.py:104-122,
-//     a_l = <u_l, y_{l-1}>,  wn_l = a_l/(a_l+v_l),  wo_l = v_l/(a_l+v_l),  y_l = wn_l y_{l-1} + wo_l X[p_l],
-// is sequential in l, but only through ONE scalar per step.  By linearity the scalars
-//     z_i = <u_i, y_cur>   (i = the steps still ahead inside the block of T steps)
-// follow y:  z_i <- wn_l z_i + wo_l <u_i, X[p_l]> = wn_l z_i + wo_l Gt[l][i],  so that a_l is simply z_l by the time step
-// l is reached.  The same holds ACROSS a block boundary: with y_e(k) the state after block k,
-//     y_e(k) = alpha_k y_e(k-1) + sum_l beta_l X[p_l]          (alpha_k = prod wn_l, beta_l = wo_l prod_{m>l} wn_m)
-//     z_i(k+1) = <u_i, y_e(k)> = alpha_k W_i(k+1) + s_i,   W_i(k+1) = <u_i(k+1), y_e(k-1)>,   s_i = sum_l beta_l G2[l][i]
-// and alpha, s follow the chain's own recurrence (s <- wn s + wo G2[l][i], alpha <- wn alpha), off its dependent path.
-// One CTA per image:
-//   warp 0      the chain: ALL M dependent steps back to back on scalars (one add, one reciprocal, one product and one
-//               fma on the dependent path of a step); it never waits for channel-wide work
-//   warps 1..8  the workers, one block behind: D(k) -- the y rows of block k from the weights the chain published, exactly
-//               the reference's two rounded products and one sum (:122) --, W(k+2) from the real y_e(k) (z stays anchored
-//               on the real y, two blocks back, so rounding differences to the reference's dot product cannot
-//               accumulate), and the coalesced store of the block's rows
-//   warp 9      every bulk async copy of the CTA: U and K rows through 2-stage rings, the small Gram / v part through 3
-// wn, wo use a * rcp(a+v): <= 2 ulp from the reference's IEEE divisions.
-// ---------------------------------------------------------------------------------------------
-constexpr int kScanMaxCpt = 4;           // channels per worker thread: C <= 1024
-constexpr int kScan2Workers = 256;                         // warps 1..8
-constexpr int kScan2Threads = 32 + kScan2Workers + 32;     // + the chain (warp 0) and the copy warp (warp 9)
-constexpr int kScan2GStages = 3;
+constexpr int kScanMaxCpt = 4;                             // channels per thread: C <= 1024
+constexpr int kScanCompute = 256;                          // warps 0..7
+constexpr int kScanThreads = kScanCompute + 32;            // + the copy warp
 
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kScan2Workers) : "memory"); }
+__device__ __forceinline__ void scan_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kScanCompute) : "memory"); }
 
 template <int T>
-__global__ void __launch_bounds__(kScan2Threads)
-blend_scan2_kernel(const float* __restrict__ staged, int C, int Mmax,
-                   float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out,
-                   const int* __restrict__ mcount) {
+__global__ void __launch_bounds__(kScanThreads)
+blend_scan_kernel(const float* __restrict__ staged, int C, int Mmax,
+                  float* __restrict__ y, float* __restrict__ wn_out, float* __restrict__ wo_out,
+                  const int* __restrict__ mcount) {
   extern __shared__ __align__(128) uint8_t scan_smem[];
-  // barriers: u_full[2], k_full[2], weights[2] (chain -> workers), w_ready[2] (workers -> chain), u_free[2], k_free[2]
-  // (workers -> copy warp), g_full[GS], g_free[GS] (chain -> copy warp)
-  __shared__ __align__(8) unsigned long long bars[12 + 2 * kScan2GStages];
-  __shared__ __align__(16) float wn_s[2][T], wo_s[2][T], w_s[2][T];
-  const int blk_floats = 2 * T * C + 2 * T * T + T;
-  const uint32_t row_bytes = (uint32_t)T * C * sizeof(float);
-  constexpr uint32_t g_bytes = (2u * T * T + T) * sizeof(float);
-  constexpr uint32_t g_stage = (g_bytes + 127u) & ~127u;
-  float* Uring = reinterpret_cast<float*>(scan_smem);
-  float* Kring = Uring + 2 * (size_t)T * C;
-  uint8_t* Gring = reinterpret_cast<uint8_t*>(Kring + 2 * (size_t)T * C);
-  float* ysm = reinterpret_cast<float*>(Gring + kScan2GStages * g_stage);        // [C] y at the end of the last finished block
-  float* ytile = ysm + C;                                                       // [C][T+4]
+  __shared__ __align__(8) unsigned long long bars[4];      // full[2], free[2]
+  __shared__ __align__(16) float zs[T], wn_s[T], wo_s[T];
+  const int blk_floats = 2 * T * C + T * T + T;
+  const uint32_t blk_bytes = (uint32_t)blk_floats * sizeof(float);
+  const uint32_t stage_bytes = (blk_bytes + 127u) & ~127u;
+  float* ysm = reinterpret_cast<float*>(scan_smem + 2 * (size_t)stage_bytes);     // [C] y at the end of the previous block
+  float* ytile = ysm + C;                                                        // [C][T+4] the block's y rows
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // per-image masks: strides come from the batch maximum, the steps walked from this image's own count
   const int M = mcount ? mcount[b] : Mmax;
   const int nblocks = (M + T - 1) / T;
   const float* src = staged + (size_t)b * ((Mmax + T - 1) / T) * blk_floats;
   const int Mp = padded_steps(Mmax);
-  float* yb = y + (size_t)b * C * Mp;
+  float* yb = y + (size_t)b * C * Mp;                    // [C][Mp]: channel-major, so that the paste reads rows
   float* wnb = wn_out + (size_t)b * Mmax;
   float* wob = wo_out + (size_t)b * Mmax;
   const uint32_t bar0 = smem_u32(&bars[0]);
-  auto u_full = [&](int s) { return bar0 + 8u * s; };
-  auto k_full = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto wts_bar = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto w_bar = [&](int s) { return bar0 + 8u * (6 + s); };
-  auto u_free = [&](int s) { return bar0 + 8u * (8 + s); };
-  auto k_free = [&](int s) { return bar0 + 8u * (10 + s); };
-  auto g_full = [&](int s) { return bar0 + 8u * (12 + s); };
-  auto g_free = [&](int s) { return bar0 + 8u * (12 + kScan2GStages + s); };
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto free_bar = [&](int s) { return bar0 + 8u * (2 + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < 12 + 2 * kScan2GStages; ++s)       // one arrival each, but the eight worker warps on w_ready
-      mbar_init(bar0 + 8u * s, (s == 6 || s == 7) ? kScan2Workers / 32 : 1);
+    for (int s = 0; s < 4; ++s) mbar_init(bar0 + 8u * s, 1);
     mbar_fence_init();
   }
-  for (int c = tid; c < C; c += kScan2Threads) ysm[c] = 0.f;
+  for (int c = tid; c < C; c += kScanThreads) ysm[c] = 0.f;
   __syncthreads();
   if (nblocks == 0) return;
 
-  if (warp == 9) {
-    // ------------------------------------------------------------------ the copy warp: every bulk copy of the CTA
-    // (issuing one costs several hundred cycles; here that is nobody's critical path)
+  if (warp == kScanCompute / 32) {
+    // ------------------------------------------------------------------ the copy warp
     if (lane != 0) return;
-    auto issue_u = [&](int k) {                             // U rows of block k (k >= 2: W(0) = W(1) = 0 need none)
-      mbar_expect_tx(u_full(k & 1), row_bytes);
-      bulk_g2s(smem_u32(Uring + (size_t)(k & 1) * T * C), src + (size_t)k * blk_floats, row_bytes, u_full(k & 1));
+    auto issue = [&](int k) {
+      const int s = k & 1;
+      mbar_expect_tx(full_bar(s), blk_bytes);
+      bulk_g2s(smem_u32(scan_smem) + (uint32_t)s * stage_bytes, src + (size_t)k * blk_floats, blk_bytes, full_bar(s));
     };
-    auto issue_k = [&](int k) {
-      mbar_expect_tx(k_full(k & 1), row_bytes);
-      bulk_g2s(smem_u32(Kring + (size_t)(k & 1) * T * C), src + (size_t)k * blk_floats + (size_t)T * C, row_bytes, k_full(k & 1));
-    };
-    auto issue_g = [&](int k) {
-      const int s = k % kScan2GStages;
-      mbar_expect_tx(g_full(s), g_bytes);
-      bulk_g2s(smem_u32(Gring + (size_t)s * g_stage), src + (size_t)k * blk_floats + 2 * (size_t)T * C, g_bytes, g_full(s));
-    };
-    issue_g(0);
-    issue_k(0);
-    for (int k = 1; k < kScan2GStages && k < nblocks; ++k) issue_g(k);
-    if (nblocks > 1) issue_k(1);
-    if (nblocks > 2) issue_u(2);
-    if (nblocks > 3) issue_u(3);
-    for (int k = 0; k < nblocks; ++k) {                      // refills in the order their stages come free
-      if (k + kScan2GStages < nblocks) {
-        mbar_wait(g_free(k % kScan2GStages), (uint32_t)(k / kScan2GStages) & 1u);
-        issue_g(k + kScan2GStages);
-      }
-      if (k + 2 < nblocks) {
-        mbar_wait(k_free(k & 1), (uint32_t)(k >> 1) & 1u);
-        issue_k(k + 2);
-      }
-      if (k + 4 < nblocks) {
-        mbar_wait(u_free(k & 1), (uint32_t)(k >> 1) & 1u);
-        issue_u(k + 4);
-      }
+    issue(0);
+    if (nblocks > 1) issue(1);
+    for (int k = 0; k + 2 < nblocks; ++k) {
+      mbar_wait(free_bar(k & 1), (uint32_t)(k >> 1) & 1u);  // the compute warps are done with block k's stage
+      issue(k + 2);
     }
-  } else if (warp == 0) {
-    // ------------------------------------------------------------------ the chain
+    return;
+  }
+
+  float yreg[kScanMaxCpt];
+#pragma unroll
+  for (int m = 0; m < kScanMaxCpt; ++m) yreg[m] = 0.f;
+
+  // y[c][l0 .. ) of block kb from ytile: T/4 lanes per channel row, 16 bytes each (rows of y are padded to a multiple of
+  // 8 steps, so the last vector of the image's last block stays inside its row).  Runs OFF the critical path: warps 1..7
+  // store block k-1 while warp 0 walks the scalar steps of block k.
+  auto store_ytile = [&](int kb, int w0, int nw) {
+    constexpr int LPC = T / 4, CPI = 32 / LPC;             // lanes per channel, channels per warp instruction
+    const int lb = kb * T;
+    const int nv = min(T, M - lb);
+    const int lc = lane / LPC, l4 = lane % LPC;
+    if (4 * l4 < nv) {
+#pragma unroll 4
+      for (int c = (warp - w0) * CPI + lc; c < C; c += nw * CPI)
+        *reinterpret_cast<float4*>(yb + (size_t)c * Mp + lb + 4 * l4) =
+            *reinterpret_cast<const float4*>(ytile + (size_t)c * (T + 4) + 4 * l4);
+    }
+  };
+
+  for (int k = 0; k < nblocks; ++k) {
+    const int s = k & 1;
+    mbar_wait(full_bar(s), (uint32_t)(k >> 1) & 1u);
+    const float* U = reinterpret_cast<const float*>(scan_smem + (size_t)s * stage_bytes);
+    const float* K = U + (size_t)T * C;
+    const float* Gt = K + (size_t)T * C;
+    const float* V = Gt + T * T;
+    const int l0 = k * T;
+
+    // ---- B: z_i = <u_i, y_prev> by warps 1..7 (ceil(T/7) rows each); warp 0 meanwhile fetches what its chain needs and
+    //         what does not depend on z: v of every step, v_j times the Gram column of its lane and times the element
+    //         next to the diagonal ----
     const int li = lane < T ? lane : T - 1;
-    float z = 0.f;                                           // z_i(0) = <u_i, 0>
-    for (int k = 0; k < nblocks; ++k) {
-      const int gs = k % kScan2GStages;
-      mbar_wait(g_full(gs), (uint32_t)(k / kScan2GStages) & 1u);
-      const float* Gt = reinterpret_cast<const float*>(Gring + (size_t)gs * g_stage);
-      const float* G2 = Gt + T * T;
-      // Every lane carries the DIAGONAL element zd = z_j (the one step j divides by) itself: lane j+1's state before step j
-      // is broadcast by a shuffle issued at the START of step j, and every lane applies step j's update to it with the
-      // formula lane j+1 uses for its own state (same bits).  The shuffle then runs next to the reciprocal instead of
-      // in front of it: the dependent path of a step is one add, one reciprocal, one product and one fma.
-      float vg[T], vg2[T], vgd[T], vj[T];
+    float vg[T], vgd[T], vj[T];
+    if (warp == 0) {
 #pragma unroll
       for (int j = 0; j < T; ++j) {
-        vj[j] = Gt[2 * T * T + j];                              // (uniform address: broadcast)
+        vj[j] = V[j];                                           // (uniform address: broadcast)
         vg[j] = __fmul_rn(vj[j], Gt[j * T + li]);
-        vg2[j] = __fmul_rn(vj[j], G2[j * T + li]);
         vgd[j] = (j + 1 < T) ? __fmul_rn(vj[j], Gt[j * T + j + 1]) : 0.f;
       }
-      float g0 = 0.f, g20 = 0.f, gd0 = 0.f;                   // raw first row: the very first step copies
-      if (k == 0) {
-        g0 = Gt[li];
-        g20 = G2[li];
-        gd0 = Gt[1 < T ? 1 : 0];
+    } else {
+      constexpr int NW = kScanCompute / 32 - 1;              // 7 warps
+      constexpr int R = (T + NW - 1) / NW;                   // rows per warp
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 2
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 yv = *reinterpret_cast<const float4*>(ysm + c);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = (warp - 1) + r * NW;
+          if (i < T) {
+            const float4 u = *reinterpret_cast<const float4*>(U + (size_t)i * C + c);
+            acc[r] = fmaf(u.x, yv.x, acc[r]);
+            acc[r] = fmaf(u.y, yv.y, acc[r]);
+            acc[r] = fmaf(u.z, yv.z, acc[r]);
+            acc[r] = fmaf(u.w, yv.w, acc[r]);
+          }
+        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(g_free(gs));                // every lane holds this stage's values in registers
-      float my_wn = 0.f, my_wo = 1.f, s2 = 0.f, alpha = 1.f;
-      float zd = __shfl_sync(0xffffffffu, z, 0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = (warp - 1) + r * NW;
+          if (i < T) zs[i] = acc[r];
+        }
+      }
+    }
+    scan_barrier();
+
+    // ---- C: T scalar steps ----
+    if (warp == 0) {
+      float z = zs[li];
+      float zd = zs[0];
+      float my_wn = 0.f, my_wo = 1.f;
 #pragma unroll
       for (int j = 0; j < T; ++j) {
         const float p = (j + 1 < T) ? __shfl_sync(0xffffffffu, z, j + 1) : 0.f;
         const float r = rcp_approx(__fadd_rn(zd, vj[j]));       // no clamp: inf / nan propagate      :120
         float wn = __fmul_rn(zd, r);
         float wo = __fmul_rn(vj[j], r);                         //                                     :121
-        float tz = __fmul_rn(r, vg[j]), ts = __fmul_rn(r, vg2[j]), td = __fmul_rn(r, vgd[j]);   // wo * <u_i, X[p_j]>
+        float tz = __fmul_rn(r, vg[j]), td = __fmul_rn(r, vgd[j]);   // wo * <u_i, X[p_j]>
         if (k == 0 && j == 0) {                                 // first masked patch: plain copy      :98-101
           wn = 0.f;
           wo = 1.f;
-          tz = g0;
-          ts = g20;
-          td = gd0;
+          tz = Gt[li];
+          td = Gt[1 < T ? 1 : 0];
         }
         z = fmaf(wn, z, tz);
         zd = fmaf(wn, p, td);
-        s2 = fmaf(wn, s2, ts);
-        alpha = __fmul_rn(alpha, wn);
         if (lane == j) {
           my_wn = wn;
           my_wo = wo;
         }
       }
-      const int l0 = k * T;
       if (lane < T) {
-        wn_s[k & 1][lane] = my_wn;
-        wo_s[k & 1][lane] = my_wo;
+        wn_s[lane] = my_wn;
+        wo_s[lane] = my_wo;
         if (l0 + lane < M) {
           wnb[l0 + lane] = my_wn;
           wob[l0 + lane] = my_wo;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(wts_bar(k & 1));            // weights of block k are in shared memory
-      if (k + 1 < nblocks) {
-        if (k + 1 >= 2) {                                    // W(k+1) = <u_i(k+1), y_e(k-1)> from the workers
-          mbar_wait(w_bar((k + 1) & 1), (uint32_t)(((k + 1) >> 1) - 1) & 1u);
-          z = fmaf(alpha, w_s[(k + 1) & 1][li], s2);
-        } else {
-          z = s2;                                            // y_e(-1) = 0
+    } else if (k > 0) {
+      store_ytile(k - 1, 1, kScanCompute / 32 - 1);
+    }
+    scan_barrier();
+
+    // ---- D: y rows of the block; a thread owns a channel (lane stride T+4 floats: conflict-free vector stores) ----
+    const int nvalid = min(T, M - l0);
+#pragma unroll
+    for (int m = 0; m < kScanMaxCpt; ++m) {
+      const int c = tid + m * kScanCompute;
+      if (c < C) {
+        float yy = yreg[m];
+        float* yrow = ytile + (size_t)c * (T + 4);
+        if (nvalid == T) {                                   // full block: operands first, then the 2-op chain
+          float kv[T];
+#pragma unroll
+          for (int j = 0; j < T; ++j) kv[j] = K[(size_t)j * C + c];
+#pragma unroll
+          for (int j4 = 0; j4 < T / 4; ++j4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&wn_s[4 * j4]);
+            const float4 o4 = *reinterpret_cast<const float4*>(&wo_s[4 * j4]);
+            float4 o;
+            o.x = yy = __fadd_rn(__fmul_rn(a4.x, yy), __fmul_rn(o4.x, kv[4 * j4 + 0]));          // :122
+            o.y = yy = __fadd_rn(__fmul_rn(a4.y, yy), __fmul_rn(o4.y, kv[4 * j4 + 1]));
+            o.z = yy = __fadd_rn(__fmul_rn(a4.z, yy), __fmul_rn(o4.z, kv[4 * j4 + 2]));
+            o.w = yy = __fadd_rn(__fmul_rn(a4.w, yy), __fmul_rn(o4.w, kv[4 * j4 + 3]));
+            *reinterpret_cast<float4*>(yrow + 4 * j4) = o;
+          }
+        } else {                                             // the image's last block: zeros behind its last step
+          for (int j = 0; j < T; ++j) {
+            if (j < nvalid) yy = __fadd_rn(__fmul_rn(wn_s[j], yy), __fmul_rn(wo_s[j], K[(size_t)j * C + c]));   // :122
+            yrow[j] = j < nvalid ? yy : 0.f;
+          }
         }
+        yreg[m] = yy;
+        ysm[c] = yy;
       }
     }
-  } else {
-    // ------------------------------------------------------------------ the workers, one block behind the chain
-    const int wt = tid - 32, ww = warp - 1;                  // 0..255, 0..7
-    float yreg[kScanMaxCpt];
-#pragma unroll
-    for (int m = 0; m < kScanMaxCpt; ++m) yreg[m] = 0.f;
-    for (int k = 0; k < nblocks; ++k) {
-      const int s = k & 1;
-      const uint32_t ph = (uint32_t)(k >> 1) & 1u;
-      mbar_wait(wts_bar(s), ph);
-      mbar_wait(k_full(s), ph);
-      const float* K = Kring + (size_t)s * T * C;
-      const int l0 = k * T;
-      const int nvalid = min(T, M - l0);
-      // ---- D: y rows of the block; a thread owns a channel and leaves its T values as 16-byte vectors in ytile[c][T+4]
-      //         (lane stride T+4 floats: conflict-free vector stores, and the store phase reads whole rows)
-#pragma unroll
-      for (int m = 0; m < kScanMaxCpt; ++m) {
-        const int c = wt + m * kScan2Workers;
-        if (c < C) {
-          float yy = yreg[m];
-          float* yrow = ytile + (size_t)c * (T + 4);
-          if (nvalid == T) {
-            float kv[T];
-#pragma unroll
-            for (int j = 0; j < T; ++j) kv[j] = K[(size_t)j * C + c];
-#pragma unroll
-            for (int j4 = 0; j4 < T / 4; ++j4) {
-              const float4 a4 = *reinterpret_cast<const float4*>(&wn_s[s][4 * j4]);
-              const float4 o4 = *reinterpret_cast<const float4*>(&wo_s[s][4 * j4]);
-              float4 o;
-              o.x = yy = __fadd_rn(__fmul_rn(a4.x, yy), __fmul_rn(o4.x, kv[4 * j4 + 0]));          // :122
-              o.y = yy = __fadd_rn(__fmul_rn(a4.y, yy), __fmul_rn(o4.y, kv[4 * j4 + 1]));
-              o.z = yy = __fadd_rn(__fmul_rn(a4.z, yy), __fmul_rn(o4.z, kv[4 * j4 + 2]));
-              o.w = yy = __fadd_rn(__fmul_rn(a4.w, yy), __fmul_rn(o4.w, kv[4 * j4 + 3]));
-              *reinterpret_cast<float4*>(yrow + 4 * j4) = o;
-            }
-          } else {                                           // the image's last block: zeros behind its last step
-            for (int j = 0; j < T; ++j) {
-              if (j < nvalid) yy = __fadd_rn(__fmul_rn(wn_s[s][j], yy), __fmul_rn(wo_s[s][j], K[(size_t)j * C + c]));   // :122
-              yrow[j] = j < nvalid ? yy : 0.f;
-            }
-          }
-          yreg[m] = yy;
-          ysm[c] = yy;
-        }
-      }
-      worker_barrier();                                      // ytile / ysm complete, K stage s no longer read
-      if (wt == 0) mbar_arrive(k_free(s));
-      // ---- W(k+2) = <u_i(k+2), y_e(k)> first (the chain needs it at the end of block k+1), then the store
-      if (k + 2 < nblocks) {
-        mbar_wait(u_full(s), (uint32_t)((k >> 1)) & 1u);     // block k+2 is use number k/2 of stage s
-        const float* U = Uring + (size_t)s * T * C;
-        constexpr int R = (T + 7) / 8;
-        float acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f;
-#pragma unroll 2
-        for (int c = lane * 4; c < C; c += 128) {
-          const float4 yv = *reinterpret_cast<const float4*>(ysm + c);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int i = ww + r * 8;
-            if (i < T) {
-              const float4 u = *reinterpret_cast<const float4*>(U + (size_t)i * C + c);
-              acc[r] = fmaf(u.x, yv.x, acc[r]);
-              acc[r] = fmaf(u.y, yv.y, acc[r]);
-              acc[r] = fmaf(u.z, yv.z, acc[r]);
-              acc[r] = fmaf(u.w, yv.w, acc[r]);
-            }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int i = ww + r * 8;
-            if (i < T) w_s[s][i] = acc[r];
-          }
-          mbar_arrive(w_bar(s));
-        }
-      }
-      // ---- coalesced store of the block's y rows: T/4 lanes per channel row, 16 bytes each (rows of y are padded to a
-      //      multiple of 8 steps, so the last vector of the image's last block stays inside its row)
-      {
-        constexpr int LPC = T / 4, CPI = 32 / LPC;           // lanes per channel, channels per warp instruction
-        const int lc = lane / LPC, l4 = lane % LPC;
-        if (4 * l4 < nvalid) {
-#pragma unroll 4
-          for (int c = ww * CPI + lc; c < C; c += (kScan2Workers / 32) * CPI)
-            *reinterpret_cast<float4*>(yb + (size_t)c * Mp + l0 + 4 * l4) =
-                *reinterpret_cast<const float4*>(ytile + (size_t)c * (T + 4) + 4 * l4);
-        }
-      }
-      worker_barrier();                                      // ytile free for D(k+1); U stage s no longer read
-      if (wt == 0) mbar_arrive(u_free(s));
-    }
+    scan_barrier();                                        // ysm / ytile complete; stage s no longer read
+    if (tid == 0) mbar_arrive(free_bar(s));
   }
+  store_ytile(nblocks - 1, 0, kScanCompute / 32);          // the last block: every warp helps
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -730,7 +638,7 @@ namespace ipsr {
 template <int T>
 static int launch_stage(StageArgs a, cudaStream_t st) {
   constexpr int kSplit = 256 / ((T / 2) * (T / 2));
-  size_t smem = ((size_t)3 * T * (a.C + 4) + (kSplit > 1 ? (size_t)kSplit * T * T : 0)) * sizeof(float);
+  size_t smem = ((size_t)2 * T * (a.C + 4) + (kSplit > 1 ? (size_t)kSplit * T * T : 0)) * sizeof(float);
   if (a.n_routes > 0) {
     const size_t smem_routes = (size_t)(2 * a.N + 1) * sizeof(int);
     if (smem_routes > smem) smem = smem_routes;
@@ -756,16 +664,16 @@ static int dispatch_stage(const StageArgs& a, cudaStream_t st) {
 }
 
 template <int T>
-static int launch_scan2(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, cudaStream_t st,
-                        const int32_t* mcount) {
-  const size_t g_stage = (((size_t)2 * T * T + T) * sizeof(float) + 127) & ~(size_t)127;
-  const size_t smem = ((size_t)4 * T * C + (size_t)C + (size_t)C * (T + 4)) * sizeof(float) + kScan2GStages * g_stage;
+static int launch_scan(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, cudaStream_t st,
+                       const int32_t* mcount) {
+  const size_t blk_bytes = (size_t)staged_block_floats(C) * sizeof(float);
+  const size_t smem = 2 * ((blk_bytes + 127) & ~(size_t)127) + ((size_t)C + (size_t)C * (T + 4)) * sizeof(float);
   IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d too large", C);
-  if (smem + 2048 > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(blend_scan2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem + 2048 > 48 * 1024) {   // dynamic + static shared memory above the default limit (set per call: the attribute is per device)
+    cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
   }
-  blend_scan2_kernel<T><<<B, kScan2Threads, smem, st>>>(staged, C, M, y, wn, wo, mcount);
+  blend_scan_kernel<T><<<B, kScanThreads, smem, st>>>(staged, C, M, y, wn, wo, mcount);
   return check_launch("ipsr_blend_scan");
 }
 }  // namespace ipsr
@@ -824,9 +732,9 @@ int ipsr::blend_scan_ex(const float* staged, int B, int C, int M, float* y, floa
   IPSR_REQUIRE(C % 32 == 0 && C <= 1024, IPSR_ERR_UNSUPPORTED, "ipsr_blend_scan: C=%d must be a multiple of 32, <= 1024", C);
   cudaStream_t st = as_stream(stream);
   switch (scan_block_steps(C)) {
-    case 32: return launch_scan2<32>(staged, B, C, M, y, wn, wo, st, mcount);
-    case 16: return launch_scan2<16>(staged, B, C, M, y, wn, wo, st, mcount);
-    default: return launch_scan2<8>(staged, B, C, M, y, wn, wo, st, mcount);
+    case 32: return launch_scan<32>(staged, B, C, M, y, wn, wo, st, mcount);
+    case 16: return launch_scan<16>(staged, B, C, M, y, wn, wo, st, mcount);
+    default: return launch_scan<8>(staged, B, C, M, y, wn, wo, st, mcount);
   }
 }
 

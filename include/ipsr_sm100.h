@@ -223,7 +223,6 @@ int ipsr_maxcoord(const float* s, int P, int L, int64_t* ind_i64, float* vmax, v
  *   U  [T][C]  u_l = X[q_l] * inv_norm[q_l]                      (IPSRFunction.py:109)
  *   K  [T][C]  X[p_l]                                            (known_region, :95)
  *   Gt [T][T]  Gt[j][i] = <u_{l0+i}, X[p_{l0+j}]>                (in-block Gram matrix)
- *   G2 [T][T]  G2[j][i] = <u_{l0+T+i}, X[p_{l0+j}]>              (the next block's u rows against this block's matches)
  *   v  [T]     v_l = <R[q_l], Xn[p_l]>  exact fp32               (vmax at masked positions, :70)
  * staged is [B][ceil(M/T)][ipsr_staged_block_floats(C)]; vmask [B,M] (optional copy of v_l, may be NULL).
  * C % 32 == 0, C <= 1024. */
@@ -244,10 +243,9 @@ int ipsr_staged_block_floats(int C);
 int ipsr_padded_steps(int M);
 
 /* The recurrence itself, one CTA per image.  l=0: y_0 = X[p_0] (:98-101);  l>0: a = <u_l, y_{l-1}>;
- * wn = a/(a+v); wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).  The scalars a_l are
- * tracked by linearity (a_i <- wn_l a_i + wo_l Gt[l][i], and through G2 across one block boundary) so that
- * the dependent chain is one scalar step per masked position, walked by one warp that never waits for the
- * channel-wide work; a is re-anchored on the real y of two blocks earlier at every block boundary.
+ * wn = a/(a+v); wo = v/(a+v); y_l = wn*y_{l-1} + wo*X[p_l] (:104-122, no clamping).  Inside a block the
+ * scalars a_l are tracked by linearity (a_i <- wn_l a_i + wo_l Gt[l][i]) so that the dependent chain
+ * is one scalar step per masked position; y is re-anchored at every block boundary.
  * Writes y [B][C][ipsr_padded_steps(M)] (channel-major: the paste reads rows), wn/wo [B,M] (wn[b,0] = 0,
  * wo[b,0] = 1). */
 int ipsr_blend_scan(const float* staged, int B, int C, int M,
