@@ -23,6 +23,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("IPSR_PDL");
+    return e && atoi(e) == 1;                              // measured slower (see ipsr_common.cuh): off unless asked for
+  }();
+  return on;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -388,18 +396,11 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   IPSR_FORWARD(ipsr_correlate_argmax_fp32(a->x, a->ref, at<float>(a, w.inv_norm), B, C, N, cb, ce, list, nrecheck,
                                           tensor ? 0 : (N + 63) / 64, packed, stream));
   if (!tensor) IPSR_FORWARD(record(a->ev_corr_end));
-  if (a->nrecheck_out) {
-    e = cudaMemcpyAsync(a->nrecheck_out, nrecheck, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
-    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memcpy: %s", cudaGetErrorString(e));
-  }
-  if (a->npass2_out) {
-    e = cudaMemcpyAsync(a->npass2_out, npass2, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
-    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memcpy: %s", cudaGetErrorString(e));
-  }
   // rows recomputed in exact fp32 take their key; rows with exactly two candidates are settled by two exact dot products
-  IPSR_FORWARD(ipsr_resolve_rows(packed, list, nrecheck, tensor ? at<int32_t>(a, w.pair_list) : nullptr, npair,
-                                 tensor ? at<int32_t>(a, w.cand2) : nullptr, at<float>(a, w.xt), a->ref,
-                                 at<float>(a, w.inv_norm), B, C, N, a->ind, nullptr, stream));
+  // (the kernel also copies the per-image counters out: memcpy nodes here would cut the programmatic launch chain)
+  IPSR_FORWARD(resolve_rows_ex(packed, list, nrecheck, tensor ? at<int32_t>(a, w.pair_list) : nullptr, npair,
+                               tensor ? at<int32_t>(a, w.cand2) : nullptr, at<float>(a, w.xt), a->ref, at<float>(a, w.inv_norm), B, C, N,
+                               a->ind, nullptr, npass2, a->nrecheck_out, a->npass2_out, stream));
   if (a->stop_after_corr) {
     // bank-sharded mode: every row leaves with an exact (score, idx) key of its LOCAL winner
     if (tensor)

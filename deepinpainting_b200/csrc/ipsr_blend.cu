@@ -166,6 +166,8 @@ blend_stage_cta(int kblk, int b, float* stage_smem, const float* __restrict__ xt
 template <int T>
 __global__ void __launch_bounds__(256) blend_stage_kernel(const StageArgs a) {
   extern __shared__ __align__(16) float stage_smem[];
+  pdl_trigger();
+  pdl_wait();
   int blk = blockIdx.x;
   if (blk < a.n_routes) {
     build_routes_cta(blk, reinterpret_cast<int*>(stage_smem), a.ind, a.flag, a.mask_idx, a.N, a.M, a.route_ptr, a.route_q, a.ms,
@@ -222,6 +224,8 @@ blend_scan_kernel(const float* __restrict__ staged, int C, int Mmax,
                   const int* __restrict__ mcount) {
   extern __shared__ __align__(128) uint8_t scan_smem[];
   __shared__ __align__(8) unsigned long long bars[4];      // full[2], free[2]
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float zs[T], wn_s[T], wo_s[T];
   const int blk_floats = 2 * T * C + T * T + T;
   const uint32_t blk_bytes = (uint32_t)blk_floats * sizeof(float);
@@ -566,6 +570,8 @@ __global__ void __launch_bounds__(512)
 paste_kernel(const float* __restrict__ x, const float* __restrict__ y, const int* __restrict__ ind,
              const int* __restrict__ rank, int C, int N, int M, int CT, int tiles_per_cta, float* __restrict__ out, int ms) {
   extern __shared__ __align__(128) float rows[];         // [2][CT][N] + ind[N] + rank[N]
+  pdl_trigger();
+  pdl_wait();
   paste_cta(blockIdx.x, blockIdx.y, tiles_per_cta, rows, x, y, ind, rank, C, N, M, CT, out, ms);
 }
 
@@ -575,6 +581,8 @@ paste_loss_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
                   const int* __restrict__ rank, int C, int N, int M, int CT, int tiles_per_cta, float* __restrict__ out, int ms,
                   const PasteLoss cos, long long loss_count) {
   extern __shared__ __align__(128) float rows[];
+  pdl_trigger();
+  pdl_wait();
   paste_cta(blockIdx.x, blockIdx.y, tiles_per_cta, rows, x, y, ind, rank, C, N, M, CT, out, ms, &cos,
             (int)(blockIdx.y * gridDim.x + blockIdx.x), (int)(gridDim.x * gridDim.y), loss_count);
 }
@@ -651,7 +659,10 @@ static int launch_stage(StageArgs a, cudaStream_t st) {
   a.nblocks = (a.M + T - 1) / T;
   const long long ctas = (long long)a.n_routes + (long long)a.nblocks * a.B;
   IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_blend_stage: grid too large");
-  blend_stage_kernel<T><<<(unsigned)ctas, 256, smem, st>>>(a);
+  {
+    cudaError_t le__ = launch_pdl(blend_stage_kernel<T>, dim3((unsigned)ctas), dim3(256), smem, st, a);
+    IPSR_REQUIRE(le__ == cudaSuccess, IPSR_ERR_CUDA, "ipsr_blend_stage: launch failed: %s", cudaGetErrorString(le__));
+  }
   return check_launch("ipsr_blend_stage");
 }
 
@@ -673,7 +684,10 @@ static int launch_scan(const float* staged, int B, int C, int M, float* y, float
     cudaError_t e = cudaFuncSetAttribute(blend_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "blend_scan smem attribute: %s", cudaGetErrorString(e));
   }
-  blend_scan_kernel<T><<<B, kScanThreads, smem, st>>>(staged, C, M, y, wn, wo, mcount);
+  {
+    cudaError_t le__ = launch_pdl(blend_scan_kernel<T>, dim3(B), dim3(kScanThreads), smem, st, staged, C, M, y, wn, wo, mcount);
+    IPSR_REQUIRE(le__ == cudaSuccess, IPSR_ERR_CUDA, "ipsr_blend_scan: launch failed: %s", cudaGetErrorString(le__));
+  }
   return check_launch("ipsr_blend_scan");
 }
 }  // namespace ipsr
@@ -771,11 +785,14 @@ int ipsr::paste_ex(const float* x, const float* y, const int32_t* ind, const int
       cudaError_t e = cudaFuncSetAttribute(paste_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "paste smem attribute: %s", cudaGetErrorString(e));
     }
-    paste_loss_kernel<<<dim3((ntiles + tpc - 1) / tpc, B), threads, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, tpc, out, ms,
-                                                                                             *loss, (long long)B * C * N);
+    cudaError_t le = launch_pdl(paste_loss_kernel, dim3((ntiles + tpc - 1) / tpc, B), dim3(threads), smem, as_stream(stream), x, y, ind, rank,
+                                C, N, M, CT, tpc, out, ms, *loss, (long long)B * C * N);
+    IPSR_REQUIRE(le == cudaSuccess, IPSR_ERR_CUDA, "ipsr_paste: launch failed: %s", cudaGetErrorString(le));
     return check_launch("ipsr_paste");
   }
-  paste_kernel<<<dim3((ntiles + tpc - 1) / tpc, B), threads, smem, as_stream(stream)>>>(x, y, ind, rank, C, N, M, CT, tpc, out, ms);
+  cudaError_t le = launch_pdl(paste_kernel, dim3((ntiles + tpc - 1) / tpc, B), dim3(threads), smem, as_stream(stream), x, y, ind, rank, C, N,
+                              M, CT, tpc, out, ms);
+  IPSR_REQUIRE(le == cudaSuccess, IPSR_ERR_CUDA, "ipsr_paste: launch failed: %s", cudaGetErrorString(le));
   return check_launch("ipsr_paste");
 }
 

@@ -81,6 +81,8 @@ shift_bwd_kernel(const float* __restrict__ g, int C, int N, int M, int tiles_per
   __shared__ float hdelta[2][kBwdHubInplace][CT];            // hub sums of the tile in flight (parity of the tile)
   __shared__ int nheavy, nspec_s, inplace_s;
   __shared__ __align__(8) unsigned long long full_bar[4], done_bar[4];   // S <= 4 stages
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   // per-image masks: mask_idx is [B][ms], mcount[b] steps; M stays the row stride of wn / wo
   const int Mc = mcount ? mcount[b] : M;
@@ -508,10 +510,10 @@ extern "C" int ipsr_shift_bwd_masks(const float* g, int B, int C, int N, int M,
   // IPSR_BWD_QUEUE (tests; read per call): a smaller hub queue, so that a modest case exercises its overflow
   int qcap = kBwdQueue;
   if (const char* e = getenv("IPSR_BWD_QUEUE")) qcap = std::max(1, std::min(kBwdQueue, atoi(e)));
-  kern<<<dim3(parts, B), threads, smem, as_stream(stream)>>>(g, C, N, M, tiles_per_cta, route_ptr, route_q, exc_start, exc_cnt,
-                                                            exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn, wo, triple_w,
-                                                            gin, ninfo, nexc_s, mask_stride, m_count, S,
-                                                            []{ const char* e = getenv("IPSR_BWD_LIGHT"); return e ? atoi(e) : kBwdLight; }(),
-                                                            qcap);
+  static const int light = [] { const char* e = getenv("IPSR_BWD_LIGHT"); return e ? atoi(e) : kBwdLight; }();
+  cudaError_t le = launch_pdl(kern, dim3(parts, B), dim3(threads), smem, as_stream(stream), g, C, N, M, tiles_per_cta, route_ptr, route_q,
+                              exc_start, exc_cnt, exc_l, exc_w, exc_total, exc_cap, ind, mask_idx, wn, wo, triple_w, gin, ninfo, nexc_s,
+                              mask_stride, m_count, S, light, qcap);
+  IPSR_REQUIRE(le == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_bwd: launch failed: %s", cudaGetErrorString(le));
   return check_launch("ipsr_shift_bwd");
 }

@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(256)
 corr_fp32_sparse_kernel(const float* __restrict__ x, const float* __restrict__ ref, const float* __restrict__ inv_norm,
                         int C, int N, int col_begin, int col_end,
                         const int* __restrict__ list, const int* __restrict__ nlist, long long* __restrict__ packed) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sk_smem[];
   float* Rs = sk_smem;                                   // [C][8]
   float* red = sk_smem + (size_t)C * kSkRows;            // [4][64][8]
@@ -223,8 +225,15 @@ __global__ void __launch_bounds__(256)
 resolve_kernel(const long long* __restrict__ packed, const int* __restrict__ list, const int* __restrict__ nlist,
                const int* __restrict__ pair_list, const int* __restrict__ npair, const int* __restrict__ cand2,
                const float* __restrict__ xt, const float* __restrict__ ref, const float* __restrict__ inv_norm,
-               int C, int N, int* __restrict__ ind, float* __restrict__ vmax) {
+               int C, int N, int* __restrict__ ind, float* __restrict__ vmax, const int* __restrict__ npass2,
+               int* __restrict__ nrecheck_out, int* __restrict__ npass2_out) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {               // the counters the caller keeps (diagnostics): no copy nodes
+    if (nrecheck_out) nrecheck_out[b] = nlist[b];
+    if (npass2_out && npass2) npass2_out[b] = npass2[b];
+  }
   const int nl = min(nlist[b], N);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) {
     const int q = list[(size_t)b * N + i];
@@ -340,8 +349,11 @@ extern "C" int ipsr_correlate_argmax_fp32(const float* x, const float* ref, cons
       IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_fp32_sparse smem attribute: %s", cudaGetErrorString(e));
     }
     dim3 grid((col_end - col_begin + kSkCols - 1) / kSkCols, B);
-    corr_fp32_sparse_kernel<<<grid, 256, smem, as_stream(stream)>>>(x, ref, inv_norm, C, N, col_begin, col_end, recheck_list,
-                                                                     nrecheck, reinterpret_cast<long long*>(packed));
+    {
+      cudaError_t le__ = launch_pdl(corr_fp32_sparse_kernel, grid, dim3(256), smem, as_stream(stream), x, ref, inv_norm, C, N, col_begin,
+                                    col_end, recheck_list, nrecheck, reinterpret_cast<long long*>(packed));
+      IPSR_REQUIRE(le__ == cudaSuccess, IPSR_ERR_CUDA, "ipsr_correlate_argmax_fp32: launch failed: %s", cudaGetErrorString(le__));
+    }
     return check_launch("ipsr_correlate_argmax_fp32");
   }
   const int max_ctas = (N + kFpTile - 1) / kFpTile;
@@ -367,6 +379,14 @@ extern "C" int ipsr_resolve_rows(const int64_t* packed, const int32_t* recheck_l
                                  const int32_t* pair_list, const int32_t* npair, const int32_t* cand2,
                                  const float* xt, const float* ref, const float* inv_norm,
                                  int B, int C, int N, int32_t* ind, float* vmax, void* stream) {
+  return ipsr::resolve_rows_ex(packed, recheck_list, nrecheck, pair_list, npair, cand2, xt, ref, inv_norm, B, C, N, ind, vmax, nullptr,
+                               nullptr, nullptr, stream);
+}
+
+int ipsr::resolve_rows_ex(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck, const int32_t* pair_list,
+                          const int32_t* npair, const int32_t* cand2, const float* xt, const float* ref, const float* inv_norm,
+                          int B, int C, int N, int32_t* ind, float* vmax, const int32_t* npass2, int32_t* nrecheck_out,
+                          int32_t* npass2_out, void* stream) {
   using namespace ipsr;
   IPSR_REQUIRE(packed && recheck_list && nrecheck && ind && B > 0 && N > 0 && C > 0 && B <= 65535, IPSR_ERR_INVALID_ARG,
                "ipsr_resolve_rows: bad arguments");
@@ -374,8 +394,12 @@ extern "C" int ipsr_resolve_rows(const int64_t* packed, const int32_t* recheck_l
                "ipsr_resolve_rows: the pair list needs npair, cand2, xt, ref and inv_norm");
   int G = (N + 255) / 256;
   if (G > 8) G = 8;
-  resolve_kernel<<<dim3(G, B), 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(packed), recheck_list, nrecheck,
-                                                            pair_list, npair, cand2, xt, ref, inv_norm, C, N, ind, vmax);
+  {
+    cudaError_t le__ = launch_pdl(resolve_kernel, dim3(G, B), dim3(256), 0, as_stream(stream), reinterpret_cast<const long long*>(packed),
+                                  recheck_list, nrecheck, pair_list, npair, cand2, xt, ref, inv_norm, C, N, ind, vmax, npass2, nrecheck_out,
+                                  npass2_out);
+    IPSR_REQUIRE(le__ == cudaSuccess, IPSR_ERR_CUDA, "ipsr_resolve_rows: launch failed: %s", cudaGetErrorString(le__));
+  }
   return check_launch("ipsr_resolve_rows");
 }
 

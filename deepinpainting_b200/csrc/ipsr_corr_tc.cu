@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
   constexpr uint32_t kStageBytes = (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes) + (uint32_t)AH * kTileBytes * kBT;
   constexpr int kEpiWarps = 4 * ROWT;
   constexpr uint32_t kTmemCols = (uint32_t)ROWT * 2u * kBlockN;
+  pdl_trigger();
+  pdl_wait();                                                  // (row_limit below is the previous kernel's output)
   const int KB = prm.KB, RB = prm.RB;
   const uint32_t a_bytes = A_RESIDENT ? (uint32_t)ROWT * KB * AH * kTileBytes : 0u;
   const uint32_t a_base = base;
@@ -363,6 +365,8 @@ __global__ void finalize_kernel(const float* __restrict__ part_best, const int* 
                                 const uint8_t* __restrict__ r_tiles, uint8_t* __restrict__ c_tiles, int KB,
                                 const int* __restrict__ part_idx2, const float* __restrict__ part_third,
                                 int* __restrict__ cand2, int* __restrict__ pair_list, int* __restrict__ npair, int n_valid) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = r < n_valid;                                // rows >= n_valid are padding of the tile image
@@ -479,13 +483,15 @@ static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
   cfg.blockDim = dim3(96 + 128 * ROWT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, prm);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_correlate_argmax_tc: launch failed: %s", cudaGetErrorString(e));
   return check_launch("ipsr_correlate_argmax_tc");
@@ -637,9 +643,13 @@ extern "C" int ipsr_finalize_argmax_valid(const float* part_best, const int32_t*
   if (part_idx2)
     IPSR_REQUIRE(part_third && cand2 && pair_list && npair, IPSR_ERR_INVALID_ARG,
                  "ipsr_finalize_argmax: the pair list needs part_third, cand2, pair_list and npair");
-  finalize_kernel<<<dim3((N + 255) / 256, B), 256, 0, as_stream(stream)>>>(
-      part_best, part_idx, part_second, psplit, rnorm, rscale, rerr, xerr_max, nonfinite, list_in, nlist_in, B, N, tol_rel,
-      tol_abs, ind, list_out, nlist_out, reinterpret_cast<long long*>(packed), reinterpret_cast<const uint8_t*>(r_tiles),
-      reinterpret_cast<uint8_t*>(c_tiles), c_tiles ? C / kTileK : 0, part_idx2, part_third, cand2, pair_list, npair, n_valid);
+  {
+    cudaError_t le__ = launch_pdl(finalize_kernel, dim3((N + 255) / 256, B), dim3(256), 0, as_stream(stream), part_best, part_idx, part_second,
+                                  psplit, rnorm, rscale, rerr, xerr_max, nonfinite, list_in, nlist_in, B, N, tol_rel, tol_abs, ind, list_out,
+                                  nlist_out, reinterpret_cast<long long*>(packed), reinterpret_cast<const uint8_t*>(r_tiles),
+                                  reinterpret_cast<uint8_t*>(c_tiles), c_tiles ? C / kTileK : 0, part_idx2, part_third, cand2, pair_list,
+                                  npair, n_valid);
+    IPSR_REQUIRE(le__ == cudaSuccess, IPSR_ERR_CUDA, "ipsr_finalize_argmax: launch failed: %s", cudaGetErrorString(le__));
+  }
   return check_launch("ipsr_finalize_argmax");
 }

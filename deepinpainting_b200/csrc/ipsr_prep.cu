@@ -69,6 +69,8 @@ prep_kernel(const float* __restrict__ x, const float* __restrict__ ref, int C, i
             int* __restrict__ nonfinite, float* __restrict__ rscale, float* __restrict__ rerr,
             float* __restrict__ xerr, int* __restrict__ xerr_max, int ms) {
   extern __shared__ float smem[];
+  pdl_trigger();
+  pdl_wait();
   float* tile = smem;                      // [C][33]
   float* part = smem + (size_t)C * 33;     // [8][32] sums of squares, then [8][32] maxima
   float* scale = part + 2 * 8 * 32;        // [32]
@@ -259,10 +261,12 @@ int ipsr::extract_normalize_ex(const float* x, const float* ref, int B, int C, i
     IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "prep smem attribute: %s", cudaGetErrorString(e));
   }
   dim3 grid((N + kPrepPos - 1) / kPrepPos, B, 2);
-  prep_kernel<<<grid, kPrepThreads, smem, as_stream(stream)>>>(
-      x, ref, C, N, rank_i32, M, inv_norm, rnorm, xt, (M > 0 ? r_masked : nullptr),
-      reinterpret_cast<uint8_t*>(x_tiles), reinterpret_cast<uint8_t*>(r_tiles), nonfinite, rscale, rerr, xerr,
-      reinterpret_cast<int*>(xerr_max), ms);
+  {
+    cudaError_t le__ = launch_pdl(prep_kernel, grid, dim3(kPrepThreads), smem, as_stream(stream), x, ref, C, N, rank_i32, M, inv_norm, rnorm, xt,
+                                  (M > 0 ? r_masked : nullptr), reinterpret_cast<uint8_t*>(x_tiles), reinterpret_cast<uint8_t*>(r_tiles),
+                                  nonfinite, rscale, rerr, xerr, reinterpret_cast<int*>(xerr_max), ms);
+    IPSR_REQUIRE(le__ == cudaSuccess, IPSR_ERR_CUDA, "ipsr_extract_normalize: launch failed: %s", cudaGetErrorString(le__));
+  }
   return check_launch("ipsr_extract_normalize");
 }
 
