@@ -49,7 +49,7 @@ constexpr float kDefaultTolAbs = 1e-12f;
 
 struct Workspace {
   size_t total = 0;
-  size_t inv_norm, rnorm, counters /* nonfinite[B] + nrecheck[B] + npass2[B] + xerr_max[B] + npair[B] */, xt, r_masked, staged, vmask, y,
+  size_t inv_norm, rnorm, counters /* nonfinite[B] + nrecheck[B] + npass2[B] + xerr_max[B] + npair[B] + done[B] */, xt, r_masked, staged, vmask, y,
       packed, list;
   size_t x_tiles, r_tiles, c_tiles, rscale, rerr, list2, part_best, part_idx, part_second, part_idx2, part_third, cand2, pair_list;
   bool tensor = false;
@@ -72,7 +72,7 @@ static Workspace carve(int B, int C, int N, int M, int mode) {
   const size_t BN = (size_t)B * N, BM = (size_t)B * (M > 0 ? M : 1);
   w.inv_norm = take(cur, BN * 4);
   w.rnorm = take(cur, BN * 4);
-  w.counters = take(cur, (size_t)5 * B * 4);
+  w.counters = take(cur, (size_t)6 * B * 4);
   w.xt = take(cur, BN * C * 4);
   w.r_masked = take(cur, BM * C * 4);
   w.staged = take(cur, (size_t)B * (size_t)((M + ipsr_scan_block_steps(C) - 1) / ipsr_scan_block_steps(C) + 1) *
@@ -280,7 +280,7 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
   int32_t* list = at<int32_t>(a, w.list);
   int64_t* packed = at<int64_t>(a, w.packed);
 
-  cudaError_t e = cudaMemsetAsync(nonfinite, 0, (size_t)5 * B * sizeof(int32_t), st);
+  cudaError_t e = cudaMemsetAsync(nonfinite, 0, (size_t)6 * B * sizeof(int32_t), st);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_shift_forward: memset: %s", cudaGetErrorString(e));
   if (a->need_grad && M > 1) {
     e = cudaMemsetAsync(a->exc_total, 0, ((size_t)2 * B + 2) * sizeof(int32_t), st);
@@ -391,6 +391,13 @@ extern "C" int ipsr_shift_forward(const ipsr_fwd_args* a, void* stream) {
     }
   } else {
     IPSR_FORWARD(ipsr_select_all_rows(B, N, list, nrecheck, packed, stream));
+  }
+  if (tensor && cb == 0 && ce == N && !a->stop_after_corr) {
+    // whole bank: the exact recheck of the listed rows and the pair / key resolution in ONE launch
+    IPSR_FORWARD(recheck_resolve_ex(a->x, a->ref, at<float>(a, w.inv_norm), at<float>(a, w.xt), B, C, N, list, nrecheck, packed,
+                                    at<int32_t>(a, w.pair_list), npair, at<int32_t>(a, w.cand2), a->ind, npair + B, npass2,
+                                    a->nrecheck_out, a->npass2_out, stream));
+    return run_blend_and_paste(a, w, stream);
   }
   if (!tensor) IPSR_FORWARD(record(a->ev_corr_begin));
   IPSR_FORWARD(ipsr_correlate_argmax_fp32(a->x, a->ref, at<float>(a, w.inv_norm), B, C, N, cb, ce, list, nrecheck,

@@ -70,6 +70,11 @@ int blend_stage_with_routes_ex(const float* xt, const float* r_masked, const flo
                                float* vmask, int32_t* route_ptr, int32_t* route_q, void* stream, int ms, const int32_t* mcount);
 int blend_scan_ex(const float* staged, int B, int C, int M, float* y, float* wn, float* wo, void* stream,
                   const int32_t* mcount);
+// ipsr_correlate_argmax_fp32 over the whole bank (sparse row lists) + ipsr_resolve_rows as ONE launch; done is [B], zero on entry
+int recheck_resolve_ex(const float* x, const float* ref, const float* inv_norm, const float* xt, int B, int C, int N,
+                       const int32_t* list, const int32_t* nlist, int64_t* packed, const int32_t* pair_list,
+                       const int32_t* npair, const int32_t* cand2, int32_t* ind, int32_t* done, const int32_t* npass2,
+                       int32_t* nrecheck_out, int32_t* npass2_out, void* stream);
 // ipsr_resolve_rows that also hands the per-image counters out (nrecheck_out / npass2_out, optional)
 int resolve_rows_ex(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck, const int32_t* pair_list,
                     const int32_t* npair, const int32_t* cand2, const float* xt, const float* ref, const float* inv_norm,

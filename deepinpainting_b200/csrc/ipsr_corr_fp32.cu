@@ -117,21 +117,15 @@ corr_fp32_kernel(const float* __restrict__ x, const float* __restrict__ ref, con
 constexpr int kSkCols = 64;
 constexpr int kSkRows = 8;
 
-__global__ void __launch_bounds__(256)
-corr_fp32_sparse_kernel(const float* __restrict__ x, const float* __restrict__ ref, const float* __restrict__ inv_norm,
-                        int C, int N, int col_begin, int col_end,
-                        const int* __restrict__ list, const int* __restrict__ nlist, long long* __restrict__ packed) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(16) float sk_smem[];
+// one CTA: the listed rows of image b against bank columns [col_begin + tile * 64, + 64)
+__device__ __forceinline__ void
+sparse_cta(float* sk_smem, int* rows, int tile, int b, int nrows, const float* __restrict__ x, const float* __restrict__ ref,
+           const float* __restrict__ inv_norm, int C, int N, int col_begin, int col_end, const int* __restrict__ list,
+           long long* __restrict__ packed) {
   float* Rs = sk_smem;                                   // [C][8]
   float* red = sk_smem + (size_t)C * kSkRows;            // [4][64][8]
-  __shared__ int rows[kSkRows];
-  const int b = blockIdx.y;
-  const int nrows = min(nlist[b], N);
-  if (nrows == 0) return;
   const int j = threadIdx.x & 63, kg = threadIdx.x >> 6;
-  const int p = col_begin + blockIdx.x * kSkCols + j;
+  const int p = col_begin + tile * kSkCols + j;
   const bool pok = p < col_end;
   const float* xb = x + (size_t)b * C * N;
   const float* rb = ref + (size_t)b * C * N;
@@ -192,6 +186,20 @@ corr_fp32_sparse_kernel(const float* __restrict__ x, const float* __restrict__ r
   }
 }
 
+__global__ void __launch_bounds__(256)
+corr_fp32_sparse_kernel(const float* __restrict__ x, const float* __restrict__ ref, const float* __restrict__ inv_norm,
+                        int C, int N, int col_begin, int col_end,
+                        const int* __restrict__ list, const int* __restrict__ nlist, long long* __restrict__ packed) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float sk_smem[];
+  __shared__ int rows[kSkRows];
+  const int b = blockIdx.y;
+  const int nrows = min(nlist[b], N);
+  if (nrows == 0) return;
+  sparse_cta(sk_smem, rows, blockIdx.x, b, nrows, x, ref, inv_norm, C, N, col_begin, col_end, list, packed);
+}
+
 __global__ void select_all_kernel(int N, int* __restrict__ list, int* __restrict__ nlist, long long* __restrict__ packed) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,6 +222,37 @@ __global__ void apply_recheck_kernel(const long long* __restrict__ packed, const
   ind[(size_t)b * N + q] = idx;
   if (vmax) vmax[(size_t)b * N + q] = v;
 }
+
+// rows of `pair_list` (exactly two candidates inside the error band): one warp per row computes both exact fp32 scores
+__device__ __forceinline__ void
+resolve_pairs_cta(int part, int nparts, int b, const int* __restrict__ pair_list, const int* __restrict__ npair,
+                  const int* __restrict__ cand2, const float* __restrict__ xt, const float* __restrict__ ref,
+                  const float* __restrict__ inv_norm, int C, int N, int* __restrict__ ind, float* __restrict__ vmax) {
+  const int np = min(npair[b], N);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = part * 8 + warp; j < np; j += nparts * 8) {
+    const int q = pair_list[(size_t)b * N + j];
+    const int p1 = ind[(size_t)b * N + q], p2 = cand2[(size_t)b * N + q];
+    const float i1 = inv_norm[(size_t)b * N + p1], i2 = inv_norm[(size_t)b * N + p2];
+    const float* x1 = xt + ((size_t)b * N + p1) * C;
+    const float* x2 = xt + ((size_t)b * N + p2) * C;
+    const float* rr = ref + (size_t)b * C * N + q;
+    float a1 = 0.f, a2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float r = __ldg(rr + (size_t)c * N);
+      a1 = fmaf(r, __fmul_rn(__ldg(x1 + c), i1), a1);      // Xn = fl(X * inv_norm)   (NPS:40)
+      a2 = fmaf(r, __fmul_rn(__ldg(x2 + c), i2), a2);
+    }
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if (lane == 0) {
+      const bool second_wins = (a2 > a1) || (a2 == a1 && p2 < p1);
+      ind[(size_t)b * N + q] = second_wins ? p2 : p1;
+      if (vmax) vmax[(size_t)b * N + q] = second_wins ? a2 : a1;
+    }
+  }
+}
+
 
 // Settles what the tensor passes left open, in one launch:
 //   (1) rows of `list` (recomputed in exact fp32 by ipsr_correlate_argmax_fp32): ind[b,q] <- packed[b,q];
@@ -244,28 +283,50 @@ resolve_kernel(const long long* __restrict__ packed, const int* __restrict__ lis
     if (vmax) vmax[(size_t)b * N + q] = v;
   }
   if (!pair_list) return;
-  const int np = min(npair[b], N);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = blockIdx.x * 8 + warp; j < np; j += gridDim.x * 8) {
-    const int q = pair_list[(size_t)b * N + j];
-    const int p1 = ind[(size_t)b * N + q], p2 = cand2[(size_t)b * N + q];
-    const float i1 = inv_norm[(size_t)b * N + p1], i2 = inv_norm[(size_t)b * N + p2];
-    const float* x1 = xt + ((size_t)b * N + p1) * C;
-    const float* x2 = xt + ((size_t)b * N + p2) * C;
-    const float* rr = ref + (size_t)b * C * N + q;
-    float a1 = 0.f, a2 = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float r = __ldg(rr + (size_t)c * N);
-      a1 = fmaf(r, __fmul_rn(__ldg(x1 + c), i1), a1);      // Xn = fl(X * inv_norm)   (NPS:40)
-      a2 = fmaf(r, __fmul_rn(__ldg(x2 + c), i2), a2);
+  resolve_pairs_cta(blockIdx.x, gridDim.x, b, pair_list, npair, cand2, xt, ref, inv_norm, C, N, ind, vmax);
+}
+
+// The exact fp32 recheck of the listed rows over the WHOLE bank and everything resolve_kernel does, as one launch
+// (ipsr_shift_forward, tensor mode): grid = (N / 64 column tiles + gpairs, B).  The pair CTAs need nothing from the
+// recheck; the listed rows take their keys from the image's LAST column tile to finish (ticket in done[b], zero on entry).
+__global__ void __launch_bounds__(256)
+recheck_resolve_kernel(const float* __restrict__ x, const float* __restrict__ ref, const float* __restrict__ inv_norm,
+                       const float* __restrict__ xt, int C, int N, const int* __restrict__ list, const int* __restrict__ nlist,
+                       long long* __restrict__ packed, const int* __restrict__ pair_list, const int* __restrict__ npair,
+                       const int* __restrict__ cand2, int* __restrict__ ind, int* __restrict__ done,
+                       const int* __restrict__ npass2, int* __restrict__ nrecheck_out, int* __restrict__ npass2_out,
+                       int ntiles, int gpairs) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float sk_smem[];
+  __shared__ int rows[kSkRows];
+  __shared__ int last;
+  const int b = blockIdx.y;
+  if ((int)blockIdx.x >= ntiles) {
+    if ((int)blockIdx.x == ntiles && threadIdx.x == 0) {
+      if (nrecheck_out) nrecheck_out[b] = nlist[b];
+      if (npass2_out && npass2) npass2_out[b] = npass2[b];
     }
-    a1 = warp_sum(a1);
-    a2 = warp_sum(a2);
-    if (lane == 0) {
-      const bool second_wins = (a2 > a1) || (a2 == a1 && p2 < p1);
-      ind[(size_t)b * N + q] = second_wins ? p2 : p1;
-      if (vmax) vmax[(size_t)b * N + q] = second_wins ? a2 : a1;
-    }
+    resolve_pairs_cta((int)blockIdx.x - ntiles, gpairs, b, pair_list, npair, cand2, xt, ref, inv_norm, C, N, ind, nullptr);
+    return;
+  }
+  const int nrows = min(nlist[b], N);
+  if (nrows == 0) return;
+  sparse_cta(sk_smem, rows, blockIdx.x, b, nrows, x, ref, inv_norm, C, N, 0, N, list, packed);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                                       // this CTA's keys before its ticket
+    last = (atomicAdd(done + b, 1) == ntiles - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+    const int q = list[(size_t)b * N + i];
+    float v;
+    int idx;
+    unpack_maxidx(__ldcg(packed + (size_t)b * N + q), &v, &idx);
+    ind[(size_t)b * N + q] = idx;
   }
 }
 
@@ -363,6 +424,28 @@ extern "C" int ipsr_correlate_argmax_fp32(const float* x, const float* ref, cons
                                                                 recheck_list, nrecheck,
                                                                 reinterpret_cast<long long*>(packed));
   return check_launch("ipsr_correlate_argmax_fp32");
+}
+
+int ipsr::recheck_resolve_ex(const float* x, const float* ref, const float* inv_norm, const float* xt, int B, int C, int N,
+                             const int32_t* list, const int32_t* nlist, int64_t* packed, const int32_t* pair_list,
+                             const int32_t* npair, const int32_t* cand2, int32_t* ind, int32_t* done, const int32_t* npass2,
+                             int32_t* nrecheck_out, int32_t* npass2_out, void* stream) {
+  using namespace ipsr;
+  IPSR_REQUIRE(x && ref && inv_norm && xt && list && nlist && packed && pair_list && npair && cand2 && ind && done,
+               IPSR_ERR_INVALID_ARG, "recheck_resolve: null pointer");
+  IPSR_REQUIRE(B > 0 && B <= 65535 && C > 0 && N > 0, IPSR_ERR_INVALID_ARG, "recheck_resolve: bad dims");
+  const size_t smem = ((size_t)C * kSkRows + 4 * (size_t)kSkCols * kSkRows) * sizeof(float);
+  IPSR_REQUIRE(smem <= 227 * 1024, IPSR_ERR_UNSUPPORTED, "recheck_resolve: C=%d too large", C);
+  if (smem + 2048 > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(recheck_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "recheck_resolve smem attribute: %s", cudaGetErrorString(e));
+  }
+  const int ntiles = (N + kSkCols - 1) / kSkCols, gpairs = 4;
+  cudaError_t le = launch_pdl(recheck_resolve_kernel, dim3(ntiles + gpairs, B), dim3(256), smem, as_stream(stream), x, ref, inv_norm, xt, C, N,
+                              list, nlist, reinterpret_cast<long long*>(packed), pair_list, npair, cand2, ind, done, npass2, nrecheck_out,
+                              npass2_out, ntiles, gpairs);
+  IPSR_REQUIRE(le == cudaSuccess, IPSR_ERR_CUDA, "recheck_resolve: launch failed: %s", cudaGetErrorString(le));
+  return check_launch("recheck_resolve");
 }
 
 extern "C" int ipsr_apply_recheck(const int64_t* packed, const int32_t* recheck_list, const int32_t* nrecheck,

@@ -582,8 +582,10 @@ int ipsr::correlate_argmax_tc_ex(const void* r_tiles, const void* x_tiles, int B
   if (passes == 3) {
     const long long ctas = (long long)B * prm.RB * psplit;
     IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
-    const bool pairs = (prm.RB % 2 == 0) && s_dump == nullptr;
-    return a_res ? launch_tc_cl<1, 3, true>(prm, C, ctas, pairs, st) : launch_tc_cl<1, 3, false>(prm, C, ctas, pairs, st);
+    static const int env_pairs = [] { const char* e = getenv("IPSR_TC_PAIRS"); return e ? atoi(e) : 1; }();     // A/B runs
+    static const int env_ares = [] { const char* e = getenv("IPSR_TC_ARES"); return e ? atoi(e) : 1; }();
+    const bool pairs = (prm.RB % 2 == 0) && s_dump == nullptr && env_pairs != 0;
+    return (a_res && env_ares) ? launch_tc_cl<1, 3, true>(prm, C, ctas, pairs, st) : launch_tc_cl<1, 3, false>(prm, C, ctas, pairs, st);
   }
   // two row tiles per CTA when the grid still fills most of the machine and both fit next to >= 4 ring stages
   const bool two = a_res && (prm.RB % 2 == 0) && (2 * a_one + 4 * (size_t)kTileBytes + 2048 <= 227 * 1024) &&

@@ -468,7 +468,7 @@ def launches_per_step(C: int, N: int, M: int, need_grad: bool = True, mode: Opti
         n += 1 if ps == 1 else 2
     else:
         n += 4 if tensor else 1               # (correlate_tc + finalize) x 2 with the cascade | select_all_rows
-    n += 2                                  # correlate_fp32 + resolve_rows
+    n += 1 if tensor else 2                 # whole bank, tensor mode: recheck + resolve in one launch | correlate_fp32 + resolve_rows
     if M > 0:
         n += 2                              # blend_stage (+ routes builders in the same launch) + blend_scan
     elif need_grad:
