@@ -59,8 +59,13 @@ struct TcParams {
 // MMAs of BOTH CTAs have retired it (multicast commits onto both empty barriers).
 // BN: bank columns per accumulator block = N of the tcgen05.mma instruction (128, or 256 with ROWT = 1 and one pass: two
 // adjacent bank tiles per stage, one 128 x 256 x 16 instruction instead of two 128 x 128 x 16 ones).
-template <int ROWT, int PASSES, bool A_RESIDENT, int CL, int BN = 128>
+// A_TMEM: the (resident) row tile lives in TENSOR memory instead of shared memory -- the epilogue warps copy their rows
+// there once (tcgen05.st), the MMAs take A from TMEM -- so that shared memory feeds the B operand only (a 128 x 128 x 16
+// instruction with both operands in shared memory reads 8 KB per 64 tensor cycles: all of the shared-memory bandwidth) and
+// the whole shared memory is ring.  Needs 2 BN + (C/64) * 32 * parts <= 512 TMEM columns.
+template <int ROWT, int PASSES, bool A_RESIDENT, int CL, int BN = 128, bool A_TMEM = false>
 __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcParams prm) {
+  static_assert(!A_TMEM || (A_RESIDENT && ROWT == 1), "the TMEM row tile replaces a resident one, one row tile per CTA");
   static_assert(BN == 128 || (BN == 256 && ROWT == 1 && PASSES == 1), "256-column blocks: one row tile, one pass");
   constexpr int kBlockN = BN;                                  // shadows the namespace constant inside this kernel
   constexpr int kBT = BN / 128;                                // bank tiles per block
@@ -76,11 +81,12 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
   constexpr int AH = (PASSES == 3) ? 2 : 1;                    // operand parts per 64-channel block (hi[, lo])
   constexpr uint32_t kStageBytes = (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes) + (uint32_t)AH * kTileBytes * kBT;
   constexpr int kEpiWarps = 4 * ROWT;
-  constexpr uint32_t kTmemCols = (uint32_t)ROWT * 2u * kBlockN;
+  constexpr uint32_t kTmemCols = A_TMEM ? 512u : (uint32_t)ROWT * 2u * kBlockN;
+  constexpr uint32_t kATmemCol0 = 2u * kBlockN;                // the row tile sits behind the two accumulators
   pdl_trigger();
   pdl_wait();                                                  // (row_limit below is the previous kernel's output)
   const int KB = prm.KB, RB = prm.RB;
-  const uint32_t a_bytes = A_RESIDENT ? (uint32_t)ROWT * KB * AH * kTileBytes : 0u;
+  const uint32_t a_bytes = (A_RESIDENT && !A_TMEM) ? (uint32_t)ROWT * KB * AH * kTileBytes : 0u;
   const uint32_t a_base = base;
   const uint32_t ring_base = base + a_bytes;
   const uint32_t bar_base = ring_base + (uint32_t)prm.stages * kStageBytes;
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), CL);             // one commit per CTA of the cluster
     }
-    mbar_init(a_full_bar, 1);
+    mbar_init(a_full_bar, A_TMEM ? 4 : 1);     // the four epilogue warps | the producer's expect_tx
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kEpiWarps);     // one arrive per epilogue warp
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
     const int pid = warp == 0 ? 0 : 1;
     const int nprod = prm.nprod;
     if (lane == 0 && nblk > 0 && pid < nprod) {
-      if (A_RESIDENT) {
+      if (A_RESIDENT && !A_TMEM) {
         if (pid == 0) mbar_expect_tx(a_full_bar, a_bytes);
         int idx = 0;
         for (int rt = 0; rt < ROWT; ++rt)
@@ -212,7 +218,25 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
             const uint32_t d_tmem = tmem_base + (uint32_t)((rt * 2 + as) * kBlockN);
             const uint32_t a_hi = A_RESIDENT ? a_base + (uint32_t)((rt * KB + kb) * AH) * kTileBytes : stage;
             const uint32_t a_lo = a_hi + kTileBytes;
-            if (PASSES == 3) {
+            if (A_TMEM) {
+              const uint32_t t_hi = tmem_base + kATmemCol0 + (uint32_t)kb * 32u, t_lo = t_hi + (uint32_t)KB * 32u;
+              const uint64_t dbh = umma_desc_k_sw128(b_hi), dbl = umma_desc_k_sw128(b_lo);
+              if (PASSES == 3) {
+                const uint32_t ta[3] = {t_hi, t_lo, t_hi};
+                const uint64_t db[3] = {dbl, dbh, dbh};
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                  for (int k = 0; k < kTileK / 16; ++k)
+                    umma_f16_ts(d_tmem, ta[pass] + (uint32_t)(8 * k), db[pass] + (uint64_t)(2 * k), idesc,
+                                (kb > 0 || pass > 0 || k > 0) ? 1u : 0u);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k)
+                  umma_f16_ts(d_tmem, t_hi + (uint32_t)(8 * k), dbh + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            } else if (PASSES == 3) {
               const uint64_t da[3] = {umma_desc_k_sw128(a_hi), umma_desc_k_sw128(a_lo), umma_desc_k_sw128(a_hi)};
               const uint64_t db[3] = {umma_desc_k_sw128(b_lo), umma_desc_k_sw128(b_hi), umma_desc_k_sw128(b_hi)};
               // small cross terms first, hi*hi last
@@ -244,6 +268,25 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
     const int q = (rbg * ROWT + rt) * kTileRows + row;   // (compact) row index
+    if (A_TMEM && nblk > 0) {
+      // this thread's row of the tile image (8 x 16-byte chunks per 64-channel block) -> its TMEM lane
+      const int nparts = (PASSES == 3) ? 2 : 1;
+      for (int hl = 0; hl < nparts; ++hl)
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint8_t* src = prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg, KB, RB, prm.a_parts);
+          uint32_t v[32];
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 qv = __ldg(reinterpret_cast<const uint4*>(src + tile_chunk_offset(row, ch)));
+            v[4 * ch + 0] = qv.x; v[4 * ch + 1] = qv.y; v[4 * ch + 2] = qv.z; v[4 * ch + 3] = qv.w;
+          }
+          tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + kATmemCol0 + (uint32_t)(hl * KB + kb) * 32u, v);
+        }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full_bar);
+    }
     float best = -INFINITY, second = -INFINITY, third = -INFINITY;
     int bidx = prm.col_begin + blk0 * kBlockN, sidx = bidx;
     const bool top3 = prm.part_idx2 != nullptr;
@@ -462,10 +505,10 @@ static int tc_stage_count(size_t a_bytes, size_t stage, size_t* smem_out) {
   return stages;
 }
 
-template <int ROWT, int PASSES, bool A_RES, int CL, int BN = 128>
+template <int ROWT, int PASSES, bool A_RES, int CL, int BN = 128, bool A_TMEM = false>
 static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
   constexpr int AH = (PASSES == 3) ? 2 : 1;
-  const size_t a_bytes = A_RES ? (size_t)ROWT * (C / kTileK) * AH * kTileBytes : 0;
+  const size_t a_bytes = (A_RES && !A_TMEM) ? (size_t)ROWT * (C / kTileK) * AH * kTileBytes : 0;
   const size_t stage = (A_RES ? 0 : (size_t)AH * kTileBytes) + (size_t)AH * kTileBytes * (BN / 128);
   size_t smem = 0;
   prm.stages = tc_stage_count(a_bytes, stage, &smem);
@@ -475,7 +518,7 @@ static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
   }();
   prm.nprod = producers;
   IPSR_REQUIRE(prm.stages >= 2, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: C=%d leaves %d pipeline stages", C, prm.stages);
-  auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL, BN>;
+  auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL, BN, A_TMEM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
   cudaLaunchConfig_t cfg = {};
@@ -582,6 +625,13 @@ int ipsr::correlate_argmax_tc_ex(const void* r_tiles, const void* x_tiles, int B
   if (passes == 3) {
     const long long ctas = (long long)B * prm.RB * psplit;
     IPSR_REQUIRE(ctas <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
+    // IPSR_TC_ATMEM=1 / IPSR_TC_ATMEM1=1 (A/B runs): the row tile in tensor memory.  Measured SLOWER on the B200: 37.0 us against
+    // 35.0 us for the three-pass launch at 32x32x256 (batch 16), 832 us against 609 us for the single pass at 64x64x256
+    // (batch 64; 128-column instructions instead of 256-column ones) -- the A operand's shared-memory reads are not what
+    // holds the tensor pipe back.
+    static const int env_atmem = [] { const char* e = getenv("IPSR_TC_ATMEM"); return e ? atoi(e) : 0; }();
+    if (env_atmem && s_dump == nullptr && 2 * 128 + (C / kTileK) * 32 * 2 <= 512)
+      return (prm.RB % 2 == 0) ? launch_tc<1, 3, true, 2, 128, true>(prm, C, ctas, st) : launch_tc<1, 3, true, 1, 128, true>(prm, C, ctas, st);
     static const int env_pairs = [] { const char* e = getenv("IPSR_TC_PAIRS"); return e ? atoi(e) : 1; }();     // A/B runs
     static const int env_ares = [] { const char* e = getenv("IPSR_TC_ARES"); return e ? atoi(e) : 1; }();
     const bool pairs = (prm.RB % 2 == 0) && s_dump == nullptr && env_pairs != 0;
@@ -599,6 +649,13 @@ int ipsr::correlate_argmax_tc_ex(const void* r_tiles, const void* x_tiles, int B
   // At C = 512 (128 KiB resident row tile, only 3 stages of 32 KiB): 440 us against 739 us at B = 32, 64 x 64 x 512 (0.90
   // against 0.54).  Taken when the resident row tile leaves >= 3 stages of 32 KiB (C <= 512), the splits stay whole
   // blocks and the grid fills the machine.  IPSR_TC_BN256=<n> in the environment sets the minimum ring depth (0 turns it off; A/B runs).
+  static const int env_atmem1 = [] { const char* e = getenv("IPSR_TC_ATMEM1"); return e ? atoi(e) : 0; }();       // A/B runs
+  if (env_atmem1 && s_dump == nullptr && 2 * 128 + (C / kTileK) * 32 <= 512) {
+    // single pass with the row tile in tensor memory: 128 x 128 x 16 instructions fed from shared memory with B only
+    const long long ctas1 = (long long)B * prm.RB * psplit;
+    IPSR_REQUIRE(ctas1 <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
+    return (prm.RB % 2 == 0) ? launch_tc<1, 1, true, 2, 128, true>(prm, C, ctas1, st) : launch_tc<1, 1, true, 1, 128, true>(prm, C, ctas1, st);
+  }
   if (s_dump == nullptr && tc_pass1_wide(B, C, N, col_begin, col_end, psplit)) {
     prm.blocks_total = (col_end - col_begin) / 256;
     const long long ctas1 = (long long)B * prm.RB * psplit;
