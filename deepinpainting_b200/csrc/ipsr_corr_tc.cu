@@ -63,8 +63,12 @@ struct TcParams {
 // there once (tcgen05.st), the MMAs take A from TMEM -- so that shared memory feeds the B operand only (a 128 x 128 x 16
 // instruction with both operands in shared memory reads 8 KB per 64 tensor cycles: all of the shared-memory bandwidth) and
 // the whole shared memory is ring.  Needs 2 BN + (C/64) * 32 * parts <= 512 TMEM columns.
-template <int ROWT, int PASSES, bool A_RESIDENT, int CL, int BN = 128, bool A_TMEM = false>
-__global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcParams prm) {
+// ES: epilogue warps per TMEM lane quadrant (1 or 2).  With 2, the two warps of a quadrant take the lower and the upper half
+// of every accumulator block's columns and the upper one hands its running (best, runner-up, third) to the lower one at
+// the end of the CTA: the compare chain per accumulator block halves.
+template <int ROWT, int PASSES, bool A_RESIDENT, int CL, int BN = 128, bool A_TMEM = false, int ES = 1>
+__global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const TcParams prm) {
+  static_assert(ES == 1 || ES == 2 || (ES == 4 && ROWT == 1), "one, two or (one row tile) four epilogue warps per lane quadrant");
   static_assert(!A_TMEM || (A_RESIDENT && ROWT == 1), "the TMEM row tile replaces a resident one, one row tile per CTA");
   static_assert(BN == 128 || (BN == 256 && ROWT == 1 && PASSES == 1), "256-column blocks: one row tile, one pass");
   constexpr int kBlockN = BN;                                  // shadows the namespace constant inside this kernel
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
 
   constexpr int AH = (PASSES == 3) ? 2 : 1;                    // operand parts per 64-channel block (hi[, lo])
   constexpr uint32_t kStageBytes = (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes) + (uint32_t)AH * kTileBytes * kBT;
-  constexpr int kEpiWarps = 4 * ROWT;
+  constexpr int kEpiWarps = 4 * ROWT * ES;
   constexpr uint32_t kTmemCols = A_TMEM ? 512u : (uint32_t)ROWT * 2u * kBlockN;
   constexpr uint32_t kATmemCol0 = 2u * kBlockN;                // the row tile sits behind the two accumulators
   pdl_trigger();
@@ -140,13 +144,13 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (CL == 2) cluster_sync_all();             // the peer's barriers exist before anything is sent to them
 
-  constexpr int kProducer2 = 2 + 4 * ROWT;                    // the second producer warp sits behind the epilogue warps
-  if (warp == 0 || warp == kProducer2) {
+  constexpr int kProducer2 = 2 + 4 * ROWT * ES;                  // the other producer warps (up to 3) sit behind the epilogue warps
+  if (warp == 0 || warp >= kProducer2) {
     // ------------------------------------------------------------------ producers
     // Measured (scripts/micro/bulk_bw.cu): a thread gets ONE bulk copy out per ~650 cycles whatever its size -- about the
     // time the tensor core needs for a whole stage -- while copies of different warps proceed side by side.  So the
     // stages alternate between two issuing warps.
-    const int pid = warp == 0 ? 0 : 1;
+    const int pid = warp == 0 ? 0 : warp - kProducer2 + 1;
     const int nprod = prm.nprod;
     if (lane == 0 && nblk > 0 && pid < nprod) {
       if (A_RESIDENT && !A_TMEM) {
@@ -264,11 +268,12 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
     }
   } else if (warp < kProducer2) {
     // ------------------------------------------------------------------ epilogue (thread == row)
-    const int rt = (warp - 2) >> 2;
+    const int rt = (warp - 2) / (4 * ES);
+    const int half = ((warp - 2) >> 2) % ES;             // which part of every block's columns this warp compares
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
     const int q = (rbg * ROWT + rt) * kTileRows + row;   // (compact) row index
-    if (A_TMEM && nblk > 0) {
+    if (A_TMEM && nblk > 0 && half == 0) {
       // this thread's row of the tile image (8 x 16-byte chunks per 64-channel block) -> its TMEM lane
       const int nparts = (PASSES == 3) ? 2 : 1;
       for (int hl = 0; hl < nparts; ++hl)
@@ -300,20 +305,21 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
       // the TMEM load of chunk ch+1 is in flight while chunk ch is compared; the accumulator is handed back to the MMA
       // warp as soon as its last chunk sits in registers
       uint32_t rbuf[2][32];
-      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((rt * 2 + as) * kBlockN);
+      constexpr int kChunks = kBlockN / 32 / ES;           // 32-column chunks of this warp
+      const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((rt * 2 + as) * kBlockN + half * kChunks * 32);
       tmem_ld32(tsrc, rbuf[0]);
 #pragma unroll
-      for (int ch = 0; ch < kBlockN / 32; ++ch) {
+      for (int ch = 0; ch < kChunks; ++ch) {
         uint32_t (&r)[32] = rbuf[ch & 1];
         tmem_ld_wait();
-        if (ch + 1 < kBlockN / 32) {
+        if (ch + 1 < kChunks) {
           tmem_ld32(tsrc + (uint32_t)((ch + 1) * 32), rbuf[(ch + 1) & 1]);
         } else {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
-        const int c0 = colb + ch * 32;
+        const int c0 = colb + (half * kChunks + ch) * 32;
         if (c0 + 32 > prm.n_valid) {                       // (warp-uniform) padding columns: -inf
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -351,7 +357,38 @@ __global__ void __launch_bounds__(96 + 128 * ROWT, 1) corr_tc_kernel(const TcPar
       }
 
     }
-    if (prm.fin.ind != nullptr) {
+    if (ES >= 2) {
+      // the other warps of the quadrant hand their states over (the ring is idle by now: every MMA that read it has completed)
+      float* mrg0 = reinterpret_cast<float*>(smem + (ring_base - base)) + (size_t)(rt * kTileRows + row) * 5;
+      constexpr size_t kMrgPart = (size_t)ROWT * kTileRows * 5;
+      if (half > 0) {
+        float* mrg = mrg0 + (size_t)(half - 1) * kMrgPart;
+        mrg[0] = best; mrg[1] = __int_as_float(bidx); mrg[2] = second; mrg[3] = __int_as_float(sidx); mrg[4] = third;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(128 * ROWT * ES) : "memory");
+      if (half == 0 && nblk > 0) {
+        // (value, column) pairs in descending value, ascending column order: equal values keep the lower column first
+        auto insert = [&](float v, int i) {
+          if (v > best || (v == best && i < bidx)) {
+            third = second; second = best; sidx = bidx; best = v; bidx = i;
+          } else if (v > second || (v == second && i < sidx)) {
+            third = second; second = v; sidx = i;
+          } else {
+            third = fmaxf(third, v);
+          }
+        };
+#pragma unroll
+        for (int h = 1; h < ES; ++h) {
+          const float* mrg = mrg0 + (size_t)(h - 1) * kMrgPart;
+          insert(mrg[0], __float_as_int(mrg[1]));
+          insert(mrg[2], top3 ? __float_as_int(mrg[3]) : 0x7FFFFFFF);
+          third = fmaxf(third, mrg[4]);
+        }
+      }
+    }
+    if (ES >= 2 && half > 0) {
+      // (the lower-half warp reports for the row)
+    } else if (prm.fin.ind != nullptr) {
       // the finalize decision inline (same arithmetic as finalize_kernel)
       const TcFinalize& f = prm.fin;
       const size_t bq = (size_t)b * prm.N + q;
@@ -492,38 +529,56 @@ __global__ void finalize_kernel(const float* __restrict__ part_best, const int* 
   }
 }
 
-static int tc_stage_count(size_t a_bytes, size_t stage, size_t* smem_out) {
-  const size_t fixed = a_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+static int tc_stage_count(size_t a_bytes, size_t stage, size_t* smem_out, int cap = 8) {
+  const size_t fixed = a_bytes + 1024 /*alignment slack*/ + 512 /*barriers*/;
   const size_t budget = 227 * 1024;
   if (fixed + 2 * stage > budget) {
     *smem_out = 0;
     return 0;
   }
   int stages = (int)((budget - fixed) / stage);
-  if (stages > 8) stages = 8;
+  if (stages > cap) stages = cap;
   *smem_out = fixed + (size_t)stages * stage;
   return stages;
 }
 
+template <int ROWT, int PASSES, bool A_RES, int CL, int BN, bool A_TMEM, int ES>
+static int launch_tc_es(TcParams prm, int C, long long ctas, cudaStream_t st);
+
 template <int ROWT, int PASSES, bool A_RES, int CL, int BN = 128, bool A_TMEM = false>
 static int launch_tc(TcParams prm, int C, long long ctas, cudaStream_t st) {
+  static const int epi = [] {                              // IPSR_TC_EPI=<1|2|4> (A/B runs): epilogue warps per lane quadrant
+    const char* e = getenv("IPSR_TC_EPI");
+    const int v = e ? atoi(e) : 2;
+    return (v == 1 || v == 4) ? v : 2;
+  }();
+  if constexpr (ROWT == 1) {
+    if (epi == 4) return launch_tc_es<ROWT, PASSES, A_RES, CL, BN, A_TMEM, 4>(prm, C, ctas, st);
+  }
+  return epi >= 2 ? launch_tc_es<ROWT, PASSES, A_RES, CL, BN, A_TMEM, 2>(prm, C, ctas, st)
+                  : launch_tc_es<ROWT, PASSES, A_RES, CL, BN, A_TMEM, 1>(prm, C, ctas, st);
+}
+
+template <int ROWT, int PASSES, bool A_RES, int CL, int BN, bool A_TMEM, int ES>
+static int launch_tc_es(TcParams prm, int C, long long ctas, cudaStream_t st) {
   constexpr int AH = (PASSES == 3) ? 2 : 1;
   const size_t a_bytes = (A_RES && !A_TMEM) ? (size_t)ROWT * (C / kTileK) * AH * kTileBytes : 0;
   const size_t stage = (A_RES ? 0 : (size_t)AH * kTileBytes) + (size_t)AH * kTileBytes * (BN / 128);
   size_t smem = 0;
-  prm.stages = tc_stage_count(a_bytes, stage, &smem);
-  static const int producers = [] {                        // IPSR_TC_PRODUCERS=1 (A/B runs): one issuing warp
+  prm.stages = tc_stage_count(a_bytes, stage, &smem, A_TMEM ? 13 : 8);
+  static const int producers = [] {                        // IPSR_TC_PRODUCERS=<1..4> (A/B runs): issuing warps
     const char* e = getenv("IPSR_TC_PRODUCERS");
-    return (e && atoi(e) == 1) ? 1 : 2;
+    const int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
   }();
   prm.nprod = producers;
   IPSR_REQUIRE(prm.stages >= 2, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: C=%d leaves %d pipeline stages", C, prm.stages);
-  auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL, BN, A_TMEM>;
+  auto kern = corr_tc_kernel<ROWT, PASSES, A_RES, CL, BN, A_TMEM, ES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)ctas);
-  cfg.blockDim = dim3(96 + 128 * ROWT);
+  cfg.blockDim = dim3(64 + 128 * ROWT * ES + 32 * (prm.nprod - 1));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

@@ -1,5 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -x -q > gpurun_out/r2_t22.log 2>&1; echo "pytest rc=$?"; tail -n 5 gpurun_out/r2_t22.log
-for v in "IPSR_TC_ATMEM=1" "IPSR_TC_ATMEM=0" "IPSR_TC_ATMEM=1 IPSR_TC_ATMEM1=1"; do
+for v in "IPSR_TC_EPI=2" "IPSR_TC_EPI=4" "IPSR_TC_EPI=2" "IPSR_TC_EPI=4"; do
 env $v timeout 300 python bench.py --steps 300 --e2e-steps 20 --no-cpu-baseline > gpurun_out/x.json 2> gpurun_out/x.err
 python - <<PY
 import json
@@ -8,3 +7,4 @@ a=d.get('also'); a=a[0] if isinstance(a,list) else a
 print('$v: A %.4f ms corr %.4f | B %.4f ms corr %.4f' % (d['ms_per_step'], d['roofline']['kernel_ms'], a['ms_per_step'], a['roofline']['kernel_ms']))
 PY
 done
+IPSR_TC_EPI=4 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -x -q > gpurun_out/r2_t24.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2_t24.log
