@@ -45,11 +45,13 @@ def _digest() -> str:
     h = hashlib.sha256()
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(INCLUDE, "ipsr_sm100.h"))
+    # names relative to the package and flags without the absolute include path: the snapshot that travels to a GPU box
+    # lives under another directory there, and must not look stale for that alone
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(a for a in NVCC_FLAGS if a != INCLUDE).encode())
     return h.hexdigest()
 
 
@@ -68,6 +70,21 @@ def is_current() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and is_current():
         return library_path()
+    # one builder at a time (the ranks of a torchrun / mp.spawn job may all find the library missing or stale at once); the
+    # others wait and then find it current
+    import fcntl
+    os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return library_path()
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJDIR, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
@@ -84,10 +101,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as pool:
         objs = list(pool.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-o", library_path(), *objs, "-lcudart"]
+    tmp = library_path() + ".tmp.%d" % os.getpid()        # link beside the target, then swap in atomically
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    os.replace(tmp, library_path())
     with open(os.path.join(LIBDIR, "build.sha256"), "w") as fh:
         fh.write(_digest())
     return library_path()

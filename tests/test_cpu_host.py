@@ -247,3 +247,20 @@ def test_key_packing_order_and_ties():
     np.testing.assert_array_equal(ii, idx)
     np.testing.assert_array_equal(vv[[0, 1, 4, 5, 6, 8, 9]], v[[0, 1, 4, 5, 6, 8, 9]])
     assert (k > np.int64(-(1 << 63))).all()
+
+
+def test_built_library_stays_current_when_the_tree_moves(tmp_path):
+    """The snapshot that travels to a GPU box lives under another directory there: the staleness check must look at file
+    CONTENTS only (a library that looked stale was rebuilt by every rank of a job at once)."""
+    import shutil, subprocess, sys
+    from deepinpainting_b200 import build as _build
+    if not _build.is_current():
+        pytest.skip("library not built in this tree")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = tmp_path / "moved"
+    shutil.copytree(os.path.join(root, "deepinpainting_b200"), dst / "deepinpainting_b200",
+                    ignore=shutil.ignore_patterns("obj", "__pycache__"))
+    shutil.copytree(os.path.join(root, "include"), dst / "include")
+    out = subprocess.run([sys.executable, "-c", "import deepinpainting_b200.build as b; print(b.PKG); print(b.is_current())"],
+                         cwd=str(dst), capture_output=True, text=True, check=True).stdout.split()
+    assert out[0].startswith(str(dst)) and out[1] == "True", out
