@@ -398,7 +398,7 @@ def measure(args, B, C, H, K, W_, world, rank, local, dev, dist, pk, with_cpu, e
     # command line (profiles/), the source is named in the line
     traffic, traffic_src, tj_all = None, None, {}
     for fname, shape, pick in (("roofline_traffic.json", (WORKLOAD["B"], WORKLOAD["C"], WORKLOAD["H"]), "corr_tc"),
-                               ("roofline_traffic_configB.json", (64, 256, 64), "pass 1")):
+                               ("roofline_traffic_configB.json", (64, 256, 64), "corr_tc_kernel<1, 1,")):   # the single pass
         tpath = os.path.join(ROOT, "profiles", fname)
         if os.path.exists(tpath) and (B, C, H) == shape:
             with open(tpath) as fh:

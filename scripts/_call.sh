@@ -1,14 +1,10 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t25.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2_t25.log
-python bench.py > gpurun_out/r2_final_bench_g1.json 2> gpurun_out/r2_final_bench_g1.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_final_ref_g1.json 2> gpurun_out/r2_final_ref_g1.err; echo "ref rc=$?"
-python bench.py --workload patch3x3 --steps 40 > gpurun_out/r2_final_patch_g1.json 2> gpurun_out/r2_final_patch_g1.err; echo "patch rc=$?"
-python - <<'PY'
-import json
-for f in ['gpurun_out/r2_final_bench_g1.json','gpurun_out/r2_final_patch_g1.json','gpurun_out/r2_final_ref_g1.json']:
-    d=json.loads([l for l in open(f) if l.startswith('{')][-1])
-    print(f, d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'), (d.get('roofline') or {}).get('frac'))
-    a=d.get('also')
-    if a:
-        a=a[0] if isinstance(a,list) else a
-        print('   also', a['value'], a['ms_per_step'], a['roofline']['frac'], a['roofline']['kernel_ms'])
-PY
+set -x
+A="python bench.py --graphs 0 --steps 3 --warmup 3 --no-also --no-cpu-baseline --e2e-steps 8"
+B="python bench.py --graphs 0 --steps 3 --warmup 3 --no-also --no-cpu-baseline --e2e-steps 8 --batch 64 --size 64"
+$A > gpurun_out/r02_plainA.json 2> gpurun_out/r02_plainA.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_configA_eager.csv $A > gpurun_out/r02_ncuA.log 2>&1
+$B > gpurun_out/r02_plainB.json 2> gpurun_out/r02_plainB.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_configB_eager.csv $B > gpurun_out/r02_ncuB.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'corr_tc|prep_kernel|paste|shift_bwd|blend_s|recheck' -s 60 -c 10 -o gpurun_out/r02_full_B $B > gpurun_out/r02_ncu_fullB.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'corr_tc|prep_kernel|paste|shift_bwd|blend_s|recheck|build_exc' -s 60 -c 9 -o gpurun_out/r02_full_A $A > gpurun_out/r02_ncu_fullA.log 2>&1
+ls -la gpurun_out/r02_*

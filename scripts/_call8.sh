@@ -1,10 +1,10 @@
-python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2_tm8.log 2>&1; echo "multi rc=$?"; tail -n 3 gpurun_out/r2_tm8.log
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-$TR --master-port 29523 bench.py --gpus 8 --steps 500 > gpurun_out/r2_final_bench_g8.json 2> gpurun_out/r2_final_bench_g8.err; echo "bench8 rc=$?"
-$TR --master-port 29521 bench.py --gpus 8 --workload patch3x3 --shard bank --steps 40 > gpurun_out/r2_final_patch_g8.json 2> gpurun_out/r2_final_patch_g8.err; echo "patch8 rc=$?"
+python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2_tm2.log 2>&1; echo "multi rc=$?"; tail -n 3 gpurun_out/r2_tm2.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+$TR --master-port 29523 bench.py --gpus 2 --steps 300 --no-cpu-baseline > gpurun_out/r2_final_bench_g2.json 2> gpurun_out/r2_final_bench_g2.err; echo "bench2 rc=$?"
+$TR --master-port 29521 bench.py --gpus 2 --workload patch3x3 --shard bank --steps 40 > gpurun_out/r2_final_patch_g2.json 2> gpurun_out/r2_final_patch_g2.err; echo "patch2 rc=$?"
 python - <<'PY'
 import json
-for f in ['gpurun_out/r2_final_bench_g8.json','gpurun_out/r2_final_patch_g8.json']:
+for f in ['gpurun_out/r2_final_bench_g2.json','gpurun_out/r2_final_patch_g2.json']:
     try:
         d=json.loads([l for l in open(f) if l.startswith('{')][-1])
     except Exception as e:
