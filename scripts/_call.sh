@@ -1,10 +1,12 @@
-set -x
-A="python bench.py --graphs 0 --steps 3 --warmup 3 --no-also --no-cpu-baseline --e2e-steps 8"
-B="python bench.py --graphs 0 --steps 3 --warmup 3 --no-also --no-cpu-baseline --e2e-steps 8 --batch 64 --size 64"
-$A > gpurun_out/r02_plainA.json 2> gpurun_out/r02_plainA.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_configA_eager.csv $A > gpurun_out/r02_ncuA.log 2>&1
-$B > gpurun_out/r02_plainB.json 2> gpurun_out/r02_plainB.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_configB_eager.csv $B > gpurun_out/r02_ncuB.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'corr_tc|prep_kernel|paste|shift_bwd|blend_s|recheck' -s 60 -c 10 -o gpurun_out/r02_full_B $B > gpurun_out/r02_ncu_fullB.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'corr_tc|prep_kernel|paste|shift_bwd|blend_s|recheck|build_exc' -s 60 -c 9 -o gpurun_out/r02_full_A $A > gpurun_out/r02_ncu_fullA.log 2>&1
-ls -la gpurun_out/r02_*
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_ragged.py tests/test_gpu_dropin.py -m gpu -x -q > gpurun_out/r2_t27.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2_t27.log
+for v in new old new old; do
+cp deepinpainting_b200/lib/$v.so.bin deepinpainting_b200/lib/libipsr_sm100.so
+timeout 300 python bench.py --steps 500 --e2e-steps 20 --no-cpu-baseline > gpurun_out/x.json 2> gpurun_out/x.err
+python - <<PY
+import json
+d=json.loads([l for l in open('gpurun_out/x.json') if l.startswith('{')][-1])
+a=d.get('also'); a=a[0] if isinstance(a,list) else a
+print('$v: A %.4f ms corr %.4f | B %.4f ms corr %.4f' % (d['ms_per_step'], d['roofline']['kernel_ms'], a['ms_per_step'], a['roofline']['kernel_ms']))
+PY
+done
+python scripts/chaos_bwd.py 64 256 64 3
