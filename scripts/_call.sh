@@ -1,9 +1,3 @@
-for v in "IPSR_TC_DBG=0" "IPSR_TC_DBG=1" "IPSR_TC_DBG=2"; do
-env $v timeout 300 python bench.py --steps 200 --e2e-steps 20 --no-cpu-baseline > gpurun_out/x.json 2> gpurun_out/x.err
-python - <<PY
-import json
-d=json.loads([l for l in open('gpurun_out/x.json') if l.startswith('{')][-1])
-a=d.get('also'); a=a[0] if isinstance(a,list) else a
-print('$v: A corr %.4f | B corr %.4f' % (d['roofline']['kernel_ms'], a['roofline']['kernel_ms']))
-PY
+for v in "X=0" "IPSR_BWD_TILE_KB=16 IPSR_BWD_STAGES=2" "IPSR_BWD_TILE_KB=16 IPSR_BWD_STAGES=4" "IPSR_BWD_TILE_KB=8 IPSR_BWD_STAGES=4" "IPSR_BWD_LIGHT=32" "IPSR_BWD_LIGHT=48"; do
+echo "$v"; env $v python scripts/bwd_timing.py 16 256 32 2>&1 | tail -1
 done
