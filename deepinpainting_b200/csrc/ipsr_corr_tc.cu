@@ -94,13 +94,14 @@ __global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const
   const uint32_t a_base = base;
   const uint32_t ring_base = base + a_bytes;
   const uint32_t bar_base = ring_base + (uint32_t)prm.stages * kStageBytes;
-  // barriers: full[stages], empty[stages], a_full, tmem_full[2], tmem_empty[2]; then the TMEM address
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], a_full[KB] (one per 64-channel block of the resident
+  // row tile: the first MMAs start when ITS block has landed, not the whole tile); then the TMEM address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (prm.stages + s); };
-  const uint32_t a_full_bar = bar_base + 8u * (2 * prm.stages);
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * prm.stages + 1 + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * prm.stages + 3 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * prm.stages + 5);
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * prm.stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * prm.stages + 2 + s); };
+  auto a_full_bar = [&](int kb) { return bar_base + 8u * (2 * prm.stages + 4 + kb); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * prm.stages + 4 + (A_RESIDENT ? KB : 1));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), CL);             // one commit per CTA of the cluster
     }
-    mbar_init(a_full_bar, A_TMEM ? 4 : 1);     // the four epilogue warps | the producer's expect_tx
+    if (A_RESIDENT)                              // per block: one expect_tx arrival per copy | (TMEM row tile) the four loading warps
+      for (int kb = 0; kb < KB; ++kb) mbar_init(a_full_bar(kb), A_TMEM ? 4 : (uint32_t)(ROWT * AH));
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), kEpiWarps);     // one arrive per epilogue warp
@@ -154,14 +156,15 @@ __global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const
     const int nprod = prm.nprod;
     if (lane == 0 && nblk > 0 && pid < nprod) {
       if (A_RESIDENT && !A_TMEM) {
-        if (pid == 0) mbar_expect_tx(a_full_bar, a_bytes);
         int idx = 0;
-        for (int rt = 0; rt < ROWT; ++rt)
-          for (int kb = 0; kb < KB; ++kb)
+        for (int kb = 0; kb < KB; ++kb)                      // block 0 first: the MMAs of the first stage wait for it only
+          for (int rt = 0; rt < ROWT; ++rt)
             for (int hl = 0; hl < AH; ++hl, ++idx)
-              if (idx % nprod == pid)
+              if (idx % nprod == pid) {
+                mbar_expect_tx(a_full_bar(kb), kTileBytes);
                 bulk_g2s(a_base + (uint32_t)((rt * KB + kb) * AH + hl) * kTileBytes,
-                         prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg * ROWT + rt, KB, RB, prm.a_parts), kTileBytes, a_full_bar);
+                         prm.r_tiles + tile_offset_bytes_n(b, kb, hl, rbg * ROWT + rt, KB, RB, prm.a_parts), kTileBytes, a_full_bar(kb));
+              }
       }
       int it = 0;
       for (int blk = blk0; blk < blk1; ++blk) {
@@ -199,8 +202,8 @@ __global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && nblk > 0) {
       const uint32_t idesc = umma_idesc_f16(128, kBlockN);
-      if (A_RESIDENT) {
-        mbar_wait(a_full_bar, 0);
+      if (A_TMEM) {
+        mbar_wait(a_full_bar(0), 0);
         tc_fence_after();
       }
       int it = 0;
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const
           const int s = it % prm.stages;
           const uint32_t ph = (uint32_t)(it / prm.stages) & 1u;
           mbar_wait(full_bar(s), ph);
+          if (A_RESIDENT && !A_TMEM && j == 0) mbar_wait(a_full_bar(kb), 0);   // this block of the row tile has landed
           tc_fence_after();
           const uint32_t stage = ring_base + (uint32_t)s * kStageBytes;
           const uint32_t b_hi = stage + (A_RESIDENT ? 0u : (uint32_t)AH * kTileBytes);
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full_bar);
+      if (lane == 0) mbar_arrive(a_full_bar(0));
     }
     float best = -INFINITY, second = -INFINITY, third = -INFINITY;
     int bidx = prm.col_begin + blk0 * kBlockN, sidx = bidx;
