@@ -1,10 +1,9 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_patches.py -m gpu -x -q > gpurun_out/r2_t28.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2_t28.log
-for i in 1 2; do
-timeout 300 python bench.py --steps 300 --e2e-steps 20 --no-cpu-baseline > gpurun_out/x.json 2> gpurun_out/x.err
-python - <<PY
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t29.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2_t29.log
+python bench.py > gpurun_out/r2_final_bench_g1.json 2> gpurun_out/r2_final_bench_g1.err; echo "bench rc=$?"
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python - <<'PY'
 import json
-d=json.loads([l for l in open('gpurun_out/x.json') if l.startswith('{')][-1])
-a=d.get('also'); a=a[0] if isinstance(a,list) else a
-print('A %.4f ms corr %.4f | B %.4f ms corr %.4f' % (d['ms_per_step'], d['roofline']['kernel_ms'], a['ms_per_step'], a['roofline']['kernel_ms']))
+d=json.loads([l for l in open('gpurun_out/r2_final_bench_g1.json') if l.startswith('{')][-1])
+a=d['also']; a=a[0] if isinstance(a,list) else a
+print('A %.0f img/s %.4f ms e2e %.0f frac %.3f | B %.0f img/s %.4f ms frac %.3f traffic %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], a['value'], a['ms_per_step'], a['roofline']['frac'], a['roofline']['traffic']))
 PY
-done
