@@ -431,6 +431,232 @@ __global__ void __launch_bounds__(160 + 128 * ROWT * ES, 1) corr_tc_kernel(const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The single pass, PERSISTENT: one CTA pair per SM pair walks its share of the (image, row-tile pair, column split) items.
+// Inside its MMA loop the one-item kernel above already runs at the tensor pipe's sustained rate (one 128 x 256 x 16 MMA
+// per ~181 cycles); what it loses is per CTA -- launch, barrier / TMEM set-up, the row tile that must land before the first
+// MMA, the epilogue of the last block, 14 times per SM at 64 x 64 x 256 (batch 64).  Here
+//   * barriers, TMEM and the cluster handshake are set up once;
+//   * the row tile of the NEXT item replaces the current one block by block: its 64-channel block kb is fetched as soon as
+//     the last MMAs that read block kb of the current tile have retired (the producer learns that from the ring slot it is
+//     about to refill) and lands while the current item's remaining stages run -- one A buffer, the ring keeps its depth;
+//   * the epilogue of an item's last block overlaps the first MMAs of the next item (the accumulators keep alternating).
+// ROWT = 1, BN = 256, CTA pairs (multicast bank tiles), two epilogue warps per TMEM lane quadrant; writes the per-split
+// partial results (ipsr_finalize_argmax merges them).  352 threads: warp 0 / warp 10 producers, warp 1 MMA, warps 2..9 epilogue.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(352, 1) corr_tc_p1_persistent_kernel(const TcParams prm, int nitems) {
+  constexpr int kBN = 256, ES = 2;
+  constexpr uint32_t kStageBytes = 2u * kTileBytes;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  pdl_trigger();
+  pdl_wait();
+  const int KB = prm.KB, RB = prm.RB, stages = prm.stages;
+  const uint32_t a_base = base;
+  const uint32_t ring_base = base + (uint32_t)KB * kTileBytes;
+  const uint32_t bar_base = ring_base + (uint32_t)stages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * stages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * stages + 2 + s); };
+  auto a_full_bar = [&](int kb) { return bar_base + 8u * (2 * stages + 4 + kb); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4 + KB);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+  float* mrg_all = reinterpret_cast<float*>(smem + (tmem_slot + 16u - base));        // [128][3] hand-over of the upper-half warps
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int cl = (int)(blockIdx.x >> 1), ncl = (int)(gridDim.x >> 1);
+  const int RBGc = RB / 2;
+  const int per = (prm.blocks_total + prm.psplit - 1) / prm.psplit;
+  struct Item { int b, rbg, split, blk0, nblk; };
+  auto decode = [&](int item) {
+    Item w;
+    int t = item;
+    w.split = t % prm.psplit; t /= prm.psplit;
+    w.b = t / RBGc;
+    w.rbg = (t % RBGc) * 2 + (int)crank;
+    w.blk0 = w.split * per;
+    w.nblk = max(0, min(prm.blocks_total, w.blk0 + per) - w.blk0);
+    return w;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 2);              // one commit per CTA of the pair
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4 * ES);
+    }
+    for (int kb = 0; kb < KB; ++kb) mbar_init(a_full_bar(kb), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  cluster_sync_all();
+
+  if (warp == 0 || warp == 10) {
+    // ------------------------------------------------------------------ producers (alternate stages)
+    const int pid = warp == 0 ? 0 : 1;
+    if (lane == 0 && cl < nitems) {
+      auto load_a = [&](const Item& w, int kb) {
+        mbar_expect_tx(a_full_bar(kb), kTileBytes);
+        bulk_g2s(a_base + (uint32_t)kb * kTileBytes, prm.r_tiles + tile_offset_bytes_n(w.b, kb, 0, w.rbg, KB, RB, prm.a_parts), kTileBytes,
+                 a_full_bar(kb));
+      };
+      {
+        const Item w0 = decode(cl);
+        for (int kb = pid; kb < KB; kb += 2) load_a(w0, kb);
+      }
+      long long it = 0;
+      // reload_at[kb]: the ring index whose slot was last used by (previous item, last block, kb): once that slot is free
+      // again the MMAs that read block kb of the previous row tile have retired
+      long long reload_at[16];
+      Item reload_item[16];
+      for (int kb = 0; kb < KB; ++kb) reload_at[kb] = -1;
+      for (int item = cl; item < nitems; item += ncl) {
+        const Item w = decode(item);
+        const bool has_next = item + ncl < nitems;
+        const Item nxt = has_next ? decode(item + ncl) : w;
+        for (int j = 0; j < w.nblk; ++j) {
+          const int cb = (prm.col_begin >> 7) + (w.blk0 + j) * 2;
+          for (int kb = 0; kb < KB; ++kb, ++it) {
+            const bool mine = (it % 2) == pid;           // (both producers keep the whole schedule; each acts on its own indices)
+            if (mine) {
+              const int s = (int)(it % stages);
+              const uint32_t ph = (uint32_t)(it / stages) & 1u;
+              mbar_wait(empty_bar(s), ph ^ 1u);
+              for (int k2 = 0; k2 < KB; ++k2)
+                if (reload_at[k2] == it) load_a(reload_item[k2], k2);
+              mbar_expect_tx(full_bar(s), kStageBytes);
+              bulk_g2s_multicast(ring_base + (uint32_t)s * kStageBytes + crank * kTileBytes,
+                                 prm.x_tiles + tile_offset_bytes(w.b, kb, 0, cb + (int)crank, KB, RB), kTileBytes, full_bar(s), (uint16_t)0x3);
+            }
+            if (j == w.nblk - 1 && has_next) {     // this index holds (item, last block, kb): its slot comes free at it + stages
+              reload_at[kb] = it + stages;
+              reload_item[kb] = nxt;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && cl < nitems) {
+      const uint32_t idesc = umma_idesc_f16(128, kBN);
+      long long it = 0;
+      int jt = 0, n = 0;
+      for (int item = cl; item < nitems; item += ncl, ++n) {
+        const Item w = decode(item);
+        for (int j = 0; j < w.nblk; ++j, ++jt) {
+          const int as = jt & 1;
+          mbar_wait(tempty_bar(as), ((uint32_t)(jt >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int s = (int)(it % stages);
+            mbar_wait(full_bar(s), (uint32_t)(it / stages) & 1u);
+            if (j == 0) mbar_wait(a_full_bar(kb), (uint32_t)n & 1u);     // block kb of THIS item's row tile has landed
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBN);
+            const uint64_t da = umma_desc_k_sw128(a_base + (uint32_t)kb * kTileBytes);
+            const uint64_t db = umma_desc_k_sw128(ring_base + (uint32_t)s * kStageBytes);
+#pragma unroll
+            for (int k = 0; k < kTileK / 16; ++k)
+              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_multicast(empty_bar(s), (uint16_t)0x3);
+          }
+          umma_commit(tfull_bar(as));
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ epilogue (thread == row, two warps per lane quadrant)
+    const int half = ((warp - 2) >> 2) % ES;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    float* mrg = mrg_all + (size_t)row * 3;
+    int jt = 0;
+    for (int item = cl; item < nitems; item += ncl) {
+      const Item w = decode(item);
+      const int q = w.rbg * kTileRows + row;
+      float best = -INFINITY, second = -INFINITY;
+      int bidx = prm.col_begin + w.blk0 * kBN;
+      for (int j = 0; j < w.nblk; ++j, ++jt) {
+        const int as = jt & 1;
+        mbar_wait(tfull_bar(as), (uint32_t)(jt >> 1) & 1u);
+        tc_fence_after();
+        const int colb = prm.col_begin + (w.blk0 + j) * kBN;
+        uint32_t rbuf[2][32];
+        constexpr int kChunks = kBN / 32 / ES;
+        const uint32_t tsrc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kBN + half * kChunks * 32);
+        tmem_ld32(tsrc, rbuf[0]);
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          uint32_t (&r)[32] = rbuf[ch & 1];
+          tmem_ld_wait();
+          if (ch + 1 < kChunks) {
+            tmem_ld32(tsrc + (uint32_t)((ch + 1) * 32), rbuf[(ch + 1) & 1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+          }
+          const int c0 = colb + (half * kChunks + ch) * 32;
+          if (c0 + 32 > prm.n_valid) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e >= prm.n_valid) r[e] = 0xFF800000u;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float v = __uint_as_float(r[e]);
+            const bool gt = v > best;                     // strict: the lowest column wins ties
+            second = gt ? best : fmaxf(second, v);
+            bidx = gt ? (c0 + e) : bidx;
+            best = gt ? v : best;
+          }
+        }
+      }
+      // hand-over of the upper-half warp, then the row's partial result of this item
+      if (half == 1) {
+        mrg[0] = best; mrg[1] = __int_as_float(bidx); mrg[2] = second;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (half == 0) {
+        if (w.nblk > 0) {
+          const float b2 = mrg[0], s2 = mrg[2];
+          const int i2 = __float_as_int(mrg[1]);
+          if (b2 > best || (b2 == best && i2 < bidx)) {
+            second = fmaxf(best, s2); best = b2; bidx = i2;
+          } else {
+            second = fmaxf(second, b2);
+          }
+        }
+        const size_t o = ((size_t)w.split * prm.B + w.b) * prm.N + q;
+        prm.part_best[o] = best;
+        prm.part_idx[o] = bidx;
+        prm.part_second[o] = second;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");       // the hand-over buffer is free for the next item
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // Merge the per-split triples (scores in scaled units; true score = scaled * rscale[q] > 0 scaling) and decide
 // which rows can be trusted.
 //   rows: list_in == NULL: row index = q; else row index r < nlist_in[b] is position q = list_in[b][r]
@@ -717,6 +943,54 @@ int ipsr::correlate_argmax_tc_ex(const void* r_tiles, const void* x_tiles, int B
   }
   if (s_dump == nullptr && tc_pass1_wide(B, C, N, col_begin, col_end, psplit)) {
     prm.blocks_total = (col_end - col_begin) / 256;
+    {
+      // persistent variant (IPSR_TC_PERSIST=0 turns it off): CTA pairs walk the items; needs whole pairs, several items
+      // per pair and items long enough for the rolling reload of the row tile
+      // (read per call: 0 = never, 1 = when every pair gets >= 4 items, 2 = whenever legal -- tests)
+      const char* pe = getenv("IPSR_TC_PERSIST");
+      const int env_persist = pe ? atoi(pe) : 1;
+      const int KB = C / kTileK;
+      const long long items = (long long)B * (prm.RB / 2) * psplit;
+      const int per = prm.blocks_total / psplit;
+      int stages = 0;
+      size_t smem = 0;
+      for (int sg = 8; sg >= 3; --sg) {
+        const size_t need = 1024 + (size_t)KB * kTileBytes + (size_t)sg * 2 * kTileBytes + (size_t)(2 * sg + 4 + KB) * 8 + 16 + 1536;
+        if (need <= 227 * 1024) { stages = sg; smem = need; break; }
+      }
+      if (env_persist && row_limit == nullptr && prm.RB % 2 == 0 && KB <= 16 && stages >= 3 && (items >= 4 * 74 || env_persist == 2) &&
+          (long long)per * KB >= stages + KB && items <= 0x7FFFFFFF) {
+        prm.stages = stages;
+        prm.nprod = 2;
+        cudaError_t e = cudaFuncSetAttribute(corr_tc_p1_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "corr_tc persistent smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(148);
+        cfg.blockDim = dim3(352);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        // as many CTA pairs as can be resident at once (GPCs with an odd SM count leave SMs without a partner)
+        int nclusters = 0;
+        e = cudaOccupancyMaxActiveClusters(&nclusters, corr_tc_p1_persistent_kernel, &cfg);
+        IPSR_REQUIRE(e == cudaSuccess && nclusters > 0, IPSR_ERR_CUDA, "corr_tc persistent occupancy query: %s", cudaGetErrorString(e));
+        if (getenv("IPSR_TC_PERSIST_VERBOSE")) fprintf(stderr, "ipsr: persistent single pass: %d CTA pairs resident, %lld items\n", nclusters, items);
+        if ((long long)nclusters > items) nclusters = (int)items;
+        cfg.gridDim = dim3(2 * nclusters);
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        e = cudaLaunchKernelEx(&cfg, corr_tc_p1_persistent_kernel, prm, (int)items);
+        IPSR_REQUIRE(e == cudaSuccess, IPSR_ERR_CUDA, "ipsr_correlate_argmax_tc: launch failed: %s", cudaGetErrorString(e));
+        return check_launch("ipsr_correlate_argmax_tc");
+      }
+    }
     const long long ctas1 = (long long)B * prm.RB * psplit;
     IPSR_REQUIRE(ctas1 <= 0x7FFFFFFFll, IPSR_ERR_UNSUPPORTED, "ipsr_correlate_argmax_tc: grid too large");
     return (prm.RB % 2 == 0) ? launch_tc<1, 1, true, 2, 256>(prm, C, ctas1, st) : launch_tc<1, 1, true, 1, 256>(prm, C, ctas1, st);
