@@ -1,13 +1,8 @@
-for v in "IPSR_TC_PERSIST=1 IPSR_TC_PERSIST_VERBOSE=1" "IPSR_TC_PERSIST=0" "IPSR_TC_PERSIST=1" "IPSR_TC_PERSIST=0"; do
-env $v timeout 300 python bench.py --batch 64 --size 64 --steps 200 --e2e-steps 20 --no-cpu-baseline --no-also > gpurun_out/x.json 2> gpurun_out/x.err
-python - <<PY
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t31.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2_t31.log
+python bench.py > gpurun_out/r2_final_bench_g1.json 2> gpurun_out/r2_final_bench_g1.err; echo "bench rc=$?"
+python - <<'PY'
 import json
-try:
-    d=json.loads([l for l in open('gpurun_out/x.json') if l.startswith('{')][-1])
-    print('$v: B %.4f ms corr %.4f frac %.3f' % (d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac']))
-except Exception as e:
-    print('$v failed', e)
+d=json.loads([l for l in open('gpurun_out/r2_final_bench_g1.json') if l.startswith('{')][-1])
+a=d['also']; a=a[0] if isinstance(a,list) else a
+print('A %.0f img/s %.4f ms e2e %.0f frac %.3f | B %.0f img/s %.4f ms frac %.3f corr %.4f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], a['value'], a['ms_per_step'], a['roofline']['frac'], a['roofline']['kernel_ms']))
 PY
-grep "ipsr: persistent" gpurun_out/x.err | head -1
-done
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "persistent" 2>&1 | tail -2
